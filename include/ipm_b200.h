@@ -1,0 +1,141 @@
+/*
+ * ipm_b200.h — C ABI of the B200-native Newton-step hot path.
+ *
+ * Drop-in boundary for the predictor-corrector interior-point LP solver
+ * payakorn/InteriorPointMethod.  The reference has no FFI of its own: its seams are the
+ * plain Python functions of `main.py` listed beside each entry point below (file:line are
+ * into the reference tree).  The reference-side binding a maintainer would add (a ctypes
+ * stub that rebinds those names) is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative IPM_ERR_* code; nothing throws
+ *     across the ABI.  Numerical breakdown is reported through `status`, never as an
+ *     error (the reference returns NaN, it does not raise: main.py:180, 780, 812).
+ *   - all pointers are HOST pointers unless the name ends in `_d` (device pointers in
+ *     the handle's device).  Host buffers are borrowed for the duration of the call.
+ *   - all reals are IEEE float64, all indices int32; matrices are ROW-major.
+ *   - a handle binds one GPU and one stream and is not thread-safe; distinct handles
+ *     may be used from distinct threads.
+ *   - there is no CPU fallback: without a usable CUDA device ipm_create fails with
+ *     IPM_ERR_CUDA.
+ */
+#ifndef IPM_B200_H
+#define IPM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ipm_handle ipm_handle;
+
+enum {
+    IPM_OK = 0,
+    IPM_ERR_CUDA = -1,      /* CUDA runtime failure; text in ipm_last_error */
+    IPM_ERR_ARG = -2,       /* null pointer / bad enum */
+    IPM_ERR_SHAPE = -3,     /* inconsistent m, n, nnz, lda, indices out of range */
+    IPM_ERR_STATE = -4,     /* call order violated (e.g. ipm_direction before ipm_factor) */
+    IPM_ERR_NOMEM = -5
+};
+
+/* status values written by the solve-level calls (reference behaviour in parentheses) */
+enum {
+    IPM_STATUS_CONVERGED = 0,   /* check_optimality turned False (main.py:169-173) */
+    IPM_STATUS_MAX_ITER = 1,    /* hit the cap: 5000 in interior_sparse (main.py:780), 50000 in interior (main.py:725) */
+    IPM_STATUS_NAN = 2          /* a non-finite iterate: the reference loop exits because every
+                                   comparison with NaN is False (main.py:170-173, 780) */
+};
+
+/* ---------------------------------------------------------------- lifetime */
+int  ipm_create(ipm_handle **h, int device_ordinal);
+void ipm_destroy(ipm_handle *h);
+const char *ipm_last_error(const ipm_handle *h);   /* h may be NULL: last error of a failed ipm_create / batched call */
+const char *ipm_version(void);
+
+/* Kernels launched by this library in this process since load (bench.py "gpu_launches"). */
+int64_t ipm_launch_count(void);
+
+/* ---------------------------------------------------------------- problem data
+ * Replaces what create_problem_from_mps hands to the drivers (sparse_interior.py:211-216):
+ * A (scipy CSC there; CSR here — the Python shim converts), b (m), c (n).
+ * The symbolic pattern of M = A A^T is built once here. */
+int ipm_load_csr(ipm_handle *h, int m, int n, int64_t nnz,
+                 const int32_t *rowptr, const int32_t *colind, const double *val,
+                 const double *b, const double *c);
+/* Dense A, row-major with leading dimension lda >= n (the `interior` caller, main.py:707-757). */
+int ipm_load_dense(ipm_handle *h, int m, int n, const double *A, int64_t lda,
+                   const double *b, const double *c);
+/* Dense A already resident in this handle's device (borrowed, must outlive the handle's use). */
+int ipm_load_dense_d(ipm_handle *h, int m, int n, const double *A_d, int64_t lda,
+                     const double *b_d, const double *c_d);
+
+/* ---------------------------------------------------------------- iterate */
+/* x = s = 1; y = 1 (initial_vector_sparse, sparse_interior.py:193-200) or y = 0 (initial_vector, main.py:287-302). */
+int ipm_init_state(ipm_handle *h, int y0_is_one);
+int ipm_set_state(ipm_handle *h, const double *x, const double *y, const double *s);
+int ipm_get_state(ipm_handle *h, double *x, double *y, double *s);
+
+/* ---------------------------------------------------------------- op level (parity tests mirror the Python seams) */
+/* out = { |A x - b|_2, |A^T y + s - c|_2, x^T s, |b|_2, |c|_2 } — the quantities check_optimality
+ * compares (main.py:169-172).  Also refreshes the residual vectors rb, rc kept in the handle. */
+int ipm_residual_norms(ipm_handle *h, double out[5]);
+int ipm_get_residuals(ipm_handle *h, double *rb, double *rc);
+/* M = A diag(x/s) A^T (main.py:223-224): SpGEMM (CSR input) or DMMA SYRK (dense input). */
+int ipm_assemble_normal(ipm_handle *h);
+/* Debug/parity: full m x m row-major copy; lower triangle is meaningful (M before ipm_factor, L after). */
+int ipm_get_M(ipm_handle *h, double *M_rowmajor);
+/* Safeguarded blocked Cholesky of M in place, replacing solve_linear (main.py:176-182):
+ * pivot <= pivot_rel_thresh * max diag(M) (or NaN) -> 1e128. */
+int ipm_factor(ipm_handle *h, double pivot_rel_thresh, int *n_fixed);
+/* kind 0: predictor, rhs [-rc;-rb;-x*s]         (direction_predicted_sparse, main.py:197-229)
+ * kind 1: corrector, rhs [-rc;-rb;-(x*s+dxa*dsa-sigma*mu)] using the predictor direction and the
+ *         sigma, mu stored by ipm_sigma           (direction_corrected_sparse, main.py:247-277; create_rhs_corrected main.py:142-159)
+ * Needs ipm_residual_norms + ipm_assemble_normal + ipm_factor for the current iterate.
+ * dx, dy, ds may be NULL (results stay on the device). */
+int ipm_direction(ipm_handle *h, int kind, double *dx, double *dy, double *ds);
+/* kind 0: predicted_stepsize (main.py:305-322) on the predictor direction, eta ignored.
+ * kind 1: full_stepsize (main.py:604-626) on the corrector direction: min(1, eta*min(...)).
+ * alpha = { alpha_primal, alpha_dual }. */
+int ipm_ratio_test(ipm_handle *h, int kind, double eta, double alpha[2]);
+/* out = { mu_aff, mu, sigma } (duality_gap, main.py:588-601; predicted, main.py:562-585). */
+int ipm_sigma(ipm_handle *h, double out[3]);
+/* x += alpha_p dx; y += alpha_d dy; s += alpha_d ds with the corrector direction (corrected, main.py:694-696). */
+int ipm_update(ipm_handle *h, double alpha_p, double alpha_d);
+
+/* ---------------------------------------------------------------- solve level
+ * Whole predictor-corrector loop on the device (interior_sparse main.py:760-815 when the problem
+ * was loaded with ipm_load_csr, interior main.py:707-757 when loaded dense).  Starts from
+ * ipm_init_state(y0_is_one).  e1 = e2 = e3 = tol as in both drivers.
+ * Outputs (each may be NULL): x (n), y (m), s (n), obj = c^T x (the caller subtracts cTlb),
+ * iters, status, resid = { |rb|, |rc|, x^T s, |b|, |c| } at exit. */
+int ipm_solve(ipm_handle *h, double tol, int max_iter, int y0_is_one,
+              double *x, double *y, double *s, double *obj, int *iters, int *status, double resid[5]);
+
+/* Batch of B independent dense LPs of one shape, contiguous A[B][m][n], b[B][m], c[B][n].
+ * HOST buffers: the call stages chunks host->device on a copy stream overlapped with the solve
+ * of the previous chunk.  x (B*n) may be NULL.  Start y = 0 (dense driver convention). */
+int ipm_solve_batched_dense(int device_ordinal, int B, int m, int n,
+                            const double *A, const double *b, const double *c,
+                            double tol, int max_iter,
+                            double *obj, int *iters, int *status, double *x);
+/* Same with everything resident on `device_ordinal`; stream 0 of that device; synchronises before return.
+ * work_d: scratch of ipm_batched_workspace_bytes(B,m,n) bytes or NULL (allocated internally). */
+int ipm_solve_batched_dense_d(int device_ordinal, int B, int m, int n,
+                              const double *A_d, const double *b_d, const double *c_d,
+                              double tol, int max_iter,
+                              double *obj_d, int *iters_d, int *status_d, double *x_d,
+                              void *work_d, int *iterations_run);
+int64_t ipm_batched_workspace_bytes(int B, int m, int n);
+
+/* ---------------------------------------------------------------- stand-alone kernels (roofline benches, parity)
+ * C_lower = A diag(d) A^T for a dense row-major device matrix (the SYRK of main.py:224). */
+int ipm_syrk_d(int device_ordinal, int m, int n, const double *A_d, int64_t lda, const double *d_d,
+               double *M_d, int64_t ldm);
+/* In-place safeguarded Cholesky of a dense row-major device matrix (lower). */
+int ipm_potrf_d(int device_ordinal, int m, double *M_d, int64_t ldm, double pivot_rel_thresh, int *n_fixed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IPM_B200_H */
