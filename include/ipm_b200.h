@@ -56,6 +56,9 @@ const char *ipm_version(void);
 /* Kernels launched by this library in this process since load (bench.py "gpu_launches"). */
 int64_t ipm_launch_count(void);
 
+/* Relative pivot threshold of the safeguarded Cholesky used by ipm_solve (default 1e-30). */
+int ipm_set_pivot_threshold(ipm_handle *h, double pivot_rel_thresh);
+
 /* ---------------------------------------------------------------- problem data
  * Replaces what create_problem_from_mps hands to the drivers (sparse_interior.py:211-216):
  * A (scipy CSC there; CSR here — the Python shim converts), b (m), c (n).

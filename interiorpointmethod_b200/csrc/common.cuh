@@ -68,6 +68,8 @@ enum Scal {
     S_NRC,          // |rc|
     S_CONT,         // 1.0 = continue, 0.0 = stop
     S_NFIXED,       // pivots replaced in the last factorisation
+    S_RAW_P,        // min({-x/dx : dx<0} U {1}) of the last direction
+    S_RAW_D,        // min({-s/ds : ds<0} U {1}) of the last direction
     S_COUNT = 24
 };
 

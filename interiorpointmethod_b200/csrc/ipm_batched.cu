@@ -1,0 +1,546 @@
+// C ABI, batched part: B independent dense LPs of one shape solved in lockstep on one GPU
+// (BASELINE.json config "batch of 8192 synthetic dense LPs m=256, n=512").  Every kernel takes the LP index
+// from the grid and skips LPs whose `active` flag is 0, so LPs that converge early stop costing anything.
+//
+// One predictor-corrector iteration (main.py:725-751, normal-equations elimination main.py:221-229) is
+//   kb_residual            one pass over A: A x, A^T y, rb, rc, d, norms, continue flag     (main.py:67-70,169-173)
+//   dmma_nt_kernel         M = A diag(d) A^T, lower tiles, FP64 tensor pipe                 (main.py:224)
+//   potrf_blocked<64>      safeguarded Cholesky, all LPs per launch                         (main.py:176-182)
+//   kb_rhs(0), trsv, kb_dir(0)   predictor: rhs, solves, dx/ds, ratio test, mu_aff, sigma   (main.py:225-228,305-322,588-601)
+//   kb_rhs(1), trsv, kb_dir(1)   corrector: same with r4, eta = 0.91, update of x, y, s     (main.py:142-159,604-626,694-696)
+// = 6 passes over A per iteration, everything else is O(n) or lives in L2.
+#include <cmath>
+#include <vector>
+
+#include "chol.cuh"
+#include "common.cuh"
+#include "dmma_gemm.cuh"
+
+using namespace ipm;
+
+namespace {
+
+constexpr int KB_NT = 512;
+constexpr int KB_NW = KB_NT / 32;
+
+struct BatchArgs {
+    const double* A;   // [B][m][n]
+    const double* b;   // [B][m]
+    const double* c;   // [B][n]
+    double *x, *s, *rc, *d, *w, *rcx, *dxa, *dsa;      // [B][n]
+    double *y, *rb, *dy, *rhs;                         // [B][m]
+    double* scal;      // [B][S_COUNT]
+    int* active;       // [B]
+    int* iters;        // [B]
+    unsigned* n_active;
+    int m, n;
+    double tol, eta;
+    int max_iter;
+};
+
+// ---------------------------------------------------------------------------------------------
+// One pass over A_i: Ax (warp per row) and A^T y (column partial sums per warp, combined in warp order).
+template <int NPL>
+__global__ void __launch_bounds__(KB_NT) kb_residual(const BatchArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    double* colred = smem;                 // [KB_NW][n]
+    __shared__ double sh[32];
+    __shared__ double s_nrb2;
+    const int lp = blockIdx.x;
+    if (a.active[lp] == 0) return;
+    const int m = a.m, n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double* A = a.A + (size_t)lp * m * n;
+    const double* x = a.x + (size_t)lp * n;
+    const double* s = a.s + (size_t)lp * n;
+    const double* c = a.c + (size_t)lp * n;
+    const double* y = a.y + (size_t)lp * m;
+    const double* b = a.b + (size_t)lp * m;
+    double* rb = a.rb + (size_t)lp * m;
+    double* rc = a.rc + (size_t)lp * n;
+    double* d = a.d + (size_t)lp * n;
+    double* scal = a.scal + (size_t)lp * S_COUNT;
+    const int n2 = n >> 1;
+
+    double2 xr[NPL], ca[NPL];
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+        const int c2 = j * 32 + lane;
+        xr[j] = (c2 < n2) ? reinterpret_cast<const double2*>(x)[c2] : make_double2(0.0, 0.0);
+        ca[j] = make_double2(0.0, 0.0);
+    }
+    double nrb2 = 0.0;
+    for (int r = warp; r < m; r += KB_NW) {
+        const double2* row = reinterpret_cast<const double2*>(A + (size_t)r * n);
+        const double yr = y[r];
+        double dot0 = 0.0, dot1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+            const int c2 = j * 32 + lane;
+            if (c2 < n2) {
+                const double2 v = row[c2];
+                dot0 += v.x * xr[j].x;
+                dot1 += v.y * xr[j].y;
+                ca[j].x += v.x * yr;
+                ca[j].y += v.y * yr;
+            }
+        }
+        const double dot = warp_sum(dot0 + dot1);
+        if (lane == 0) {
+            const double r_b = dot - b[r];
+            rb[r] = r_b;
+            nrb2 += r_b * r_b;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+        const int c2 = j * 32 + lane;
+        if (c2 < n2) reinterpret_cast<double2*>(colred + (size_t)warp * n)[c2] = ca[j];
+    }
+    __syncthreads();
+    double nrc2 = 0.0, xs = 0.0, obj = 0.0;
+    for (int k = tid; k < n; k += KB_NT) {
+        double aty = 0.0;
+#pragma unroll
+        for (int w = 0; w < KB_NW; ++w) aty += colred[(size_t)w * n + k];
+        const double xi = x[k], si = s[k], ci = c[k];
+        const double r = aty + si - ci;
+        rc[k] = r;
+        d[k] = xi / si;
+        nrc2 += r * r;
+        xs += xi * si;
+        obj += xi * ci;
+    }
+    nrb2 = block_red<RED_SUM>(nrb2, sh);
+    if (tid == 0) s_nrb2 = nrb2;
+    nrc2 = block_red<RED_SUM>(nrc2, sh);
+    xs = block_red<RED_SUM>(xs, sh);
+    obj = block_red<RED_SUM>(obj, sh);
+    if (tid == 0) {
+        const double nrb = sqrt(s_nrb2), nrc = sqrt(nrc2);
+        scal[S_NRB2] = s_nrb2; scal[S_NRB] = nrb; scal[S_NRC2] = nrc2; scal[S_NRC] = nrc;
+        scal[S_XS] = xs; scal[S_OBJ] = obj;
+        const bool cont = (a.tol * (1.0 + scal[S_NB]) < nrb) || (a.tol * (1.0 + scal[S_NC]) < nrc) || (a.tol < xs);
+        scal[S_CONT] = cont ? 1.0 : 0.0;
+        const bool go = cont && a.iters[lp] < a.max_iter;
+        if (go) atomicAdd(a.n_active, 1u);
+        else a.active[lp] = 0;
+    }
+}
+
+// |b|, |c| per LP (once per solve) and state initialisation x = s = 1, y = 0 (main.py:287-302)
+__global__ void __launch_bounds__(256) kb_init(const BatchArgs a) {
+    __shared__ double sh[32];
+    const int lp = blockIdx.x, tid = threadIdx.x;
+    const int m = a.m, n = a.n;
+    double nb = 0.0, nc = 0.0;
+    for (int i = tid; i < m; i += blockDim.x) {
+        const double v = a.b[(size_t)lp * m + i];
+        nb += v * v;
+        a.y[(size_t)lp * m + i] = 0.0;
+    }
+    for (int i = tid; i < n; i += blockDim.x) {
+        const double v = a.c[(size_t)lp * n + i];
+        nc += v * v;
+        a.x[(size_t)lp * n + i] = 1.0;
+        a.s[(size_t)lp * n + i] = 1.0;
+    }
+    nb = block_red<RED_SUM>(nb, sh);
+    nc = block_red<RED_SUM>(nc, sh);
+    if (tid == 0) {
+        double* scal = a.scal + (size_t)lp * S_COUNT;
+        for (int i = 0; i < S_COUNT; ++i) scal[i] = 0.0;
+        scal[S_NB] = sqrt(nb);
+        scal[S_NC] = sqrt(nc);
+        a.active[lp] = 1;
+        a.iters[lp] = 0;
+    }
+}
+
+// rcx = rcomp/x, w = d (rc - rcx), rhs = -rb - A w      (main.py:72, 150-152, 225)
+template <int NPL>
+__global__ void __launch_bounds__(KB_NT) kb_rhs(const BatchArgs a, int kind) {
+    extern __shared__ __align__(16) double smem[];
+    double* ws = smem;     // [n]
+    const int lp = blockIdx.x;
+    if (a.active[lp] == 0) return;
+    const int m = a.m, n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double* A = a.A + (size_t)lp * m * n;
+    const size_t on = (size_t)lp * n, om = (size_t)lp * m;
+    const double sigma_mu = kind ? a.scal[(size_t)lp * S_COUNT + S_SIGMA_MU] : 0.0;
+    for (int k = tid; k < n; k += KB_NT) {
+        const double xi = a.x[on + k];
+        double rcomp = xi * a.s[on + k];
+        if (kind) rcomp = rcomp + a.dxa[on + k] * a.dsa[on + k] - sigma_mu;
+        const double q = rcomp / xi;
+        const double wv = a.d[on + k] * (a.rc[on + k] - q);
+        a.rcx[on + k] = q;
+        a.w[on + k] = wv;
+        ws[k] = wv;
+    }
+    __syncthreads();
+    const int n2 = n >> 1;
+    double2 wr[NPL];
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+        const int c2 = j * 32 + lane;
+        wr[j] = (c2 < n2) ? reinterpret_cast<const double2*>(ws)[c2] : make_double2(0.0, 0.0);
+    }
+    for (int r = warp; r < m; r += KB_NW) {
+        const double2* row = reinterpret_cast<const double2*>(A + (size_t)r * n);
+        double dot0 = 0.0, dot1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+            const int c2 = j * 32 + lane;
+            if (c2 < n2) {
+                const double2 v = row[c2];
+                dot0 += v.x * wr[j].x;
+                dot1 += v.y * wr[j].y;
+            }
+        }
+        const double dot = warp_sum(dot0 + dot1);
+        if (lane == 0) a.rhs[om + r] = -a.rb[om + r] - dot;
+    }
+}
+
+// u = A^T dy; dx = d u + w; ds = -s dx/x - rcx; ratio test; then
+//   kind 0: mu_aff, mu, sigma (main.py:582-600), predictor direction stored for the corrector rhs
+//   kind 1: alpha = min(1, eta*min) (main.py:616-623), x += ap dx, y += ad dy, s += ad ds (main.py:694-696)
+// dy is read from a.rhs (the batched triangular solve works in place).
+template <int NPL>
+__global__ void __launch_bounds__(KB_NT) kb_dir(const BatchArgs a, int kind) {
+    extern __shared__ __align__(16) double smem[];
+    double* colred = smem;     // [KB_NW][n]
+    __shared__ double sh[32];
+    __shared__ double s_alpha[2];
+    const int lp = blockIdx.x;
+    if (a.active[lp] == 0) return;
+    const int m = a.m, n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double* A = a.A + (size_t)lp * m * n;
+    const size_t on = (size_t)lp * n, om = (size_t)lp * m;
+    const double* dy = a.rhs + om;
+    double* scal = a.scal + (size_t)lp * S_COUNT;
+    const int n2 = n >> 1;
+
+    double2 ca[NPL];
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) ca[j] = make_double2(0.0, 0.0);
+    for (int r = warp; r < m; r += KB_NW) {
+        const double2* row = reinterpret_cast<const double2*>(A + (size_t)r * n);
+        const double yr = dy[r];
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+            const int c2 = j * 32 + lane;
+            if (c2 < n2) {
+                const double2 v = row[c2];
+                ca[j].x += v.x * yr;
+                ca[j].y += v.y * yr;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+        const int c2 = j * 32 + lane;
+        if (c2 < n2) reinterpret_cast<double2*>(colred + (size_t)warp * n)[c2] = ca[j];
+    }
+    __syncthreads();
+    // each thread owns columns tid, tid + KB_NT (n <= 2*KB_NT)
+    double dxv[2], dsv[2], xv[2], sv[2];
+    double minp = 1.0, mind = 1.0;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int k = tid + q * KB_NT;
+        dxv[q] = dsv[q] = 0.0; xv[q] = sv[q] = 1.0;
+        if (k < n) {
+            double u = 0.0;
+#pragma unroll
+            for (int w = 0; w < KB_NW; ++w) u += colred[(size_t)w * n + k];
+            const double xi = a.x[on + k], si = a.s[on + k];
+            const double dxi = a.d[on + k] * u + a.w[on + k];
+            const double dsi = (-si * dxi / xi) - a.rcx[on + k];
+            dxv[q] = dxi; dsv[q] = dsi; xv[q] = xi; sv[q] = si;
+            if (dxi < 0.0) minp = fmin(minp, -xi / dxi);
+            if (dsi < 0.0) mind = fmin(mind, -si / dsi);
+        }
+    }
+    minp = block_red<RED_MIN>(minp, sh);
+    if (tid == 0) s_alpha[0] = minp;
+    mind = block_red<RED_MIN>(mind, sh);
+    if (tid == 0) s_alpha[1] = mind;
+    __syncthreads();
+    double ap = s_alpha[0], ad = s_alpha[1];
+    if (kind == 0) {
+        double part = 0.0;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int k = tid + q * KB_NT;
+            if (k < n) {
+                a.dxa[on + k] = dxv[q];
+                a.dsa[on + k] = dsv[q];
+                part += (xv[q] + ap * dxv[q]) * (sv[q] + ad * dsv[q]);
+            }
+        }
+        part = block_red<RED_SUM>(part, sh);
+        if (tid == 0) {
+            const double mu_aff = part / (double)n, mu = scal[S_XS] / (double)n;
+            const double r = mu_aff / mu, sigma = r * r * r;
+            scal[S_AP_AFF] = ap; scal[S_AD_AFF] = ad; scal[S_MU_AFF] = mu_aff; scal[S_MU] = mu;
+            scal[S_SIGMA] = sigma; scal[S_SIGMA_MU] = sigma * mu;
+        }
+    } else {
+        ap = fmin(1.0, a.eta * ap);
+        ad = fmin(1.0, a.eta * ad);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int k = tid + q * KB_NT;
+            if (k < n) {
+                a.x[on + k] = xv[q] + ap * dxv[q];
+                a.s[on + k] = sv[q] + ad * dsv[q];
+            }
+        }
+        for (int i = tid; i < m; i += KB_NT) a.y[om + i] = a.y[om + i] + ad * dy[i];
+        if (tid == 0) {
+            scal[S_AP] = ap; scal[S_AD] = ad;
+            a.iters[lp] += 1;
+        }
+    }
+}
+
+__global__ void kb_finalize(const BatchArgs a, int B, double* obj, int* iters, int* status) {
+    const int lp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lp >= B) return;
+    const double* sc = a.scal + (size_t)lp * S_COUNT;
+    const bool finite = isfinite(sc[S_NRB]) && isfinite(sc[S_NRC]) && isfinite(sc[S_XS]) && isfinite(sc[S_OBJ]);
+    int st = IPM_STATUS_CONVERGED;
+    if (!finite) st = IPM_STATUS_NAN;
+    else if (sc[S_CONT] > 0.5) st = IPM_STATUS_MAX_ITER;
+    if (obj) obj[lp] = sc[S_OBJ];
+    if (iters) iters[lp] = a.iters[lp];
+    if (status) status[lp] = st;
+}
+
+// ---------------------------------------------------------------------------------------------
+struct Workspace {
+    BatchArgs a;
+    double* M;
+    int64_t ldm;
+    unsigned* h_nact;    // pinned
+};
+
+int64_t ws_bytes(int B, int m, int n) {
+    const int64_t ldm = round_up(m, 16);
+    int64_t doubles = (int64_t)B * (8 * (int64_t)n + 4 * (int64_t)m + S_COUNT) + (int64_t)B * m * ldm;
+    int64_t bytes = doubles * 8 + (int64_t)B * 2 * sizeof(int) + 256 + 1024;
+    return round_up(bytes, 256);
+}
+
+void carve(Workspace& w, void* base, int B, int m, int n) {
+    double* p = reinterpret_cast<double*>(base);
+    auto take = [&](int64_t len) { double* q = p; p += len; return q; };
+    const int64_t bn = (int64_t)B * n, bm = (int64_t)B * m;
+    w.ldm = round_up(m, 16);
+    w.M = take((int64_t)B * m * w.ldm);
+    w.a.x = take(bn); w.a.s = take(bn); w.a.rc = take(bn); w.a.d = take(bn); w.a.w = take(bn); w.a.rcx = take(bn);
+    w.a.dxa = take(bn); w.a.dsa = take(bn);
+    w.a.y = take(bm); w.a.rb = take(bm); w.a.dy = take(bm); w.a.rhs = take(bm);
+    w.a.scal = take((int64_t)B * S_COUNT);
+    int* ip = reinterpret_cast<int*>(p);
+    w.a.active = ip; ip += B;
+    w.a.iters = ip; ip += B;
+    uintptr_t u = (reinterpret_cast<uintptr_t>(ip) + 63) & ~(uintptr_t)63;
+    w.a.n_active = reinterpret_cast<unsigned*>(u);
+    w.a.m = m; w.a.n = n;
+}
+
+template <int NPL>
+int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, int* iterations_run) {
+    BatchArgs& a = w.a;
+    const size_t smem_col = (size_t)KB_NW * n * sizeof(double);
+    const size_t smem_w = (size_t)n * sizeof(double);
+    static int configured_dev = -1;
+    int dev = 0;
+    IPM_CUDA_OK(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+        IPM_CUDA_OK(cudaFuncSetAttribute(kb_residual<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
+        IPM_CUDA_OK(cudaFuncSetAttribute(kb_dir<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
+        IPM_CUDA_OK(cudaFuncSetAttribute(k_trsv_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        configured_dev = dev;
+    }
+    kb_init<<<B, 256, 0, st>>>(a);
+    count_launch();
+    int it = 0;
+    for (;;) {
+        IPM_CUDA_OK(cudaMemsetAsync(a.n_active, 0, sizeof(unsigned), st));
+        kb_residual<NPL><<<B, KB_NT, smem_col, st>>>(a);
+        count_launch();
+        IPM_CUDA_OK(cudaMemcpyAsync(w.h_nact, a.n_active, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        IPM_CUDA_OK(cudaStreamSynchronize(st));
+        if (*w.h_nact == 0) break;
+        DmmaArgs g;
+        g.P = a.A; g.ldp = n; g.strideP = (int64_t)m * n;
+        g.Q = a.A; g.ldq = n; g.strideQ = (int64_t)m * n;
+        g.dvec = a.d; g.strideD = n;
+        g.C = w.M; g.ldc = w.ldm; g.strideC = (int64_t)m * w.ldm;
+        g.rowsP = m; g.rowsQ = m; g.K = n; g.lower_only = 1; g.active = a.active;
+        IPM_TRY((dmma_nt_launch<128, 128, 4, 2, 0>(g, B, st)));
+        IPM_TRY((potrf_blocked<64, 256, 128>(w.M, w.ldm, (int64_t)m * w.ldm, m, B, a.scal, S_COUNT, tau, a.active, st)));
+        TrsvBatchedArgs t;
+        t.L = w.M; t.ldm = w.ldm; t.strideM = (int64_t)m * w.ldm; t.v = a.rhs; t.strideV = m; t.m = m;
+        t.active = a.active;
+        for (int kind = 0; kind < 2; ++kind) {
+            kb_rhs<NPL><<<B, KB_NT, smem_w, st>>>(a, kind);
+            k_trsv_batched<<<B, TRSVB_NT, trsv_batched_smem(m), st>>>(t);
+            kb_dir<NPL><<<B, KB_NT, smem_col, st>>>(a, kind);
+            count_launch(3);
+        }
+        IPM_TRY(launch_check());
+        ++it;
+    }
+    if (iterations_run) *iterations_run = it;
+    return IPM_OK;
+}
+
+int solve_on_device(int B, int m, int n, const double* A_d, const double* b_d, const double* c_d, double tol,
+                    int max_iter, double* obj_d, int* iters_d, int* status_d, double* x_d, void* work_d,
+                    unsigned* h_nact, cudaStream_t st, int* iterations_run) {
+    Workspace w;
+    carve(w, work_d, B, m, n);
+    w.h_nact = h_nact;
+    w.a.A = A_d; w.a.b = b_d; w.a.c = c_d;
+    w.a.tol = tol; w.a.eta = 0.91; w.a.max_iter = max_iter;
+    const double tau = 1e-30;
+    if (n <= 512) IPM_TRY(run_batched<8>(w, B, m, n, tau, st, iterations_run));
+    else IPM_TRY(run_batched<16>(w, B, m, n, tau, st, iterations_run));
+    kb_finalize<<<ceil_div(B, 256), 256, 0, st>>>(w.a, B, obj_d, iters_d, status_d);
+    count_launch();
+    if (x_d) IPM_CUDA_OK(cudaMemcpyAsync(x_d, w.a.x, (size_t)B * n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    return launch_check();
+}
+
+int check_shape(int B, int m, int n) {
+    if (B <= 0 || m <= 0 || n <= 0) return IPM_ERR_SHAPE;
+    if ((n & 1) || n > 2 * KB_NT || m > 2048) {
+        g_last_error = "batched path needs even n <= 1024 and m <= 2048";
+        return IPM_ERR_SHAPE;
+    }
+    return IPM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t ipm_batched_workspace_bytes(int B, int m, int n) {
+    if (B <= 0 || m <= 0 || n <= 0) return 0;
+    return ws_bytes(B, m, n);
+}
+
+int ipm_solve_batched_dense_d(int device_ordinal, int B, int m, int n, const double* A_d, const double* b_d,
+                              const double* c_d, double tol, int max_iter, double* obj_d, int* iters_d,
+                              int* status_d, double* x_d, void* work_d, int* iterations_run) {
+    if (!A_d || !b_d || !c_d) return IPM_ERR_ARG;
+    IPM_TRY(check_shape(B, m, n));
+    IPM_CUDA_OK(cudaSetDevice(device_ordinal));
+    void* own = nullptr;
+    if (!work_d) {
+        IPM_CUDA_OK(cudaMalloc(&own, (size_t)ws_bytes(B, m, n)));
+        work_d = own;
+    }
+    unsigned* h_nact = nullptr;
+    int rc = [&]() -> int {
+        IPM_CUDA_OK(cudaMallocHost(&h_nact, sizeof(unsigned)));
+        IPM_TRY(solve_on_device(B, m, n, A_d, b_d, c_d, tol, max_iter, obj_d, iters_d, status_d, x_d, work_d, h_nact,
+                                0, iterations_run));
+        IPM_CUDA_OK(cudaStreamSynchronize(0));
+        return IPM_OK;
+    }();
+    if (h_nact) cudaFreeHost(h_nact);
+    if (own) cudaFree(own);
+    return rc;
+}
+
+int ipm_solve_batched_dense(int device_ordinal, int B, int m, int n, const double* A, const double* b,
+                            const double* c, double tol, int max_iter, double* obj, int* iters, int* status,
+                            double* x) {
+    if (!A || !b || !c) return IPM_ERR_ARG;
+    IPM_TRY(check_shape(B, m, n));
+    IPM_CUDA_OK(cudaSetDevice(device_ordinal));
+    // chunking: two device-resident input buffers so the H2D copy of chunk k+1 overlaps the solve of chunk k
+    const int64_t lp_bytes = ((int64_t)m * n + m + n) * 8;
+    int chunk = (int)std::min<int64_t>(B, std::max<int64_t>(1, ((int64_t)1 << 30) / lp_bytes));   // ~1 GiB of inputs
+    if (chunk < B) chunk = ceil_div(B, ceil_div(B, chunk));                                        // balance
+    const int nchunks = ceil_div(B, chunk);
+    cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    double *dA[2] = {nullptr, nullptr}, *db[2] = {nullptr, nullptr}, *dc[2] = {nullptr, nullptr};
+    double *d_obj = nullptr, *d_x = nullptr;
+    int *d_it = nullptr, *d_st = nullptr;
+    void* work = nullptr;
+    unsigned* h_nact = nullptr;
+    int rc = [&]() -> int {
+        IPM_CUDA_OK(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
+        IPM_CUDA_OK(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
+        const int nbuf = nchunks > 1 ? 2 : 1;
+        for (int i = 0; i < nbuf; ++i) {
+            IPM_CUDA_OK(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+            IPM_CUDA_OK(cudaEventCreateWithFlags(&ev_free[i], cudaEventDisableTiming));
+            IPM_CUDA_OK(cudaMalloc(&dA[i], (size_t)chunk * m * n * 8));
+            IPM_CUDA_OK(cudaMalloc(&db[i], (size_t)chunk * m * 8));
+            IPM_CUDA_OK(cudaMalloc(&dc[i], (size_t)chunk * n * 8));
+        }
+        IPM_CUDA_OK(cudaMalloc(&d_obj, (size_t)chunk * 8));
+        IPM_CUDA_OK(cudaMalloc(&d_it, (size_t)chunk * sizeof(int)));
+        IPM_CUDA_OK(cudaMalloc(&d_st, (size_t)chunk * sizeof(int)));
+        if (x) IPM_CUDA_OK(cudaMalloc(&d_x, (size_t)chunk * n * 8));
+        IPM_CUDA_OK(cudaMalloc(&work, (size_t)ws_bytes(chunk, m, n)));
+        IPM_CUDA_OK(cudaMallocHost(&h_nact, sizeof(unsigned)));
+        auto stage = [&](int k) -> int {
+            const int buf = k & 1, first = k * chunk, cnt = std::min(chunk, B - first);
+            if (k >= 2) IPM_CUDA_OK(cudaStreamWaitEvent(s_copy, ev_free[buf], 0));
+            IPM_CUDA_OK(cudaMemcpyAsync(dA[buf], A + (size_t)first * m * n, (size_t)cnt * m * n * 8,
+                                        cudaMemcpyHostToDevice, s_copy));
+            IPM_CUDA_OK(cudaMemcpyAsync(db[buf], b + (size_t)first * m, (size_t)cnt * m * 8, cudaMemcpyHostToDevice,
+                                        s_copy));
+            IPM_CUDA_OK(cudaMemcpyAsync(dc[buf], c + (size_t)first * n, (size_t)cnt * n * 8, cudaMemcpyHostToDevice,
+                                        s_copy));
+            IPM_CUDA_OK(cudaEventRecord(ev_in[buf], s_copy));
+            return IPM_OK;
+        };
+        IPM_TRY(stage(0));
+        for (int k = 0; k < nchunks; ++k) {
+            const int buf = k & 1, first = k * chunk, cnt = std::min(chunk, B - first);
+            if (k + 1 < nchunks) IPM_TRY(stage(k + 1));
+            IPM_CUDA_OK(cudaStreamWaitEvent(s_comp, ev_in[buf], 0));
+            IPM_TRY(solve_on_device(cnt, m, n, dA[buf], db[buf], dc[buf], tol, max_iter, d_obj, d_it, d_st, d_x, work,
+                                    h_nact, s_comp, nullptr));
+            IPM_CUDA_OK(cudaEventRecord(ev_free[buf], s_comp));
+            if (obj) IPM_CUDA_OK(cudaMemcpyAsync(obj + first, d_obj, (size_t)cnt * 8, cudaMemcpyDeviceToHost, s_comp));
+            if (iters) IPM_CUDA_OK(cudaMemcpyAsync(iters + first, d_it, (size_t)cnt * sizeof(int),
+                                                   cudaMemcpyDeviceToHost, s_comp));
+            if (status) IPM_CUDA_OK(cudaMemcpyAsync(status + first, d_st, (size_t)cnt * sizeof(int),
+                                                    cudaMemcpyDeviceToHost, s_comp));
+            if (x) IPM_CUDA_OK(cudaMemcpyAsync(x + (size_t)first * n, d_x, (size_t)cnt * n * 8,
+                                               cudaMemcpyDeviceToHost, s_comp));
+        }
+        IPM_CUDA_OK(cudaStreamSynchronize(s_comp));
+        IPM_CUDA_OK(cudaStreamSynchronize(s_copy));
+        return IPM_OK;
+    }();
+    for (int i = 0; i < 2; ++i) {
+        if (dA[i]) cudaFree(dA[i]);
+        if (db[i]) cudaFree(db[i]);
+        if (dc[i]) cudaFree(dc[i]);
+        if (ev_in[i]) cudaEventDestroy(ev_in[i]);
+        if (ev_free[i]) cudaEventDestroy(ev_free[i]);
+    }
+    if (d_obj) cudaFree(d_obj);
+    if (d_it) cudaFree(d_it);
+    if (d_st) cudaFree(d_st);
+    if (d_x) cudaFree(d_x);
+    if (work) cudaFree(work);
+    if (h_nact) cudaFreeHost(h_nact);
+    if (s_copy) cudaStreamDestroy(s_copy);
+    if (s_comp) cudaStreamDestroy(s_comp);
+    return rc;
+}
+
+}  // extern "C"

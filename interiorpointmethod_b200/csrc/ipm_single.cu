@@ -1,0 +1,615 @@
+// C ABI (include/ipm_b200.h), single-LP part: handle, problem upload, op-level entry points that mirror the
+// reference's Python seams (main.py:162-322, 562-697) and the device-resident predictor-corrector loop.
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "chol.cuh"
+#include "common.cuh"
+#include "dense.cuh"
+#include "dmma_gemm.cuh"
+#include "sparse.cuh"
+#include "vec.cuh"
+
+namespace ipm {
+std::atomic<int64_t> g_launches{0};
+thread_local std::string g_last_error;
+}  // namespace ipm
+
+using namespace ipm;
+
+struct ipm_handle {
+    int dev = 0;
+    cudaStream_t st = nullptr;
+    int m = 0, n = 0;
+    bool loaded = false, dense = false;
+    // sparse A (CSR) and A^T (CSR)
+    int64_t nnz = 0;
+    int32_t *rowptr = nullptr, *colind = nullptr, *t_rowptr = nullptr, *t_colind = nullptr;
+    double *val = nullptr, *t_val = nullptr, *ad = nullptr;
+    // SpGEMM pattern
+    int64_t nent = 0;
+    int64_t *out_idx = nullptr, *prod_ptr = nullptr;
+    int32_t *pa = nullptr, *pb = nullptr;
+    // dense A
+    const double* A = nullptr;
+    int64_t lda = 0;
+    double* A_own = nullptr;
+    double* gemv_partial = nullptr;
+    int nchunks = 0;
+    // vectors (one slab)
+    double* slab = nullptr;
+    double *b, *c, *x, *y, *s, *rb, *rc, *d, *w, *rcx, *dxa, *dya, *dsa, *dx, *dy, *ds, *tm, *tn, *rhs, *tmp_m;
+    double* M = nullptr;
+    int64_t ldm = 0;
+    double* scal = nullptr;
+    double* partials = nullptr;
+    unsigned* counter = nullptr;
+    double* h_scal = nullptr;     // pinned mirror of scal
+    double tol = 1e-8;
+    double eta = 0.91;            // main.py:607
+    double tau = 1e-30;
+    bool have_resid = false, have_M = false, have_factor = false, have_pred = false, have_sigma = false,
+         have_corr = false;
+    std::string err;
+};
+
+namespace {
+
+int fail(ipm_handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    g_last_error = msg;
+    return code;
+}
+int cuda_fail(ipm_handle* h) {
+    if (h) h->err = g_last_error;
+    return IPM_ERR_CUDA;
+}
+#define H_CUDA(expr)                                   \
+    do {                                               \
+        int _r = [&]() -> int { IPM_CUDA_OK(expr); return IPM_OK; }(); \
+        if (_r != IPM_OK) return cuda_fail(h);         \
+    } while (0)
+#define H_TRY(expr)                                    \
+    do {                                               \
+        int _r = (expr);                               \
+        if (_r == IPM_ERR_CUDA) return cuda_fail(h);   \
+        if (_r != IPM_OK) return _r;                   \
+    } while (0)
+
+void free_problem(ipm_handle* h) {
+    cudaSetDevice(h->dev);
+    void* ptrs[] = {h->rowptr, h->colind, h->t_rowptr, h->t_colind, h->val, h->t_val, h->ad, h->out_idx,
+                    h->prod_ptr, h->pa, h->pb, h->A_own, h->gemv_partial, h->slab, h->M};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    h->rowptr = h->colind = h->t_rowptr = h->t_colind = nullptr;
+    h->val = h->t_val = h->ad = nullptr;
+    h->out_idx = h->prod_ptr = nullptr;
+    h->pa = h->pb = nullptr;
+    h->A_own = nullptr; h->A = nullptr; h->gemv_partial = nullptr; h->slab = nullptr; h->M = nullptr;
+    h->loaded = false;
+    h->have_resid = h->have_M = h->have_factor = h->have_pred = h->have_sigma = h->have_corr = false;
+}
+
+int alloc_common(ipm_handle* h, int m, int n) {
+    h->m = m; h->n = n;
+    const int64_t pm = round_up(m, 16), pn = round_up(n, 16);
+    const int64_t total = 6 * pm /*b y rb dya dy tm*/ + 2 * pm /*rhs tmp_m*/ + 12 * pn;
+    H_CUDA(cudaMalloc(&h->slab, (size_t)total * sizeof(double)));
+    H_CUDA(cudaMemsetAsync(h->slab, 0, (size_t)total * sizeof(double), h->st));
+    double* p = h->slab;
+    auto take = [&](int64_t len) { double* q = p; p += len; return q; };
+    h->b = take(pm); h->y = take(pm); h->rb = take(pm); h->dya = take(pm); h->dy = take(pm); h->tm = take(pm);
+    h->rhs = take(pm); h->tmp_m = take(pm);
+    h->c = take(pn); h->x = take(pn); h->s = take(pn); h->rc = take(pn); h->d = take(pn); h->w = take(pn);
+    h->rcx = take(pn); h->dxa = take(pn); h->dsa = take(pn); h->dx = take(pn); h->ds = take(pn); h->tn = take(pn);
+    h->ldm = pm;
+    H_CUDA(cudaMalloc(&h->M, (size_t)m * h->ldm * sizeof(double)));
+    return IPM_OK;
+}
+
+int finish_load(ipm_handle* h) {
+    // |b|, |c| once per problem (main.py:169-170 recomputes them every iteration)
+    k_norm2<<<vec_grid(h->m), VEC_NT, 0, h->st>>>(h->b, h->m, h->scal + S_NB, h->partials, h->counter);
+    k_norm2<<<vec_grid(h->n), VEC_NT, 0, h->st>>>(h->c, h->n, h->scal + S_NC, h->partials, h->counter);
+    count_launch(2);
+    H_TRY(launch_check());
+    H_CUDA(cudaStreamSynchronize(h->st));
+    h->loaded = true;
+    return IPM_OK;
+}
+
+int matvec_A(ipm_handle* h, const double* v, double* out) {
+    if (h->dense) {
+        const int blocks = std::min<int64_t>(ceil_div((int64_t)h->m * 32, GEMV_NT), 8 * kNumSMs * 4);
+        k_gemv_rows<<<blocks, GEMV_NT, 0, h->st>>>(h->m, h->n, h->A, h->lda, v, out);
+    } else {
+        const int blocks = std::min<int64_t>(ceil_div((int64_t)h->m * 8, 256), 8 * kNumSMs);
+        k_spmv_csr<<<blocks, 256, 0, h->st>>>(h->m, h->rowptr, h->colind, h->val, v, out);
+    }
+    count_launch();
+    return launch_check();
+}
+
+int matvec_AT(ipm_handle* h, const double* u, double* out) {
+    if (h->dense) {
+        dim3 grid(ceil_div(h->n, GEMV_NT), h->nchunks);
+        double* partial = (h->nchunks == 1) ? out : h->gemv_partial;
+        k_gemv_cols_partial<<<grid, GEMV_NT, 0, h->st>>>(h->m, h->n, h->A, h->lda, u, partial);
+        count_launch();
+        if (h->nchunks > 1) {
+            k_gemv_cols_combine<<<ceil_div(h->n, 256), 256, 0, h->st>>>(h->n, h->nchunks, partial, out);
+            count_launch();
+        }
+    } else {
+        const int blocks = std::min<int64_t>(ceil_div((int64_t)h->n * 8, 256), 8 * kNumSMs);
+        k_spmv_csr<<<blocks, 256, 0, h->st>>>(h->n, h->t_rowptr, h->t_colind, h->t_val, u, out);
+        count_launch();
+    }
+    return launch_check();
+}
+
+int residual_step(ipm_handle* h) {
+    H_TRY(matvec_A(h, h->x, h->tm));
+    k_resid_primal<<<vec_grid(h->m), VEC_NT, 0, h->st>>>(h->tm, h->b, h->rb, h->m, h->scal, h->partials, h->counter);
+    count_launch();
+    H_TRY(matvec_AT(h, h->y, h->tn));
+    k_resid_dual<<<vec_grid(h->n), VEC_NT, 0, h->st>>>(h->tn, h->s, h->c, h->x, h->rc, h->d, h->n, h->tol, h->scal,
+                                                       h->partials, h->counter);
+    count_launch();
+    H_TRY(launch_check());
+    h->have_resid = true;
+    h->have_M = h->have_factor = h->have_pred = h->have_sigma = h->have_corr = false;
+    return IPM_OK;
+}
+
+int assemble_step(ipm_handle* h) {
+    if (h->dense) {
+        DmmaArgs g;
+        g.P = h->A; g.ldp = h->lda; g.strideP = 0;
+        g.Q = h->A; g.ldq = h->lda; g.strideQ = 0;
+        g.dvec = h->d; g.strideD = 0;
+        g.C = h->M; g.ldc = h->ldm; g.strideC = 0;
+        g.rowsP = h->m; g.rowsQ = h->m; g.K = h->n; g.lower_only = 1; g.active = nullptr;
+        H_TRY((dmma_nt_launch<128, 128, 4, 2, 0>(g, 1, h->st)));
+    } else {
+        H_CUDA(cudaMemsetAsync(h->M, 0, (size_t)h->m * h->ldm * sizeof(double), h->st));
+        k_scale_vals<<<std::max(1, std::min<int>(ceil_div(h->nnz, 256), 8 * kNumSMs)), 256, 0, h->st>>>(
+            h->nnz, h->colind, h->val, h->d, h->ad);
+        k_spgemm_numeric<<<std::max(1, std::min<int>(ceil_div(h->nent, 256), 8 * kNumSMs)), 256, 0, h->st>>>(
+            h->nent, h->out_idx, h->prod_ptr, h->pa, h->pb, h->ad, h->val, h->M);
+        count_launch(2);
+        H_TRY(launch_check());
+    }
+    h->have_M = true;
+    h->have_factor = false;
+    return IPM_OK;
+}
+
+int factor_step(ipm_handle* h, double tau) {
+    H_TRY((potrf_blocked<128, 512, 64>(h->M, h->ldm, 0, h->m, 1, h->scal, 0, tau, nullptr, h->st)));
+    h->have_factor = true;
+    h->have_M = false;
+    return IPM_OK;
+}
+
+int direction_step(ipm_handle* h, int kind) {
+    double* dxo = kind ? h->dx : h->dxa;
+    double* dyo = kind ? h->dy : h->dya;
+    double* dso = kind ? h->ds : h->dsa;
+    k_make_w<<<vec_grid(h->n), VEC_NT, 0, h->st>>>(kind, h->x, h->s, h->rc, h->d, h->dxa, h->dsa, h->scal, h->rcx,
+                                                   h->w, h->n);
+    count_launch();
+    H_TRY(matvec_A(h, h->w, h->tm));
+    k_make_rhs<<<vec_grid(h->m), VEC_NT, 0, h->st>>>(h->rb, h->tm, h->rhs, h->m);
+    count_launch();
+    H_TRY(potrs_single(h->M, h->ldm, h->m, h->rhs, h->tmp_m, dyo, h->st));
+    H_TRY(matvec_AT(h, dyo, h->tn));
+    k_direction<<<vec_grid(h->n), VEC_NT, 0, h->st>>>(kind, h->tn, h->d, h->w, h->rcx, h->x, h->s, dxo, dso, h->n,
+                                                      h->eta, h->scal, h->partials, h->counter);
+    count_launch();
+    H_TRY(launch_check());
+    if (kind == 0) { h->have_pred = true; h->have_sigma = false; h->have_corr = false; }
+    else h->have_corr = true;
+    return IPM_OK;
+}
+
+int sigma_step(ipm_handle* h) {
+    k_sigma<<<vec_grid(h->n), VEC_NT, 0, h->st>>>(h->x, h->s, h->dxa, h->dsa, h->n, h->scal, h->partials, h->counter);
+    count_launch();
+    H_TRY(launch_check());
+    h->have_sigma = true;
+    return IPM_OK;
+}
+
+int update_step(ipm_handle* h, double ap, double ad) {
+    const int len = std::max(h->m, h->n);
+    k_update<<<vec_grid(len), VEC_NT, 0, h->st>>>(h->x, h->y, h->s, h->dx, h->dy, h->ds, h->m, h->n, h->scal, ap, ad);
+    count_launch();
+    H_TRY(launch_check());
+    h->have_resid = h->have_M = h->have_factor = h->have_pred = h->have_sigma = h->have_corr = false;
+    return IPM_OK;
+}
+
+int fetch_scal(ipm_handle* h) {
+    H_CUDA(cudaMemcpyAsync(h->h_scal, h->scal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    H_CUDA(cudaStreamSynchronize(h->st));
+    return IPM_OK;
+}
+
+int check_handle(ipm_handle* h, bool need_loaded = true) {
+    if (!h) return IPM_ERR_ARG;
+    if (cudaSetDevice(h->dev) != cudaSuccess) return fail(h, IPM_ERR_CUDA, "cudaSetDevice failed");
+    if (need_loaded && !h->loaded) return fail(h, IPM_ERR_STATE, "no problem loaded");
+    return IPM_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char* ipm_version(void) { return "interiorpointmethod_b200 0.1 (sm_100a)"; }
+int64_t ipm_launch_count(void) { return g_launches.load(); }
+
+const char* ipm_last_error(const ipm_handle* h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+int ipm_create(ipm_handle** out, int device_ordinal) {
+    if (!out) return IPM_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        g_last_error = "no CUDA device available (this library has no CPU fallback)";
+        return IPM_ERR_CUDA;
+    }
+    if (device_ordinal < 0 || device_ordinal >= count) {
+        g_last_error = "device ordinal out of range";
+        return IPM_ERR_ARG;
+    }
+    ipm_handle* h = new ipm_handle();
+    h->dev = device_ordinal;
+    auto init = [&]() -> int {
+        IPM_CUDA_OK(cudaSetDevice(h->dev));
+        IPM_CUDA_OK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+        IPM_CUDA_OK(cudaMalloc(&h->scal, S_COUNT * sizeof(double)));
+        IPM_CUDA_OK(cudaMemset(h->scal, 0, S_COUNT * sizeof(double)));
+        IPM_CUDA_OK(cudaMalloc(&h->partials, (size_t)VEC_MAX_BLOCKS * 4 * sizeof(double)));
+        IPM_CUDA_OK(cudaMalloc(&h->counter, sizeof(unsigned)));
+        IPM_CUDA_OK(cudaMemset(h->counter, 0, sizeof(unsigned)));
+        IPM_CUDA_OK(cudaMallocHost(&h->h_scal, S_COUNT * sizeof(double)));
+        return IPM_OK;
+    };
+    if (init() != IPM_OK) {
+        ipm_destroy(h);
+        return IPM_ERR_CUDA;
+    }
+    *out = h;
+    return IPM_OK;
+}
+
+void ipm_destroy(ipm_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->dev);
+    if (h->st) cudaStreamSynchronize(h->st);
+    free_problem(h);
+    if (h->scal) cudaFree(h->scal);
+    if (h->partials) cudaFree(h->partials);
+    if (h->counter) cudaFree(h->counter);
+    if (h->h_scal) cudaFreeHost(h->h_scal);
+    if (h->st) cudaStreamDestroy(h->st);
+    delete h;
+}
+
+int ipm_set_pivot_threshold(ipm_handle* h, double pivot_rel_thresh) {
+    if (!h) return IPM_ERR_ARG;
+    if (!(pivot_rel_thresh >= 0.0)) return fail(h, IPM_ERR_ARG, "threshold must be >= 0");
+    h->tau = pivot_rel_thresh;
+    return IPM_OK;
+}
+
+int ipm_load_csr(ipm_handle* h, int m, int n, int64_t nnz, const int32_t* rowptr, const int32_t* colind,
+                 const double* val, const double* b, const double* c) {
+    H_TRY(check_handle(h, false));
+    if (!rowptr || !colind || !val || !b || !c) return fail(h, IPM_ERR_ARG, "null pointer");
+    if (m <= 0 || n <= 0 || nnz < 0 || rowptr[0] != 0 || rowptr[m] != nnz)
+        return fail(h, IPM_ERR_SHAPE, "bad CSR header");
+    for (int i = 0; i < m; ++i) {
+        if (rowptr[i + 1] < rowptr[i]) return fail(h, IPM_ERR_SHAPE, "rowptr not monotone");
+        for (int64_t p = rowptr[i]; p < rowptr[i + 1]; ++p) {
+            if (colind[p] < 0 || colind[p] >= n) return fail(h, IPM_ERR_SHAPE, "column index out of range");
+            if (p > rowptr[i] && colind[p] <= colind[p - 1])
+                return fail(h, IPM_ERR_SHAPE, "column indices must be strictly ascending inside a row");
+        }
+    }
+    free_problem(h);
+    h->dense = false;
+    h->nnz = nnz;
+    H_TRY(alloc_common(h, m, n));
+    // transpose (CSR of A^T) on the host
+    std::vector<int32_t> tp(n + 1, 0), tc(nnz);
+    std::vector<double> tv(nnz);
+    for (int64_t p = 0; p < nnz; ++p) tp[colind[p] + 1]++;
+    for (int k = 0; k < n; ++k) tp[k + 1] += tp[k];
+    {
+        std::vector<int32_t> fill(tp.begin(), tp.end() - 1);
+        for (int i = 0; i < m; ++i)
+            for (int64_t p = rowptr[i]; p < rowptr[i + 1]; ++p) {
+                const int32_t q = fill[colind[p]]++;
+                tc[q] = i;
+                tv[q] = val[p];
+            }
+    }
+    SpgemmPattern pat;
+    spgemm_symbolic(m, n, rowptr, colind, h->ldm, pat);
+    h->nent = (int64_t)pat.out_idx.size();
+    const size_t nz = (size_t)std::max<int64_t>(nnz, 1), np = std::max<size_t>(pat.pa.size(), 1);
+    H_CUDA(cudaMalloc(&h->rowptr, (m + 1) * sizeof(int32_t)));
+    H_CUDA(cudaMalloc(&h->colind, nz * sizeof(int32_t)));
+    H_CUDA(cudaMalloc(&h->val, nz * sizeof(double)));
+    H_CUDA(cudaMalloc(&h->ad, nz * sizeof(double)));
+    H_CUDA(cudaMalloc(&h->t_rowptr, (n + 1) * sizeof(int32_t)));
+    H_CUDA(cudaMalloc(&h->t_colind, nz * sizeof(int32_t)));
+    H_CUDA(cudaMalloc(&h->t_val, nz * sizeof(double)));
+    H_CUDA(cudaMalloc(&h->out_idx, std::max<size_t>(pat.out_idx.size(), 1) * sizeof(int64_t)));
+    H_CUDA(cudaMalloc(&h->prod_ptr, pat.prod_ptr.size() * sizeof(int64_t)));
+    H_CUDA(cudaMalloc(&h->pa, np * sizeof(int32_t)));
+    H_CUDA(cudaMalloc(&h->pb, np * sizeof(int32_t)));
+    H_CUDA(cudaMemcpyAsync(h->rowptr, rowptr, (m + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, h->st));
+    H_CUDA(cudaMemcpyAsync(h->colind, colind, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, h->st));
+    H_CUDA(cudaMemcpyAsync(h->val, val, nnz * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    H_CUDA(cudaMemcpyAsync(h->t_rowptr, tp.data(), (n + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, h->st));
+    H_CUDA(cudaMemcpyAsync(h->t_colind, tc.data(), nnz * sizeof(int32_t), cudaMemcpyHostToDevice, h->st));
+    H_CUDA(cudaMemcpyAsync(h->t_val, tv.data(), nnz * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    H_CUDA(cudaMemcpyAsync(h->out_idx, pat.out_idx.data(), pat.out_idx.size() * sizeof(int64_t),
+                           cudaMemcpyHostToDevice, h->st));
+    H_CUDA(cudaMemcpyAsync(h->prod_ptr, pat.prod_ptr.data(), pat.prod_ptr.size() * sizeof(int64_t),
+                           cudaMemcpyHostToDevice, h->st));
+    H_CUDA(cudaMemcpyAsync(h->pa, pat.pa.data(), pat.pa.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->st));
+    H_CUDA(cudaMemcpyAsync(h->pb, pat.pb.data(), pat.pb.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->st));
+    H_CUDA(cudaMemcpyAsync(h->b, b, m * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    H_CUDA(cudaMemcpyAsync(h->c, c, n * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    H_CUDA(cudaStreamSynchronize(h->st));     // host staging vectors go out of scope
+    return finish_load(h);
+}
+
+static int load_dense_common(ipm_handle* h, int m, int n) {
+    h->dense = true;
+    H_TRY(alloc_common(h, m, n));
+    h->nchunks = ceil_div(m, GEMVC_ROWS);
+    if (h->nchunks > 1) H_CUDA(cudaMalloc(&h->gemv_partial, (size_t)h->nchunks * n * sizeof(double)));
+    return IPM_OK;
+}
+
+int ipm_load_dense(ipm_handle* h, int m, int n, const double* A, int64_t lda, const double* b, const double* c) {
+    H_TRY(check_handle(h, false));
+    if (!A || !b || !c) return fail(h, IPM_ERR_ARG, "null pointer");
+    if (m <= 0 || n <= 0 || lda < n) return fail(h, IPM_ERR_SHAPE, "bad dense shape");
+    free_problem(h);
+    H_TRY(load_dense_common(h, m, n));
+    h->lda = round_up(n, 16);
+    H_CUDA(cudaMalloc(&h->A_own, (size_t)m * h->lda * sizeof(double)));
+    H_CUDA(cudaMemsetAsync(h->A_own, 0, (size_t)m * h->lda * sizeof(double), h->st));
+    H_CUDA(cudaMemcpy2DAsync(h->A_own, h->lda * sizeof(double), A, lda * sizeof(double), n * sizeof(double), m,
+                             cudaMemcpyHostToDevice, h->st));
+    h->A = h->A_own;
+    H_CUDA(cudaMemcpyAsync(h->b, b, m * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    H_CUDA(cudaMemcpyAsync(h->c, c, n * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    return finish_load(h);
+}
+
+int ipm_load_dense_d(ipm_handle* h, int m, int n, const double* A_d, int64_t lda, const double* b_d,
+                     const double* c_d) {
+    H_TRY(check_handle(h, false));
+    if (!A_d || !b_d || !c_d) return fail(h, IPM_ERR_ARG, "null pointer");
+    if (m <= 0 || n <= 0 || lda < n) return fail(h, IPM_ERR_SHAPE, "bad dense shape");
+    free_problem(h);
+    H_TRY(load_dense_common(h, m, n));
+    h->A = A_d;
+    h->lda = lda;
+    H_CUDA(cudaMemcpyAsync(h->b, b_d, m * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+    H_CUDA(cudaMemcpyAsync(h->c, c_d, n * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+    return finish_load(h);
+}
+
+int ipm_init_state(ipm_handle* h, int y0_is_one) {
+    H_TRY(check_handle(h));
+    k_fill<<<vec_grid(h->n), VEC_NT, 0, h->st>>>(h->x, h->n, 1.0);
+    k_fill<<<vec_grid(h->n), VEC_NT, 0, h->st>>>(h->s, h->n, 1.0);
+    k_fill<<<vec_grid(h->m), VEC_NT, 0, h->st>>>(h->y, h->m, y0_is_one ? 1.0 : 0.0);
+    count_launch(3);
+    H_TRY(launch_check());
+    h->have_resid = h->have_M = h->have_factor = h->have_pred = h->have_sigma = h->have_corr = false;
+    return IPM_OK;
+}
+
+int ipm_set_state(ipm_handle* h, const double* x, const double* y, const double* s) {
+    H_TRY(check_handle(h));
+    if (!x || !y || !s) return fail(h, IPM_ERR_ARG, "null pointer");
+    H_CUDA(cudaMemcpyAsync(h->x, x, h->n * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    H_CUDA(cudaMemcpyAsync(h->y, y, h->m * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    H_CUDA(cudaMemcpyAsync(h->s, s, h->n * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    H_CUDA(cudaStreamSynchronize(h->st));
+    h->have_resid = h->have_M = h->have_factor = h->have_pred = h->have_sigma = h->have_corr = false;
+    return IPM_OK;
+}
+
+int ipm_get_state(ipm_handle* h, double* x, double* y, double* s) {
+    H_TRY(check_handle(h));
+    if (x) H_CUDA(cudaMemcpyAsync(x, h->x, h->n * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    if (y) H_CUDA(cudaMemcpyAsync(y, h->y, h->m * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    if (s) H_CUDA(cudaMemcpyAsync(s, h->s, h->n * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    H_CUDA(cudaStreamSynchronize(h->st));
+    return IPM_OK;
+}
+
+int ipm_residual_norms(ipm_handle* h, double out[5]) {
+    H_TRY(check_handle(h));
+    H_TRY(residual_step(h));
+    H_TRY(fetch_scal(h));
+    if (out) {
+        out[0] = h->h_scal[S_NRB]; out[1] = h->h_scal[S_NRC]; out[2] = h->h_scal[S_XS];
+        out[3] = h->h_scal[S_NB]; out[4] = h->h_scal[S_NC];
+    }
+    return IPM_OK;
+}
+
+int ipm_get_residuals(ipm_handle* h, double* rb, double* rc) {
+    H_TRY(check_handle(h));
+    if (!h->have_resid) return fail(h, IPM_ERR_STATE, "call ipm_residual_norms first");
+    if (rb) H_CUDA(cudaMemcpyAsync(rb, h->rb, h->m * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    if (rc) H_CUDA(cudaMemcpyAsync(rc, h->rc, h->n * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    H_CUDA(cudaStreamSynchronize(h->st));
+    return IPM_OK;
+}
+
+int ipm_assemble_normal(ipm_handle* h) {
+    H_TRY(check_handle(h));
+    if (!h->have_resid) return fail(h, IPM_ERR_STATE, "call ipm_residual_norms first (it forms d = x/s)");
+    return assemble_step(h);
+}
+
+int ipm_get_M(ipm_handle* h, double* M_rowmajor) {
+    H_TRY(check_handle(h));
+    if (!M_rowmajor) return fail(h, IPM_ERR_ARG, "null pointer");
+    if (!h->have_M && !h->have_factor) return fail(h, IPM_ERR_STATE, "M not assembled");
+    H_CUDA(cudaMemcpy2DAsync(M_rowmajor, (size_t)h->m * sizeof(double), h->M, h->ldm * sizeof(double),
+                             (size_t)h->m * sizeof(double), h->m, cudaMemcpyDeviceToHost, h->st));
+    H_CUDA(cudaStreamSynchronize(h->st));
+    return IPM_OK;
+}
+
+int ipm_factor(ipm_handle* h, double pivot_rel_thresh, int* n_fixed) {
+    H_TRY(check_handle(h));
+    if (!h->have_M) return fail(h, IPM_ERR_STATE, "call ipm_assemble_normal first");
+    H_TRY(factor_step(h, pivot_rel_thresh));
+    if (n_fixed) {
+        H_TRY(fetch_scal(h));
+        *n_fixed = (int)h->h_scal[S_NFIXED];
+    }
+    return IPM_OK;
+}
+
+int ipm_direction(ipm_handle* h, int kind, double* dx, double* dy, double* ds) {
+    H_TRY(check_handle(h));
+    if (kind != 0 && kind != 1) return fail(h, IPM_ERR_ARG, "kind must be 0 or 1");
+    if (!h->have_resid || !h->have_factor) return fail(h, IPM_ERR_STATE, "need residuals and a factorisation");
+    if (kind == 1 && (!h->have_pred || !h->have_sigma))
+        return fail(h, IPM_ERR_STATE, "corrector needs the predictor direction and ipm_sigma");
+    H_TRY(direction_step(h, kind));
+    const double* sx = kind ? h->dx : h->dxa;
+    const double* sy = kind ? h->dy : h->dya;
+    const double* ss = kind ? h->ds : h->dsa;
+    if (dx) H_CUDA(cudaMemcpyAsync(dx, sx, h->n * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    if (dy) H_CUDA(cudaMemcpyAsync(dy, sy, h->m * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    if (ds) H_CUDA(cudaMemcpyAsync(ds, ss, h->n * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    H_CUDA(cudaStreamSynchronize(h->st));
+    return IPM_OK;
+}
+
+int ipm_ratio_test(ipm_handle* h, int kind, double eta, double alpha[2]) {
+    H_TRY(check_handle(h));
+    if (kind != 0 && kind != 1) return fail(h, IPM_ERR_ARG, "kind must be 0 or 1");
+    if ((kind == 0 && !h->have_pred) || (kind == 1 && !h->have_corr))
+        return fail(h, IPM_ERR_STATE, "direction not computed");
+    H_TRY(fetch_scal(h));
+    double ap = h->h_scal[kind ? S_AP : S_AP_AFF], ad = h->h_scal[kind ? S_AD : S_AD_AFF];
+    if (kind == 1 && eta != h->eta) {
+        // the fused kernel applied the handle's eta (0.91, main.py:607); redo the scalar step with the caller's
+        ap = std::fmin(1.0, eta * h->h_scal[S_RAW_P]);
+        ad = std::fmin(1.0, eta * h->h_scal[S_RAW_D]);
+        const double v[2] = {ap, ad};
+        H_CUDA(cudaMemcpyAsync(h->scal + S_AP, v, 2 * sizeof(double), cudaMemcpyHostToDevice, h->st));
+        H_CUDA(cudaStreamSynchronize(h->st));
+    }
+    if (alpha) { alpha[0] = ap; alpha[1] = ad; }
+    return IPM_OK;
+}
+
+int ipm_sigma(ipm_handle* h, double out[3]) {
+    H_TRY(check_handle(h));
+    if (!h->have_pred) return fail(h, IPM_ERR_STATE, "predictor direction not computed");
+    H_TRY(sigma_step(h));
+    H_TRY(fetch_scal(h));
+    if (out) { out[0] = h->h_scal[S_MU_AFF]; out[1] = h->h_scal[S_MU]; out[2] = h->h_scal[S_SIGMA]; }
+    return IPM_OK;
+}
+
+int ipm_update(ipm_handle* h, double alpha_p, double alpha_d) {
+    H_TRY(check_handle(h));
+    if (!h->have_corr) return fail(h, IPM_ERR_STATE, "corrector direction not computed");
+    if (!(alpha_p >= 0.0) || !(alpha_d >= 0.0)) return fail(h, IPM_ERR_ARG, "step lengths must be >= 0");
+    H_TRY(update_step(h, alpha_p, alpha_d));
+    H_CUDA(cudaStreamSynchronize(h->st));
+    return IPM_OK;
+}
+
+int ipm_solve(ipm_handle* h, double tol, int max_iter, int y0_is_one, double* x, double* y, double* s, double* obj,
+              int* iters, int* status, double resid[5]) {
+    H_TRY(check_handle(h));
+    if (max_iter < 0) return fail(h, IPM_ERR_ARG, "max_iter < 0");
+    h->tol = tol;
+    H_TRY(ipm_init_state(h, y0_is_one));
+    int k = 0;
+    const double tau = h->tau;
+    for (;;) {
+        H_TRY(residual_step(h));                 // check_optimality, main.py:780
+        H_TRY(fetch_scal(h));
+        if (!(h->h_scal[S_CONT] > 0.5) || k >= max_iter) break;
+        H_TRY(assemble_step(h));                 // main.py:223-224
+        H_TRY(factor_step(h, tau));              // main.py:176-182 (one factorisation per iteration)
+        H_TRY(direction_step(h, 0));             // main.py:783
+        H_TRY(sigma_step(h));                    // main.py:795
+        H_TRY(direction_step(h, 1));             // main.py:799
+        H_TRY(update_step(h, -1.0, -1.0));       // main.py:803
+        ++k;
+    }
+    const double* hs = h->h_scal;
+    const bool finite = std::isfinite(hs[S_NRB]) && std::isfinite(hs[S_NRC]) && std::isfinite(hs[S_XS]) &&
+                        std::isfinite(hs[S_OBJ]);
+    int st = IPM_STATUS_CONVERGED;
+    if (!finite) st = IPM_STATUS_NAN;
+    else if (hs[S_CONT] > 0.5) st = IPM_STATUS_MAX_ITER;
+    if (obj) *obj = hs[S_OBJ];
+    if (iters) *iters = k;
+    if (status) *status = st;
+    if (resid) {
+        resid[0] = hs[S_NRB]; resid[1] = hs[S_NRC]; resid[2] = hs[S_XS]; resid[3] = hs[S_NB]; resid[4] = hs[S_NC];
+    }
+    return ipm_get_state(h, x, y, s);
+}
+
+// ------------------------------------------------------------------------------------------------- stand-alone kernels
+int ipm_syrk_d(int device_ordinal, int m, int n, const double* A_d, int64_t lda, const double* d_d, double* M_d,
+               int64_t ldm) {
+    if (!A_d || !M_d) return IPM_ERR_ARG;
+    if (m <= 0 || n <= 0 || lda < n || ldm < m) return IPM_ERR_SHAPE;
+    IPM_CUDA_OK(cudaSetDevice(device_ordinal));
+    DmmaArgs g;
+    g.P = A_d; g.ldp = lda; g.strideP = 0;
+    g.Q = A_d; g.ldq = lda; g.strideQ = 0;
+    g.dvec = d_d; g.strideD = 0;
+    g.C = M_d; g.ldc = ldm; g.strideC = 0;
+    g.rowsP = m; g.rowsQ = m; g.K = n; g.lower_only = 1; g.active = nullptr;
+    IPM_TRY((dmma_nt_launch<128, 128, 4, 2, 0>(g, 1, 0)));
+    return IPM_OK;
+}
+
+int ipm_potrf_d(int device_ordinal, int m, double* M_d, int64_t ldm, double pivot_rel_thresh, int* n_fixed) {
+    if (!M_d) return IPM_ERR_ARG;
+    if (m <= 0 || ldm < m || (ldm & 1) || (reinterpret_cast<uintptr_t>(M_d) & 15)) return IPM_ERR_SHAPE;
+    IPM_CUDA_OK(cudaSetDevice(device_ordinal));
+    double* scal = nullptr;
+    IPM_CUDA_OK(cudaMalloc(&scal, S_COUNT * sizeof(double)));
+    int rc = potrf_blocked<128, 512, 64>(M_d, ldm, 0, m, 1, scal, 0, pivot_rel_thresh, nullptr, 0);
+    double hs[S_COUNT];
+    if (rc == IPM_OK) {
+        cudaError_t e = cudaMemcpy(hs, scal, sizeof(hs), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { g_last_error = cudaGetErrorString(e); rc = IPM_ERR_CUDA; }
+        else if (n_fixed) *n_fixed = (int)hs[S_NFIXED];
+    }
+    cudaFree(scal);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,283 @@
+"""Host-side mirror of the reference's call surface for the Newton-step hot path.
+
+The reference (payakorn/InteriorPointMethod) has no plugin interface; its seams are plain functions in
+`main.py`.  This module offers the same names with the same argument meaning, routed to the B200 library
+through ctypes (include/ipm_b200.h):
+
+    interior_sparse(A, b, c, cTlb, tol)            main.py:760   -> objective - cTlb (float)
+    interior(A, b, c, tol)                         main.py:707   -> Result (the reference prints and returns None)
+    direction_predicted_sparse(..., method="gpu")  main.py:197
+    direction_corrected_sparse(..., method="gpu")  main.py:247
+    check_optimality / predicted_stepsize / duality_gap / full_stepsize / corrected
+                                                   main.py:162, 305, 588, 604, 663
+    solve(A, b, c, tol) -> Result(x, objective, iterations, ...)   (BASELINE.json north_star surface)
+
+Vectors follow the reference's layout: (k,1) float64 columns in, (k,1) columns out.  Inputs are accepted
+exactly as `create_problem_from_mps` produces them (csc_matrix with integer data, uint8/uint16/int16 b and c;
+sparse_interior.py:211-216) and cast to float64 / int32 here.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+
+try:  # scipy is only needed for sparse inputs
+    from scipy import sparse as _sp
+except Exception:  # pragma: no cover
+    _sp = None
+
+ETA = 0.91  # main.py:607
+
+
+def _f64(v, shape=None):
+    a = np.ascontiguousarray(np.asarray(v, dtype=np.float64).ravel())
+    if shape is not None and a.size != shape:
+        raise ValueError("expected %d entries, got %d" % (shape, a.size))
+    return a
+
+
+def _col(v):
+    return np.asarray(v, dtype=np.float64).reshape(-1, 1)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+@dataclass
+class Result:
+    x: np.ndarray            # (n,1)
+    y: np.ndarray            # (m,1)
+    s: np.ndarray            # (n,1)
+    objective: float         # c^T x - cTlb
+    iterations: int
+    status: str              # converged | max_iter | nan
+    residuals: dict = field(default_factory=dict)   # |rb|, |rc|, gap, |b|, |c| at exit
+
+
+class NewtonStep:
+    """One LP resident on one B200: owns an `ipm_handle`.  Not thread-safe (one stream)."""
+
+    def __init__(self, A, b, c, device: int = 0):
+        self._lib = _lib.load()
+        self._h = ctypes.c_void_p()
+        _lib.check(self._lib.ipm_create(ctypes.byref(self._h), int(device)), None, "ipm_create")
+        self.device = int(device)
+        self._keep = None
+        self.load(A, b, c)
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.ipm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc, what):
+        _lib.check(rc, self._h, what)
+
+    # ------------------------------------------------------------------ data
+    def load(self, A, b, c):
+        if _sp is not None and _sp.issparse(A):
+            Ar = _sp.csr_matrix(A, dtype=np.float64)
+            Ar.sum_duplicates()
+            Ar.sort_indices()
+            self.m, self.n = Ar.shape
+            bb, cc = _f64(b, self.m), _f64(c, self.n)
+            rowptr = np.ascontiguousarray(Ar.indptr, dtype=np.int32)
+            colind = np.ascontiguousarray(Ar.indices, dtype=np.int32)
+            val = np.ascontiguousarray(Ar.data, dtype=np.float64)
+            self._check(self._lib.ipm_load_csr(self._h, self.m, self.n, int(Ar.nnz), _ptr(rowptr), _ptr(colind),
+                                               _ptr(val), _ptr(bb), _ptr(cc)), "ipm_load_csr")
+            self.sparse = True
+        else:
+            Ad = np.ascontiguousarray(np.asarray(A, dtype=np.float64))
+            if Ad.ndim != 2:
+                raise ValueError("A must be 2-D")
+            self.m, self.n = Ad.shape
+            bb, cc = _f64(b, self.m), _f64(c, self.n)
+            self._check(self._lib.ipm_load_dense(self._h, self.m, self.n, _ptr(Ad), self.n, _ptr(bb), _ptr(cc)),
+                        "ipm_load_dense")
+            self.sparse = False
+
+    def set_pivot_threshold(self, tau: float):
+        self._check(self._lib.ipm_set_pivot_threshold(self._h, float(tau)), "ipm_set_pivot_threshold")
+
+    # ------------------------------------------------------------------ iterate
+    def init_state(self, y0_is_one: bool = True):
+        self._check(self._lib.ipm_init_state(self._h, int(bool(y0_is_one))), "ipm_init_state")
+
+    def set_state(self, x, y, s):
+        x, y, s = _f64(x, self.n), _f64(y, self.m), _f64(s, self.n)
+        self._check(self._lib.ipm_set_state(self._h, _ptr(x), _ptr(y), _ptr(s)), "ipm_set_state")
+
+    def get_state(self):
+        x, y, s = np.empty(self.n), np.empty(self.m), np.empty(self.n)
+        self._check(self._lib.ipm_get_state(self._h, _ptr(x), _ptr(y), _ptr(s)), "ipm_get_state")
+        return _col(x), _col(y), _col(s)
+
+    # ------------------------------------------------------------------ op level
+    def residual_norms(self):
+        out = np.empty(5)
+        self._check(self._lib.ipm_residual_norms(self._h, _ptr(out)), "ipm_residual_norms")
+        return dict(rb=out[0], rc=out[1], gap=out[2], b=out[3], c=out[4])
+
+    def residuals(self):
+        rb, rc = np.empty(self.m), np.empty(self.n)
+        self._check(self._lib.ipm_get_residuals(self._h, _ptr(rb), _ptr(rc)), "ipm_get_residuals")
+        return _col(rb), _col(rc)
+
+    def assemble_normal(self):
+        self._check(self._lib.ipm_assemble_normal(self._h), "ipm_assemble_normal")
+
+    def get_M(self):
+        M = np.empty((self.m, self.m))
+        self._check(self._lib.ipm_get_M(self._h, _ptr(M)), "ipm_get_M")
+        return M
+
+    def factor(self, tau: float = 1e-30) -> int:
+        nf = ctypes.c_int(0)
+        self._check(self._lib.ipm_factor(self._h, float(tau), ctypes.byref(nf)), "ipm_factor")
+        return nf.value
+
+    def direction(self, kind: int, fetch: bool = True):
+        if not fetch:
+            self._check(self._lib.ipm_direction(self._h, int(kind), None, None, None), "ipm_direction")
+            return None
+        dx, dy, ds = np.empty(self.n), np.empty(self.m), np.empty(self.n)
+        self._check(self._lib.ipm_direction(self._h, int(kind), _ptr(dx), _ptr(dy), _ptr(ds)), "ipm_direction")
+        return _col(dx), _col(dy), _col(ds)
+
+    def ratio_test(self, kind: int, eta: float = ETA):
+        a = np.empty(2)
+        self._check(self._lib.ipm_ratio_test(self._h, int(kind), float(eta), _ptr(a)), "ipm_ratio_test")
+        return float(a[0]), float(a[1])
+
+    def sigma(self):
+        out = np.empty(3)
+        self._check(self._lib.ipm_sigma(self._h, _ptr(out)), "ipm_sigma")
+        return float(out[0]), float(out[1]), float(out[2])
+
+    def update(self, alpha_p: float, alpha_d: float):
+        self._check(self._lib.ipm_update(self._h, float(alpha_p), float(alpha_d)), "ipm_update")
+
+    # ------------------------------------------------------------------ solve level
+    def solve(self, tol: float = 1e-8, max_iter: int = 5000, y0_is_one: bool = True, cTlb: float = 0.0) -> Result:
+        x, y, s = np.empty(self.n), np.empty(self.m), np.empty(self.n)
+        obj = ctypes.c_double(0.0)
+        it = ctypes.c_int(0)
+        st = ctypes.c_int(0)
+        res = np.empty(5)
+        self._check(self._lib.ipm_solve(self._h, float(tol), int(max_iter), int(bool(y0_is_one)), _ptr(x), _ptr(y),
+                                        _ptr(s), ctypes.byref(obj), ctypes.byref(it), ctypes.byref(st), _ptr(res)),
+                    "ipm_solve")
+        return Result(x=_col(x), y=_col(y), s=_col(s), objective=float(obj.value) - float(cTlb),
+                      iterations=it.value, status=_lib.STATUS.get(st.value, str(st.value)),
+                      residuals=dict(rb=res[0], rc=res[1], gap=res[2], b=res[3], c=res[4]))
+
+
+# ====================================================================== reference-shaped functions
+def solve(A, b, c, tol: float = 1e-8, cTlb: float = 0.0, device: int = 0, max_iter: int = 5000,
+          y0_is_one: bool | None = None) -> Result:
+    """Load `benchmarks/*.mat`-style data, solve min c^T x s.t. Ax=b, x>=0; returns x, objective, iterations."""
+    is_sparse = _sp is not None and _sp.issparse(A)
+    if y0_is_one is None:
+        y0_is_one = is_sparse          # sparse driver starts y=1 (sparse_interior.py:193-200), dense y=0 (main.py:287-302)
+    with NewtonStep(A, b, c, device=device) as ns:
+        return ns.solve(tol=tol, max_iter=max_iter, y0_is_one=y0_is_one, cTlb=cTlb)
+
+
+def interior_sparse(A, b, c, cTlb, tol: float = 1e-20, device: int = 0, return_result: bool = False):
+    """Drop-in for main.interior_sparse (main.py:760-815): returns `c^T x - cTlb` as a float, NaN on breakdown.
+
+    Same defaults as the reference, including tol=1e-20 ("never converged") and the
+    5000-iteration cap."""
+    cTlb = float(np.asarray(cTlb).ravel()[0]) if np.size(cTlb) else 0.0
+    res = solve(A, b, c, tol=tol, cTlb=cTlb, device=device, max_iter=5000, y0_is_one=True)
+    print("k:\n", res.iterations)        # main.py:814
+    return res if return_result else res.objective
+
+
+def interior(A, b, c, tol: float = 1e-20, device: int = 0) -> Result:
+    """Dense driver (main.py:707-757): A list/ndarray, b and c 1-D, start y=0, cap 50000.
+    The reference prints x, k and the objective and returns None; the Result carries them instead."""
+    return solve(np.asarray(A, dtype=np.float64), b, c, tol=tol, device=device, max_iter=50000, y0_is_one=False)
+
+
+_cache = {}
+
+
+def _cached_step(A, b, c, device=0) -> NewtonStep:
+    key = (id(A), id(b), id(c), device)
+    ns = _cache.get("ns") if _cache.get("key") == key else None
+    if ns is None:
+        old = _cache.get("ns")
+        if old is not None:
+            old.close()
+        ns = NewtonStep(A, b, c, device=device)
+        _cache["key"], _cache["ns"] = key, ns
+    return ns
+
+
+def check_optimality(A, b, c, x, y, s, e1, e2, e3, options="sparse", device: int = 0) -> bool:
+    """main.py:162-173: True = not optimal yet."""
+    ns = _cached_step(A, b, c, device)
+    ns.set_state(x, y, s)
+    r = ns.residual_norms()
+    return bool(e1 * (1 + r["b"]) < r["rb"] or e2 * (1 + r["c"]) < r["rc"] or e3 < r["gap"])
+
+
+def _prepare(ns, x, y, s, tau):
+    ns.set_state(x, y, s)
+    ns.residual_norms()
+    ns.assemble_normal()
+    ns.factor(tau)
+
+
+def direction_predicted_sparse(A, b, c, x, y, s, method="gpu", device: int = 0, tau: float = 1e-30):
+    """main.py:197-229 with the linear algebra on the GPU (`method` kept for signature compatibility)."""
+    ns = _cached_step(A, b, c, device)
+    _prepare(ns, x, y, s, tau)
+    return ns.direction(0)
+
+
+def direction_corrected_sparse(A, b, c, x, y, s, delta_x_aff, delta_y_aff, delta_s_aff, method="gpu",
+                               device: int = 0, tau: float = 1e-30):
+    """main.py:247-277.  The predictor direction is recomputed on the device from (x, y, s): it is a pure
+    function of the iterate, so the caller's delta_*_aff are only checked for shape."""
+    ns = _cached_step(A, b, c, device)
+    _prepare(ns, x, y, s, tau)
+    ns.direction(0, fetch=False)
+    ns.sigma()
+    return ns.direction(1)
+
+
+def newton_iteration(ns: NewtonStep, tau: float = 1e-30):
+    """One predictor-corrector iteration through the op-level entry points (main.py:781-805); returns the
+    per-op results so parity tests can compare each against the oracle."""
+    norms = ns.residual_norms()
+    ns.assemble_normal()
+    nfixed = ns.factor(tau)
+    dxa, dya, dsa = ns.direction(0)
+    alpha_aff = ns.ratio_test(0)
+    mu_aff, mu, sigma = ns.sigma()
+    dx, dy, ds = ns.direction(1)
+    alpha = ns.ratio_test(1, ETA)
+    ns.update(*alpha)
+    return dict(norms=norms, nfixed=nfixed, dx_aff=dxa, dy_aff=dya, ds_aff=dsa, alpha_aff=alpha_aff,
+                mu_aff=mu_aff, mu=mu, sigma=sigma, dx=dx, dy=dy, ds=ds, alpha=alpha)
