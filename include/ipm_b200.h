@@ -131,6 +131,17 @@ int ipm_solve_batched_dense_d(int device_ordinal, int B, int m, int n,
                               void *work_d, int *iterations_run);
 int64_t ipm_batched_workspace_bytes(int B, int m, int n);
 
+/* Phase timing of the batched solver (bench.py roofline): CUDA events on the solve stream around the four
+ * phases of every lockstep iteration.  ms/calls index: 0 residual pass, 1 SYRK (dmma_nt_kernel, one launch
+ * per call), 2 Cholesky, 3 both solves (rhs, triangular solves, direction/update).  lp_iterations = sum over
+ * lockstep iterations of the number of LPs still active.  ipm_profile_enable resets the accumulators. */
+int ipm_profile_enable(int on);
+int ipm_profile_read(double ms[4], int64_t calls[4], int64_t *lp_iterations);
+
+/* Issue-rate ceiling of DMMA.8x8x4 on this device in TFLOP/s (register-only loop, ~10 ms): the FP64
+ * tensor-core peak the SYRK/Cholesky roofline fractions are quoted against. */
+double ipm_measure_dmma_peak(int device_ordinal);
+
 /* ---------------------------------------------------------------- stand-alone kernels (roofline benches, parity)
  * C_lower = A diag(d) A^T for a dense row-major device matrix (the SYRK of main.py:224). */
 int ipm_syrk_d(int device_ordinal, int m, int n, const double *A_d, int64_t lda, const double *d_d,

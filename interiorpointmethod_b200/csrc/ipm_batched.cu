@@ -39,6 +39,58 @@ struct BatchArgs {
 };
 
 // ---------------------------------------------------------------------------------------------
+// Phase profiler (bench.py roofline): CUDA events on the solve stream around each phase of every lockstep
+// iteration; elapsed times are read after the solve has drained, so the timed region is not perturbed.
+enum Phase { PH_RESID = 0, PH_SYRK, PH_CHOL, PH_SOLVE, PH_COUNT };
+struct Profiler {
+    bool enabled = false;
+    double ms[PH_COUNT] = {0, 0, 0, 0};
+    int64_t calls[PH_COUNT] = {0, 0, 0, 0};
+    int64_t lp_iterations = 0;            // sum over lockstep iterations of the number of active LPs
+    std::vector<cudaEvent_t> pool;
+    std::vector<int> marks;               // phase id that ENDS at event i+1 (event i starts it)
+    size_t used = 0;
+    cudaEvent_t next() {
+        if (used == pool.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            pool.push_back(e);
+        }
+        return pool[used++];
+    }
+    void begin(cudaStream_t st) { if (enabled) cudaEventRecord(next(), st); }
+    void end_phase(int ph, cudaStream_t st) {
+        if (!enabled) return;
+        cudaEventRecord(next(), st);
+        marks.push_back(ph);
+    }
+    // events were recorded as: begin, end_phase, end_phase, ... per segment; segments are delimited by begin()
+    std::vector<size_t> seg_starts;
+    void collect() {
+        if (!enabled) { used = 0; marks.clear(); seg_starts.clear(); return; }
+        size_t mi = 0;
+        for (size_t sgi = 0; sgi < seg_starts.size(); ++sgi) {
+            const size_t e0 = seg_starts[sgi];
+            const size_t e1 = (sgi + 1 < seg_starts.size()) ? seg_starts[sgi + 1] : used;
+            for (size_t e = e0; e + 1 < e1; ++e, ++mi) {
+                float t = 0.f;
+                if (cudaEventElapsedTime(&t, pool[e], pool[e + 1]) == cudaSuccess) {
+                    ms[marks[mi]] += t;
+                    calls[marks[mi]] += 1;
+                }
+            }
+        }
+        used = 0; marks.clear(); seg_starts.clear();
+    }
+    void segment(cudaStream_t st) {
+        if (!enabled) return;
+        seg_starts.push_back(used);
+        cudaEventRecord(next(), st);
+    }
+};
+Profiler g_prof;
+
+// ---------------------------------------------------------------------------------------------
 // One pass over A_i: Ax (warp per row) and A^T y (column partial sums per warp, combined in warp order).
 template <int NPL>
 __global__ void __launch_bounds__(KB_NT) kb_residual(const BatchArgs a) {
@@ -370,11 +422,15 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
     int it = 0;
     for (;;) {
         IPM_CUDA_OK(cudaMemsetAsync(a.n_active, 0, sizeof(unsigned), st));
+        g_prof.segment(st);
         kb_residual<NPL><<<B, KB_NT, smem_col, st>>>(a);
         count_launch();
+        g_prof.end_phase(PH_RESID, st);
         IPM_CUDA_OK(cudaMemcpyAsync(w.h_nact, a.n_active, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
         IPM_CUDA_OK(cudaStreamSynchronize(st));
         if (*w.h_nact == 0) break;
+        if (g_prof.enabled) g_prof.lp_iterations += *w.h_nact;
+        g_prof.segment(st);
         DmmaArgs g;
         g.P = a.A; g.ldp = n; g.strideP = (int64_t)m * n;
         g.Q = a.A; g.ldq = n; g.strideQ = (int64_t)m * n;
@@ -382,7 +438,9 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
         g.C = w.M; g.ldc = w.ldm; g.strideC = (int64_t)m * w.ldm;
         g.rowsP = m; g.rowsQ = m; g.K = n; g.lower_only = 1; g.active = a.active;
         IPM_TRY((dmma_nt_launch<128, 128, 4, 2, 0>(g, B, st)));
+        g_prof.end_phase(PH_SYRK, st);
         IPM_TRY((potrf_blocked<64, 256, 128>(w.M, w.ldm, (int64_t)m * w.ldm, m, B, a.scal, S_COUNT, tau, a.active, st)));
+        g_prof.end_phase(PH_CHOL, st);
         TrsvBatchedArgs t;
         t.L = w.M; t.ldm = w.ldm; t.strideM = (int64_t)m * w.ldm; t.v = a.rhs; t.strideV = m; t.m = m;
         t.active = a.active;
@@ -392,6 +450,7 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
             kb_dir<NPL><<<B, KB_NT, smem_col, st>>>(a, kind);
             count_launch(3);
         }
+        g_prof.end_phase(PH_SOLVE, st);
         IPM_TRY(launch_check());
         ++it;
     }
@@ -429,6 +488,23 @@ int check_shape(int B, int m, int n) {
 
 extern "C" {
 
+int ipm_profile_enable(int on) {
+    g_prof.collect();
+    g_prof.enabled = on != 0;
+    for (int i = 0; i < PH_COUNT; ++i) { g_prof.ms[i] = 0.0; g_prof.calls[i] = 0; }
+    g_prof.lp_iterations = 0;
+    return IPM_OK;
+}
+
+int ipm_profile_read(double ms[4], int64_t calls[4], int64_t* lp_iterations) {
+    for (int i = 0; i < PH_COUNT; ++i) {
+        if (ms) ms[i] = g_prof.ms[i];
+        if (calls) calls[i] = g_prof.calls[i];
+    }
+    if (lp_iterations) *lp_iterations = g_prof.lp_iterations;
+    return IPM_OK;
+}
+
 int64_t ipm_batched_workspace_bytes(int B, int m, int n) {
     if (B <= 0 || m <= 0 || n <= 0) return 0;
     return ws_bytes(B, m, n);
@@ -453,6 +529,7 @@ int ipm_solve_batched_dense_d(int device_ordinal, int B, int m, int n, const dou
         IPM_CUDA_OK(cudaStreamSynchronize(0));
         return IPM_OK;
     }();
+    g_prof.collect();
     if (h_nact) cudaFreeHost(h_nact);
     if (own) cudaFree(own);
     return rc;
@@ -525,6 +602,7 @@ int ipm_solve_batched_dense(int device_ordinal, int B, int m, int n, const doubl
         IPM_CUDA_OK(cudaStreamSynchronize(s_copy));
         return IPM_OK;
     }();
+    g_prof.collect();
     for (int i = 0; i < 2; ++i) {
         if (dA[i]) cudaFree(dA[i]);
         if (db[i]) cudaFree(db[i]);

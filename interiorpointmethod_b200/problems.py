@@ -32,7 +32,7 @@ def create_problem_from_mps(name, root="benchmarks"):
 
 
 def load_golden_problem(name):
-    """Frozen copy written by oracle/make_golden.py from the reference's loader output."""
+    """Frozen copy of the reference loader output (written by the golden-vector script, see tests/golden/)."""
     from scipy import sparse
 
     z = np.load(os.path.join(GOLDEN_PROBLEMS, name + ".npz"))

@@ -1,0 +1,140 @@
+"""CPU tests: the oracle (oracle/ipm_oracle.py) against the golden vectors frozen from the unmodified
+reference (tests/golden/, made by oracle/make_golden.py) and against the known answers in the reference's
+source (ex1 = -775 main.py:1253, ex2 = -15000 main.py:1261, Netlib optima main.py:1417-1516)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ipm_oracle as orc
+from interiorpointmethod_b200 import load_golden_problem
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+# small enough that the as-written full-KKT path finishes in about a second each
+KKT_SET = ["AFIRO", "SC50A", "SC50B", "KB2", "SCSD1", "SHARE2B", "SC105", "STOCFOR1", "SC205", "E226", "SCTAP1"]
+NORMAL_SET = ["AFIRO", "SC50A", "SC50B", "KB2", "SCSD1", "SHARE2B", "SC105", "STOCFOR1", "SCSD6", "SC205", "E226",
+              "SCTAP1", "BANDM", "SCSD8", "GROW7"]
+NETLIB_OPT = {"AFIRO": -4.6475314286e02, "SC50A": -6.4575077059e01, "SC50B": -7.0000000000e01,
+              "SCSD1": 8.6666666743e00, "SHARE2B": -4.1573224074e02, "SC105": -5.2202061212e01,
+              "STOCFOR1": -4.1131976219e04, "SCSD8": 9.0499999993e02, "E226": -1.8751929066e01}
+
+
+@pytest.mark.parametrize("name", KKT_SET)
+def test_as_written_path_reproduces_reference(name, reference_results):
+    """linear='kkt' restates main.py:780-807 with the same scipy calls: same k, same objective up to the
+    last digits (SuperLU's BLAS calls round differently with a different OpenBLAS thread count)."""
+    A, b, c, cTlb = load_golden_problem(name)
+    res = orc.solve(A, b, c, cTlb, tol=1e-8, linear="kkt")
+    g = reference_results[name]
+    assert res["k"] == g["k"]
+    assert abs(res["obj"] - g["obj"]) <= 1e-12 * max(1.0, abs(g["obj"]))
+    assert res["status"] == 0
+
+
+@pytest.mark.parametrize("name", NORMAL_SET)
+def test_normal_equations_path_matches_reference(name, reference_results):
+    """The elimination the GPU uses: iteration count within 1, objective within 1e-8 relative (north_star)."""
+    A, b, c, cTlb = load_golden_problem(name)
+    res = orc.solve(A, b, c, cTlb, tol=1e-8, linear="normal")
+    g = reference_results[name]
+    assert abs(res["k"] - g["k"]) <= 1
+    assert abs(res["obj"] - g["obj"]) <= 1e-8 * max(1.0, abs(g["obj"]))
+    nrb, nrc, gap, nb, nc = orc.residual_norms(*_std(A, b, c), res["x"], res["y"], res["s"])
+    assert nrb <= 1e-8 * (1 + nb) and nrc <= 1e-8 * (1 + nc) and gap <= 1e-8
+
+
+def _std(A, b, c):
+    from scipy import sparse
+    return sparse.csr_matrix(A, dtype=np.float64), orc.as_column(b), orc.as_column(c)
+
+
+@pytest.mark.parametrize("name", sorted(NETLIB_OPT))
+def test_golden_objectives_agree_with_netlib_table(name, reference_results):
+    """main.py:1417-1516 lists the Netlib optima to 11 digits; the frozen reference runs reproduce them."""
+    g = reference_results[name]
+    assert abs(g["obj"] - NETLIB_OPT[name]) <= 2e-8 * max(1.0, abs(NETLIB_OPT[name]))
+
+
+def test_reference_outcome_on_25fv47_is_nan_at_k1(reference_results):
+    assert reference_results["25FV47"]["reference_outcome"] == {"k": 1, "obj": None}
+
+
+EXAMPLES = {
+    "ex1": ([[3, 6, 8], [8, 4, 1]], [30, 44], [-100, -125, -20], -775.0),
+    "ex2": ([[1, 1.5, 1, 0, 0], [2, 3, 0, 1, 0], [2, 1, 0, 0, 1]], [750, 1500, 1000], [-20, -30, 0, 0, 0], -15000.0),
+}
+
+
+@pytest.mark.parametrize("name", sorted(EXAMPLES))
+@pytest.mark.parametrize("linear", ["kkt", "normal"])
+def test_dense_examples(name, linear, dense_results):
+    A, b, c, known = EXAMPLES[name]
+    res = orc.solve(np.array(A, float), b, c, tol=1e-8, max_iter=50000, y0_is_one=False, linear=linear)
+    g = dense_results[name]
+    assert abs(res["k"] - g["k"]) <= (0 if linear == "kkt" else 1)
+    assert abs(res["obj"] - g["obj"]) <= 1e-8 * abs(g["obj"])
+    assert abs(res["obj"] - known) <= 1e-6 * abs(known)
+    if linear == "kkt":
+        assert np.allclose(res["x"].ravel(), g["x"], rtol=0, atol=1e-9 * max(1.0, np.max(np.abs(g["x"]))))
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_synthetic_dense_generator_matches_golden(seed, dense_results):
+    A, b, c = orc.synthetic_dense_lp(64, 128, seed)
+    g = dense_results["synthetic_64x128_seed%d" % seed]
+    for linear in ("kkt", "normal"):
+        res = orc.solve(A, b, c, tol=1e-8, max_iter=50000, y0_is_one=False, linear=linear)
+        assert res["k"] == g["k"]
+        assert abs(res["obj"] - g["obj"]) <= 1e-8 * abs(g["obj"])
+
+
+def test_op_level_vectors_match_reference_trace():
+    """Per-op parity on AFIRO states frozen from the reference (directions via main.py:198-212/250-269,
+    step lengths main.py:305-322/604-626, sigma main.py:588-601)."""
+    A, b, c, _ = load_golden_problem("AFIRO")
+    As, bc, cc = _std(A, b, c)
+    tr = np.load(os.path.join(GOLDEN, "trace_AFIRO.npz"))
+    for k in (0, 1, 10, 40):
+        x, y, s = tr["k%d_x" % k], tr["k%d_y" % k], tr["k%d_s" % k]
+        for linear in ("kkt", "normal"):
+            info = {}
+            orc.newton_iteration(As, bc, cc, x, y, s, linear=linear, info=info)
+            last = info["last"]
+            tol = 1e-12 if linear == "kkt" else 1e-9
+            for key in ("dx_aff", "dy_aff", "ds_aff", "dx", "dy", "ds"):
+                ref = tr["k%d_%s" % (k, key)]
+                err = np.linalg.norm(last[key] - ref) / np.linalg.norm(ref)
+                assert err <= tol, (k, linear, key, err)
+            assert abs(last["sigma"] - float(tr["k%d_sigma" % k])) <= (1e-12 if linear == "kkt" else 1e-8) * abs(float(tr["k%d_sigma" % k]))
+            assert np.allclose(last["alpha"], tr["k%d_alpha" % k], rtol=(1e-12 if linear == "kkt" else 1e-8), atol=0)
+
+
+def test_safeguarded_cholesky_c_and_numpy_agree():
+    rng = np.random.default_rng(0)
+    B = rng.standard_normal((90, 200))
+    M = B @ B.T
+    M[:, 7] = 0.0
+    M[7, :] = 0.0          # an empty row of A gives a zero row/column of M (25FV47)
+    L1, n1 = orc.cholesky_safeguarded_numpy(M)
+    L2, n2 = orc.cholesky_safeguarded(M)
+    assert n1 == n2 == 1
+    assert L1[7, 7] == L2[7, 7] == 1e64
+    mask = np.ones(90, bool); mask[7] = False
+    assert np.allclose(L1[np.ix_(mask, mask)], L2[np.ix_(mask, mask)], rtol=1e-10, atol=1e-12)
+    assert np.allclose((L2 @ L2.T)[np.ix_(mask, mask)], M[np.ix_(mask, mask)], rtol=1e-10, atol=1e-10)
+
+
+def test_ratio_test_edge_cases():
+    x = np.array([[1.0], [2.0], [3.0]])
+    assert orc.ratio_test(x, np.array([[1.0], [0.0], [2.0]])) == 1.0           # nothing blocks
+    assert orc.ratio_test(x, np.array([[-4.0], [1.0], [-3.0]])) == 0.25
+    assert orc.full_stepsize(x, x, np.ones_like(x), np.ones_like(x)) == (0.91, 0.91)   # alpha <= eta always (Q4)
+
+
+def test_nan_input_stops_like_the_reference():
+    """Any NaN makes every comparison in check_optimality False -> loop exits (main.py:170-173, Q5)."""
+    A, b, c = orc.synthetic_dense_lp(8, 16, 0)
+    b = b.copy(); b[0] = np.nan
+    res = orc.solve(A, b, c, tol=1e-8, y0_is_one=False, linear="normal")
+    assert res["k"] == 0 and res["status"] == 2 or res["status"] == 2
