@@ -149,6 +149,11 @@ int ipm_syrk_d(int device_ordinal, int m, int n, const double *A_d, int64_t lda,
 /* In-place safeguarded Cholesky of a dense row-major device matrix (lower). */
 int ipm_potrf_d(int device_ordinal, int m, double *M_d, int64_t ldm, double pivot_rel_thresh, int *n_fixed);
 
+/* In-place safeguarded Cholesky of B row-major device matrices (lower), matrix i at M_d + i*strideM.
+ * m <= 256 runs the fused one-CTA-per-matrix kernel of the batched solver. */
+int ipm_potrf_batched_d(int device_ordinal, int B, int m, double *M_d, int64_t ldm, int64_t strideM,
+                        double pivot_rel_thresh, int *n_fixed_total);
+
 #ifdef __cplusplus
 }
 #endif

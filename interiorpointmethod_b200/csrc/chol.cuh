@@ -325,8 +325,13 @@ inline int potrs_single(const double* L, int64_t ldm, int m, double* rhs, double
 }
 
 // ------------------------------------------------------------------------------------------------
-// Batched solve (one CTA per LP, order m small enough that the vector fits in shared memory):
-// forward then backward sweep in one kernel so L is read from L2 the second time.
+// Batched solve: one light CTA per LP (only the vector lives in shared memory, so 8 CTAs fit on an SM and the
+// serial 32-step diagonal solves of different LPs overlap).  Forward then backward sweep in one kernel, so L is
+// read from L2 the second time.  Per 32-wide block:
+//   forward : r_I -= L[I, 0:I) z      (warp per row, lanes over columns, coalesced)  ;  z_I = L_II^-1 r_I
+//   backward: y_I = L_II^-T z_I       ;  z[0:I) -= L[I, 0:I)^T y_I                   (thread per column, coalesced)
+// The diagonal solves run in warp 0: lane i keeps row i (forward) / column i (backward) of L_II in registers and
+// the freshly solved component is broadcast with a warp shuffle.
 struct TrsvBatchedArgs {
     const double* L; int64_t ldm; int64_t strideM;
     double* v; int64_t strideV;      // rhs in, solution out (length m per LP)
@@ -334,66 +339,85 @@ struct TrsvBatchedArgs {
     const int* active;
 };
 constexpr int TRSVB_NT = 256;
+constexpr int TRSVB_NW = TRSVB_NT / 32;
 
-static __global__ void __launch_bounds__(TRSVB_NT) k_trsv_batched(const TrsvBatchedArgs a) {
-    extern __shared__ __align__(16) double smem[];
-    double* Ls = smem;               // [64][65]
-    double* zs = smem + 64 * 65;     // [64]
-    double* vec = zs + 64;           // [m]
+static __global__ void __launch_bounds__(TRSVB_NT, 6) k_trsv_batched(const TrsvBatchedArgs a) {
+    extern __shared__ __align__(16) double smem_tb[];
+    double* Ls = smem_tb;               // [32][33] current diagonal block
+    double* vec = smem_tb + 32 * 33;    // [m]
     const int bz = blockIdx.x;
     if (a.active && a.active[bz] == 0) return;
     const double* L = a.L + (size_t)bz * a.strideM;
     double* v = a.v + (size_t)bz * a.strideV;
-    const int tid = threadIdx.x, m = a.m;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, m = a.m;
+    const int64_t ldm = a.ldm;
     for (int i = tid; i < m; i += TRSVB_NT) vec[i] = v[i];
-    __syncthreads();
-    // forward
-    for (int j0 = 0; j0 < m; j0 += 64) {
-        const int nb = (m - j0 < 64) ? (m - j0) : 64;
-        const double* Ld = L + (size_t)j0 * a.ldm + j0;
-        for (int idx = tid; idx < nb * nb; idx += TRSVB_NT) {
-            const int i = idx / nb, j = idx - i * nb;
-            Ls[i * 65 + j] = (j <= i) ? Ld[(size_t)i * a.ldm + j] : 0.0;
+    const int nblk = (m + 31) >> 5;
+    auto load_block = [&](int i0, int nb) {
+        for (int idx = tid; idx < 32 * 32; idx += TRSVB_NT) {
+            const int i = idx >> 5, c = idx & 31;
+            Ls[i * 33 + c] = (i < nb && c <= i) ? L[(size_t)(i0 + i) * ldm + i0 + c] : 0.0;
         }
-        if (tid < nb) zs[tid] = vec[j0 + tid];
-        __syncthreads();
-        if (tid < 32) trsv_diag_solve(Ls, zs, nb, false);
-        __syncthreads();
-        if (tid < nb) vec[j0 + tid] = zs[tid];
-        for (int r = j0 + nb + tid; r < m; r += TRSVB_NT) {
-            const double* row = L + (size_t)r * a.ldm + j0;
+    };
+    __syncthreads();
+    // ---- forward
+    for (int I = 0; I < nblk; ++I) {
+        const int i0 = I << 5;
+        const int nb = (m - i0 < 32) ? (m - i0) : 32;
+        load_block(i0, nb);
+        for (int rr = warp; rr < nb && i0 > 0; rr += TRSVB_NW) {
+            const double* row = L + (size_t)(i0 + rr) * ldm;
             double acc = 0.0;
-            for (int k = 0; k < nb; ++k) acc += row[k] * zs[k];
-            vec[r] -= acc;
+            for (int k = lane; k < i0; k += 32) acc += row[k] * vec[k];
+            acc = warp_sum(acc);
+            if (lane == 0) vec[i0 + rr] -= acc;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const bool ok = lane < nb;
+            double x = ok ? vec[i0 + lane] : 0.0;
+            const double inv = ok ? 1.0 / Ls[lane * 33 + lane] : 0.0;
+#pragma unroll 8
+            for (int j = 0; j < nb; ++j) {
+                const double zj = __shfl_sync(0xffffffffu, x * inv, j);
+                if (lane == j) x = zj;
+                else if (lane > j) x -= Ls[lane * 33 + j] * zj;
+            }
+            if (ok) vec[i0 + lane] = x;
         }
         __syncthreads();
     }
-    // backward
-    const int nblk = (m + 63) / 64;
-    for (int jb = nblk - 1; jb >= 0; --jb) {
-        const int j0 = jb * 64;
-        const int nb = (m - j0 < 64) ? (m - j0) : 64;
-        const double* Ld = L + (size_t)j0 * a.ldm + j0;
-        for (int idx = tid; idx < nb * nb; idx += TRSVB_NT) {
-            const int i = idx / nb, j = idx - i * nb;
-            Ls[i * 65 + j] = (j <= i) ? Ld[(size_t)i * a.ldm + j] : 0.0;
+    // ---- backward
+    for (int I = nblk - 1; I >= 0; --I) {
+        const int i0 = I << 5;
+        const int nb = (m - i0 < 32) ? (m - i0) : 32;
+        load_block(i0, nb);
+        __syncthreads();
+        if (warp == 0) {
+            const bool ok = lane < nb;
+            double x = ok ? vec[i0 + lane] : 0.0;
+            const double inv = ok ? 1.0 / Ls[lane * 33 + lane] : 0.0;
+#pragma unroll 8
+            for (int i = nb - 1; i >= 0; --i) {
+                const double yi = __shfl_sync(0xffffffffu, x * inv, i);
+                if (lane == i) x = yi;
+                else if (lane < i) x -= Ls[i * 33 + lane] * yi;
+            }
+            if (ok) vec[i0 + lane] = x;
         }
-        if (tid < nb) zs[tid] = vec[j0 + tid];
         __syncthreads();
-        if (tid < 32) trsv_diag_solve(Ls, zs, nb, true);
-        __syncthreads();
-        if (tid < nb) vec[j0 + tid] = zs[tid];
-        for (int k = tid; k < j0; k += TRSVB_NT) {
-            const double* col = L + (size_t)j0 * a.ldm + k;
+        for (int k = tid; k < i0; k += TRSVB_NT) {
+            const double* col = L + (size_t)i0 * ldm + k;
             double acc = 0.0;
-            for (int i = 0; i < nb; ++i) acc += col[(size_t)i * a.ldm] * zs[i];
+#pragma unroll 8
+            for (int i = 0; i < nb; ++i) acc += col[(size_t)i * ldm] * vec[i0 + i];
             vec[k] -= acc;
         }
         __syncthreads();
     }
     for (int i = tid; i < m; i += TRSVB_NT) v[i] = vec[i];
 }
-inline size_t trsv_batched_smem(int m) { return (size_t)(64 * 65 + 64 + m) * sizeof(double); }
+inline size_t trsv_batched_smem(int m) { return (size_t)(32 * 33 + m) * sizeof(double); }
 #endif
 
 }  // namespace ipm

@@ -1,0 +1,238 @@
+// Fused per-LP Cholesky for the batched workload: ONE CTA factors one m x m matrix (m <= KBC_MAX_M) end to
+// end, left-looking in 32-wide panels, so the whole factorisation of all LPs is a single launch and M makes one
+// trip through HBM (read) and one back (L).  Replaces solve_linear (main.py:176-182) on M (main.py:223-224).
+//
+// Panel J (columns j0..j0+31, rows j0..m-1):
+//   1. update   acc = M[:, J] - sum_{K<J} L[:, K] L[J, K]^T     DMMA.8x8x4; A/B fragments are read straight
+//                                                                from global memory (L written by this CTA a
+//                                                                moment ago -> L1/L2 hits), accumulators = panel
+//   2. diag     32x32 block: warp 0, lane i owns row i in registers, finished rows are broadcast through
+//               shared memory; pivot safeguard p <= tau*maxdiag or NaN -> 1e128;
+//               the pivot itself travels by warp shuffle
+//   3. trsm     rows below: one thread per row, forward substitution against the diagonal block
+//   4. store    panel -> global L
+#pragma once
+#include "common.cuh"
+
+namespace ipm {
+
+constexpr int KBC_NT = 256;
+constexpr int KBC_NW = KBC_NT / 32;
+constexpr int KBC_MAX_M = 256;      // 4 row tiles x 4 column tiles of accumulators per warp
+constexpr int KBC_LD = 33;
+constexpr int KBC_LDT = 34;     // transposed diagonal block: even so that 128-bit reads stay aligned
+
+struct CholBatchedArgs {
+    double* M; int64_t ldm; int64_t strideM;
+    double* scal; int64_t strideScal;     // S_MAXDIAG, S_NFIXED written per LP (nullable)
+    double tau;
+    int m;
+    const int* active;
+};
+
+inline size_t kbc_smem_bytes(int m) {
+    const int below = m > 32 ? m - 32 : 0;
+    return (size_t)(32 * KBC_LD + 2 + 32 * KBC_LDT + (size_t)below * KBC_LD + 32) * sizeof(double);
+}
+
+#ifdef __CUDACC__
+static __global__ void __launch_bounds__(KBC_NT, 2) kb_chol(const CholBatchedArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    double* D = smem;                       // [32][33]  diagonal block, becomes L_JJ
+    double* DT = smem + 32 * KBC_LD + 2;    // [32][34]  DT[k][j] = L_JJ[j][k]  (+2 doubles: 16-byte aligned)
+    double* Ps = DT + 32 * KBC_LDT;         // [m-32][33] rows below the diagonal block
+    __shared__ double sh[32];
+    __shared__ double dg[32];               // diagonal of L_JJ
+    __shared__ double s_maxdiag;
+    __shared__ int s_nfix;
+    const int lp = blockIdx.x;
+    if (a.active && a.active[lp] == 0) return;
+    const int m = a.m, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    double* Mb = a.M + (size_t)lp * a.strideM;
+    const int64_t ldm = a.ldm;
+
+    // max_i M_ii (threshold of the safeguard)
+    {
+        double v = red_identity<RED_MAX>();
+        for (int i = tid; i < m; i += KBC_NT) v = fmax(v, Mb[(size_t)i * ldm + i]);
+        v = block_red<RED_MAX>(v, sh);
+        if (tid == 0) { s_maxdiag = v; s_nfix = 0; }
+        __syncthreads();
+    }
+    const double thresh = a.tau * s_maxdiag;
+
+    for (int j0 = 0; j0 < m; j0 += 32) {
+        const int nb = (m - j0 < 32) ? (m - j0) : 32;
+        const int rows = m - j0;                       // panel rows (diag block included)
+        const int ntile = (rows + 7) >> 3;             // 8-row tiles
+        // ---------------- 1. left-looking update on the tensor pipe
+        double acc[4][4][2];
+#pragma unroll
+        for (int ti = 0; ti < 4; ++ti) {
+            const int tile = warp + ti * KBC_NW;
+            const int r = j0 + tile * 8 + g;
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+                const int c = j0 + ni * 8 + 2 * t;
+                double v0 = 0.0, v1 = 0.0;
+                if (tile < ntile && r < m) {
+                    if (c < m) v0 = Mb[(size_t)r * ldm + c];
+                    if (c + 1 < m) v1 = Mb[(size_t)r * ldm + c + 1];
+                }
+                acc[ti][ni][0] = v0;
+                acc[ti][ni][1] = v1;
+            }
+        }
+        if (j0 > 0) {
+            // 32-bit element offsets of the fragment rows (m*ldm <= 2^16 here); rows past the end read row j0
+            // and are multiplied by zero
+            int aoff[4], boff[4];
+            double amul[4], bmul[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int tile = warp + i * KBC_NW;
+                const int ra = j0 + tile * 8 + g;
+                const bool oka = (tile < ntile) && (ra < m);
+                aoff[i] = (oka ? ra : j0) * (int)ldm + t;
+                amul[i] = oka ? -1.0 : 0.0;               // negated: acc += (-a) b
+                const int rb = j0 + i * 8 + g;
+                const bool okb = rb < m;
+                boff[i] = (okb ? rb : j0) * (int)ldm + t;
+                bmul[i] = okb ? 1.0 : 0.0;
+            }
+#pragma unroll 1
+            for (int k = 0; k < j0; k += 8) {
+                double af0[4], bf0[4], af1[4], bf1[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    af0[i] = Mb[aoff[i] + k];
+                    bf0[i] = Mb[boff[i] + k];
+                    af1[i] = Mb[aoff[i] + k + 4];
+                    bf1[i] = Mb[boff[i] + k + 4];
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    af0[i] *= amul[i]; af1[i] *= amul[i];
+                    bf0[i] *= bmul[i]; bf1[i] *= bmul[i];
+                }
+#pragma unroll
+                for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) dmma884(acc[ti][ni][0], acc[ti][ni][1], af0[ti], bf0[ni]);
+#pragma unroll
+                for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) dmma884(acc[ti][ni][0], acc[ti][ni][1], af1[ti], bf1[ni]);
+            }
+        }
+        // accumulators -> shared panel
+#pragma unroll
+        for (int ti = 0; ti < 4; ++ti) {
+            const int tile = warp + ti * KBC_NW;
+            if (tile >= ntile) continue;
+            const int pr = tile * 8 + g;                // row inside the panel
+            double* dst = (pr < 32) ? (D + pr * KBC_LD) : (Ps + (size_t)(pr - 32) * KBC_LD);
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+                dst[ni * 8 + 2 * t] = acc[ti][ni][0];
+                dst[ni * 8 + 2 * t + 1] = acc[ti][ni][1];
+            }
+        }
+        __syncthreads();
+        // ---------------- 2. diagonal block: right-looking, whole CTA, two barriers per column.
+        //                     The pivot is read by every thread as a shared-memory broadcast.
+        for (int j = 0; j < nb; ++j) {
+            double p = D[j * KBC_LD + j];                      // never overwritten: L_jj goes to dg[j]
+            const bool bad = !(p > thresh);
+            if (bad) p = kPivotBig;
+            const double l = sqrt(p);
+            if (tid == 0) { dg[j] = l; if (bad) s_nfix += 1; }
+            if (tid > j && tid < nb) D[tid * KBC_LD + j] = D[tid * KBC_LD + j] / l;
+            __syncthreads();
+            // trailing update of the block: rows by lane, columns strided over the warps
+            const int i = lane;
+            if (i > j && i < nb) {
+                const double lij = D[i * KBC_LD + j];
+                for (int k = j + 1 + warp; k <= i; k += KBC_NW) D[i * KBC_LD + k] -= lij * D[k * KBC_LD + j];
+            }
+            __syncthreads();
+        }
+        // transposed copy of L_JJ so that the substitution below reads 8 consecutive entries per step
+        for (int idx = tid; idx < 32 * 32; idx += KBC_NT) {
+            const int jj = idx >> 5, kk = idx & 31;
+            DT[kk * KBC_LDT + jj] = (jj < nb && kk < jj) ? D[jj * KBC_LD + kk] : ((jj < nb && kk == jj) ? dg[jj] : 0.0);
+        }
+        __syncthreads();
+        // ---------------- 3. rows below the block: x L_JJ^T = a, one thread per row, 8 columns at a time
+        const int below = rows - 32;
+        for (int r = tid; r < below; r += KBC_NT) {
+            double* pr = Ps + (size_t)r * KBC_LD;
+#pragma unroll 1
+            for (int jb = 0; jb < 32; jb += 8) {
+                double x8[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) x8[q] = pr[jb + q];
+#pragma unroll 4
+                for (int k = 0; k < jb; ++k) {
+                    const double xk = pr[k];
+                    const double2* lp = reinterpret_cast<const double2*>(DT + k * KBC_LDT + jb);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const double2 lv = lp[q];
+                        x8[2 * q] -= xk * lv.x;
+                        x8[2 * q + 1] -= xk * lv.y;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const double* lrow = DT + (jb + q) * KBC_LDT + jb;
+                    const double xv = x8[q] / lrow[q];
+                    x8[q] = xv;
+#pragma unroll
+                    for (int q2 = q + 1; q2 < 8; ++q2) x8[q2] -= xv * lrow[q2];
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) pr[jb + q] = x8[q];
+            }
+        }
+        __syncthreads();
+        // ---------------- 4. panel -> global
+        for (int idx = tid; idx < rows * 32; idx += KBC_NT) {
+            const int pr = idx >> 5, c = idx & 31;
+            if (c >= nb) continue;
+            if (pr < 32) {
+                if (c < pr) Mb[(size_t)(j0 + pr) * ldm + j0 + c] = D[pr * KBC_LD + c];
+                else if (c == pr) Mb[(size_t)(j0 + pr) * ldm + j0 + c] = dg[pr];
+            } else {
+                Mb[(size_t)(j0 + pr) * ldm + j0 + c] = Ps[(size_t)(pr - 32) * KBC_LD + c];
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && a.scal) {
+        a.scal[(size_t)lp * a.strideScal + S_MAXDIAG] = s_maxdiag;
+        a.scal[(size_t)lp * a.strideScal + S_NFIXED] = (double)s_nfix;
+    }
+}
+
+inline int potrf_batched_fused(double* M, int64_t ldm, int64_t strideM, int m, int batch, double* scal,
+                               int64_t strideScal, double tau, const int* active, cudaStream_t st) {
+    static int configured_dev = -1;
+    int dev = 0;
+    IPM_CUDA_OK(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+        IPM_CUDA_OK(cudaFuncSetAttribute(kb_chol, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kbc_smem_bytes(KBC_MAX_M)));
+        configured_dev = dev;
+    }
+    CholBatchedArgs a;
+    a.M = M; a.ldm = ldm; a.strideM = strideM; a.scal = scal; a.strideScal = strideScal; a.tau = tau; a.m = m;
+    a.active = active;
+    kb_chol<<<batch, KBC_NT, kbc_smem_bytes(m), st>>>(a);
+    count_launch();
+    return launch_check();
+}
+#endif
+
+}  // namespace ipm

@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) dmma_nt_kernel(const DmmaArgs
     const bool vecQ = ((a.ldq & 1) == 0) && ((reinterpret_cast<uintptr_t>(Q) & 15) == 0);
 
     double2 pr[PV], qr[QV];
+    double2 sc = make_double2(1.0, 1.0);   // diag(d) entries of the tile in flight
 
     auto load_tile = [&](int kt) {
         const int k = kt * DMMA_BK + lk;
@@ -87,7 +88,6 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) dmma_nt_kernel(const DmmaArgs
             }
             pr[i] = v;
         }
-        double2 sc = make_double2(1.0, 1.0);
         if (dv) {
             sc = make_double2(0.0, 0.0);
             if (k < K) sc.x = dv[k];
@@ -104,7 +104,6 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) dmma_nt_kernel(const DmmaArgs
                     else { v.x = p[0]; v.y = p[1]; }
                 } else if (k < K) v.x = p[0];
             }
-            if (dv) { v.x *= sc.x; v.y *= sc.y; }
             qr[i] = v;
         }
     };
@@ -114,9 +113,14 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) dmma_nt_kernel(const DmmaArgs
 #pragma unroll
         for (int i = 0; i < PV; ++i)
             *reinterpret_cast<double2*>(ps + (lrow + i * (NT / 8)) * LD + lk) = pr[i];
+        // the diag(d) scaling is applied here, AFTER the MMAs of the previous tile, so the global loads issued
+        // by load_tile stay in flight during the tensor work instead of being waited on immediately
 #pragma unroll
-        for (int i = 0; i < QV; ++i)
-            *reinterpret_cast<double2*>(qs + (lrow + i * (NT / 8)) * LD + lk) = qr[i];
+        for (int i = 0; i < QV; ++i) {
+            double2 v = qr[i];
+            if (dv) { v.x *= sc.x; v.y *= sc.y; }
+            *reinterpret_cast<double2*>(qs + (lrow + i * (NT / 8)) * LD + lk) = v;
+        }
     };
 
     double acc[MI][NI][2];

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "chol.cuh"
+#include "chol_batched.cuh"
 #include "common.cuh"
 #include "dmma_gemm.cuh"
 
@@ -439,7 +440,11 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
         g.rowsP = m; g.rowsQ = m; g.K = n; g.lower_only = 1; g.active = a.active;
         IPM_TRY((dmma_nt_launch<128, 128, 4, 2, 0>(g, B, st)));
         g_prof.end_phase(PH_SYRK, st);
-        IPM_TRY((potrf_blocked<64, 256, 128>(w.M, w.ldm, (int64_t)m * w.ldm, m, B, a.scal, S_COUNT, tau, a.active, st)));
+        if (m <= KBC_MAX_M)
+            IPM_TRY(potrf_batched_fused(w.M, w.ldm, (int64_t)m * w.ldm, m, B, a.scal, S_COUNT, tau, a.active, st));
+        else
+            IPM_TRY((potrf_blocked<64, 256, 128>(w.M, w.ldm, (int64_t)m * w.ldm, m, B, a.scal, S_COUNT, tau,
+                                                 a.active, st)));
         g_prof.end_phase(PH_CHOL, st);
         TrsvBatchedArgs t;
         t.L = w.M; t.ldm = w.ldm; t.strideM = (int64_t)m * w.ldm; t.v = a.rhs; t.strideV = m; t.m = m;
@@ -503,6 +508,30 @@ int ipm_profile_read(double ms[4], int64_t calls[4], int64_t* lp_iterations) {
     }
     if (lp_iterations) *lp_iterations = g_prof.lp_iterations;
     return IPM_OK;
+}
+
+int ipm_potrf_batched_d(int device_ordinal, int B, int m, double* M_d, int64_t ldm, int64_t strideM,
+                        double pivot_rel_thresh, int* n_fixed_total) {
+    if (!M_d) return IPM_ERR_ARG;
+    if (B <= 0 || m <= 0 || ldm < m || (ldm & 1) || strideM < (int64_t)m * ldm) return IPM_ERR_SHAPE;
+    IPM_CUDA_OK(cudaSetDevice(device_ordinal));
+    double* scal = nullptr;
+    IPM_CUDA_OK(cudaMalloc(&scal, (size_t)B * S_COUNT * sizeof(double)));
+    int rc = (m <= KBC_MAX_M)
+                 ? potrf_batched_fused(M_d, ldm, strideM, m, B, scal, S_COUNT, pivot_rel_thresh, nullptr, 0)
+                 : potrf_blocked<64, 256, 128>(M_d, ldm, strideM, m, B, scal, S_COUNT, pivot_rel_thresh, nullptr, 0);
+    if (rc == IPM_OK) {
+        std::vector<double> hs((size_t)B * S_COUNT);
+        cudaError_t e = cudaMemcpy(hs.data(), scal, hs.size() * sizeof(double), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { g_last_error = cudaGetErrorString(e); rc = IPM_ERR_CUDA; }
+        else if (n_fixed_total) {
+            int tot = 0;
+            for (int i = 0; i < B; ++i) tot += (int)hs[(size_t)i * S_COUNT + S_NFIXED];
+            *n_fixed_total = tot;
+        }
+    }
+    cudaFree(scal);
+    return rc;
 }
 
 int64_t ipm_batched_workspace_bytes(int B, int m, int n) {

@@ -137,4 +137,4 @@ def test_nan_input_stops_like_the_reference():
     A, b, c = orc.synthetic_dense_lp(8, 16, 0)
     b = b.copy(); b[0] = np.nan
     res = orc.solve(A, b, c, tol=1e-8, y0_is_one=False, linear="normal")
-    assert res["k"] == 0 and res["status"] == 2 or res["status"] == 2
+    assert res["k"] <= 1 and res["status"] == 2
