@@ -130,8 +130,8 @@ static __global__ void __launch_bounds__(KBC_NT, 2) kb_chol(const CholBatchedArg
 #pragma unroll
         for (int ti = 0; ti < 4; ++ti) {
             const int tile = warp + ti * KBC_NW;
-            if (tile >= ntile) continue;
             const int pr = tile * 8 + g;                // row inside the panel
+            if (tile >= ntile || pr >= rows) continue;
             double* dst = (pr < 32) ? (D + pr * KBC_LD) : (Ps + (size_t)(pr - 32) * KBC_LD);
 #pragma unroll
             for (int ni = 0; ni < 4; ++ni) {

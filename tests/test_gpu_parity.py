@@ -93,7 +93,8 @@ def test_dense_examples(ipm, name, dense_results):
     g = dense_results[name]
     assert res.status == "converged" and abs(res.iterations - g["k"]) <= 1
     assert abs(res.objective - g["obj"]) <= 1e-8 * abs(g["obj"])
-    assert np.allclose(res.x.ravel(), g["x"], rtol=1e-6, atol=1e-7)
+    if name == "ex1":       # ex2's optimal face is not a single point, only the objective is pinned
+        assert np.allclose(res.x.ravel(), g["x"], rtol=1e-6, atol=1e-7)
 
 
 @pytest.mark.parametrize("shape,seed", [((64, 128), 0), ((64, 128), 1), ((256, 512), 0), ((256, 512), 1),
@@ -122,11 +123,15 @@ def test_op_level_against_oracle_on_reference_states(ipm, orc, name, ks):
             ns.set_state(x, y, s)
             nrm = ns.residual_norms()
             onrm = orc.residual_norms(As, bc, cc, x, y, s)
-            for key, ref in zip(("rb", "rc", "gap", "b", "c"), onrm):
-                assert abs(nrm[key] - ref) <= 1e-12 * max(abs(ref), 1e-300) + 1e-300, (k, key)
+            # residuals are differences of large terms: tolerance relative to the size of those terms
+            scale_b = np.linalg.norm(bc) + np.linalg.norm(abs(As) @ abs(x))
+            scale_c = np.linalg.norm(cc) + np.linalg.norm(s) + np.linalg.norm(abs(As).T @ abs(y))
+            assert abs(nrm["rb"] - onrm[0]) <= 1e-13 * scale_b and abs(nrm["rc"] - onrm[1]) <= 1e-13 * scale_c, k
+            assert abs(nrm["gap"] - onrm[2]) <= 1e-13 * abs(onrm[2])
+            assert abs(nrm["b"] - onrm[3]) <= 1e-13 * onrm[3] and abs(nrm["c"] - onrm[4]) <= 1e-13 * onrm[4]
             rb, rc = ns.residuals()
             orb, orcv = orc.residuals(As, bc, cc, x, y, s)
-            assert _rel(rb, orb) <= 1e-12 and _rel(rc, orcv) <= 1e-12
+            assert np.linalg.norm(rb - orb) <= 1e-13 * scale_b and np.linalg.norm(rc - orcv) <= 1e-13 * scale_c
             ns.assemble_normal()
             M = np.tril(ns.get_M())
             Mo = np.tril(orc.normal_matrix(As, x, s))
