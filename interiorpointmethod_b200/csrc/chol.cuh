@@ -9,6 +9,7 @@
 #pragma once
 #include "common.cuh"
 #include "dmma_gemm.cuh"
+#include "dmma_ws.cuh"
 
 namespace ipm {
 
@@ -185,7 +186,7 @@ inline int potrf_blocked(double* M, int64_t ldm, int64_t strideM, int m, int bat
             g.dvec = nullptr; g.strideD = 0;
             g.C = M + (size_t)(j0 + NB) * ldm + (j0 + NB); g.ldc = ldm; g.strideC = strideM;
             g.rowsP = below; g.rowsQ = below; g.K = NB; g.lower_only = 1; g.active = active;
-            IPM_TRY((dmma_nt_launch<128, 128, 4, 2, 1>(g, batch, st)));
+            IPM_TRY((dmma_syrk_auto<1>(g, batch, st)));
         }
     }
     return launch_check();

@@ -42,7 +42,7 @@ static __global__ void __launch_bounds__(KBC_NT, 2) kb_chol(const CholBatchedArg
     double* DT = smem + 32 * KBC_LD + 2;    // [32][34]  DT[k][j] = L_JJ[j][k]  (+2 doubles: 16-byte aligned)
     double* Ps = DT + 32 * KBC_LDT;         // [m-32][33] rows below the diagonal block
     __shared__ double sh[32];
-    __shared__ double dg[32];               // diagonal of L_JJ
+    __shared__ double dg[32];               // 1 / diagonal of L_JJ
     __shared__ double s_maxdiag;
     __shared__ int s_nfix;
     const int lp = blockIdx.x;
@@ -66,67 +66,69 @@ static __global__ void __launch_bounds__(KBC_NT, 2) kb_chol(const CholBatchedArg
         const int nb = (m - j0 < 32) ? (m - j0) : 32;
         const int rows = m - j0;                       // panel rows (diag block included)
         const int ntile = (rows + 7) >> 3;             // 8-row tiles
-        // ---------------- 1. left-looking update on the tensor pipe
+        // ---------------- 1. left-looking update on the tensor pipe: acc = -M[:,J] + sum_K L[:,K] L[J,K]^T,
+        //                     the sign is flipped when the accumulators are spilled to the shared panel.
         double acc[4][4][2];
+        bool aok[4], bok[4];
+        int aoff[4], boff[4];            // 32-bit element offsets (m*ldm <= 2^16 here)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int tile = warp + i * KBC_NW;
+            const int ra = j0 + tile * 8 + g;
+            aok[i] = (tile < ntile) && (ra < m);
+            aoff[i] = (aok[i] ? ra : j0) * (int)ldm + t;
+            const int rb = j0 + i * 8 + g;
+            bok[i] = rb < m;
+            boff[i] = (bok[i] ? rb : j0) * (int)ldm + t;
+        }
 #pragma unroll
         for (int ti = 0; ti < 4; ++ti) {
-            const int tile = warp + ti * KBC_NW;
-            const int r = j0 + tile * 8 + g;
+            const int r = j0 + (warp + ti * KBC_NW) * 8 + g;
 #pragma unroll
             for (int ni = 0; ni < 4; ++ni) {
                 const int c = j0 + ni * 8 + 2 * t;
                 double v0 = 0.0, v1 = 0.0;
-                if (tile < ntile && r < m) {
-                    if (c < m) v0 = Mb[(size_t)r * ldm + c];
-                    if (c + 1 < m) v1 = Mb[(size_t)r * ldm + c + 1];
+                if (aok[ti]) {
+                    if (c < m) v0 = -Mb[(size_t)r * ldm + c];
+                    if (c + 1 < m) v1 = -Mb[(size_t)r * ldm + c + 1];
                 }
                 acc[ti][ni][0] = v0;
                 acc[ti][ni][1] = v1;
             }
         }
         if (j0 > 0) {
-            // 32-bit element offsets of the fragment rows (m*ldm <= 2^16 here); rows past the end read row j0
-            // and are multiplied by zero
-            int aoff[4], boff[4];
-            double amul[4], bmul[4];
+            // software pipeline over 4-column steps: the loads of step s+1 are issued before the 16 MMAs of step s
+            double af0[4], bf0[4], af1[4], bf1[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int tile = warp + i * KBC_NW;
-                const int ra = j0 + tile * 8 + g;
-                const bool oka = (tile < ntile) && (ra < m);
-                aoff[i] = (oka ? ra : j0) * (int)ldm + t;
-                amul[i] = oka ? -1.0 : 0.0;               // negated: acc += (-a) b
-                const int rb = j0 + i * 8 + g;
-                const bool okb = rb < m;
-                boff[i] = (okb ? rb : j0) * (int)ldm + t;
-                bmul[i] = okb ? 1.0 : 0.0;
+                af0[i] = aok[i] ? Mb[aoff[i]] : 0.0;
+                bf0[i] = bok[i] ? Mb[boff[i]] : 0.0;
             }
 #pragma unroll 1
             for (int k = 0; k < j0; k += 8) {
-                double af0[4], bf0[4], af1[4], bf1[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    af0[i] = Mb[aoff[i] + k];
-                    bf0[i] = Mb[boff[i] + k];
-                    af1[i] = Mb[aoff[i] + k + 4];
-                    bf1[i] = Mb[boff[i] + k + 4];
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    af0[i] *= amul[i]; af1[i] *= amul[i];
-                    bf0[i] *= bmul[i]; bf1[i] *= bmul[i];
+                    af1[i] = aok[i] ? Mb[aoff[i] + k + 4] : 0.0;
+                    bf1[i] = bok[i] ? Mb[boff[i] + k + 4] : 0.0;
                 }
 #pragma unroll
                 for (int ti = 0; ti < 4; ++ti)
 #pragma unroll
                     for (int ni = 0; ni < 4; ++ni) dmma884(acc[ti][ni][0], acc[ti][ni][1], af0[ti], bf0[ni]);
+                if (k + 8 < j0) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        af0[i] = aok[i] ? Mb[aoff[i] + k + 8] : 0.0;
+                        bf0[i] = bok[i] ? Mb[boff[i] + k + 8] : 0.0;
+                    }
+                }
 #pragma unroll
                 for (int ti = 0; ti < 4; ++ti)
 #pragma unroll
                     for (int ni = 0; ni < 4; ++ni) dmma884(acc[ti][ni][0], acc[ti][ni][1], af1[ti], bf1[ni]);
             }
         }
-        // accumulators -> shared panel
+        // accumulators -> shared panel (sign restored)
 #pragma unroll
         for (int ti = 0; ti < 4; ++ti) {
             const int tile = warp + ti * KBC_NW;
@@ -135,33 +137,48 @@ static __global__ void __launch_bounds__(KBC_NT, 2) kb_chol(const CholBatchedArg
             double* dst = (pr < 32) ? (D + pr * KBC_LD) : (Ps + (size_t)(pr - 32) * KBC_LD);
 #pragma unroll
             for (int ni = 0; ni < 4; ++ni) {
-                dst[ni * 8 + 2 * t] = acc[ti][ni][0];
-                dst[ni * 8 + 2 * t + 1] = acc[ti][ni][1];
+                dst[ni * 8 + 2 * t] = -acc[ti][ni][0];
+                dst[ni * 8 + 2 * t + 1] = -acc[ti][ni][1];
             }
         }
         __syncthreads();
-        // ---------------- 2. diagonal block: right-looking, whole CTA, two barriers per column.
-        //                     The pivot is read by every thread as a shared-memory broadcast.
-        for (int j = 0; j < nb; ++j) {
-            double p = D[j * KBC_LD + j];                      // never overwritten: L_jj goes to dg[j]
-            const bool bad = !(p > thresh);
-            if (bad) p = kPivotBig;
-            const double l = sqrt(p);
-            if (tid == 0) { dg[j] = l; if (bad) s_nfix += 1; }
-            if (tid > j && tid < nb) D[tid * KBC_LD + j] = D[tid * KBC_LD + j] / l;
-            __syncthreads();
-            // trailing update of the block: rows by lane, columns strided over the warps
+        // ---------------- 2. diagonal block: warp 0 only, lane i owns row i (left-looking), no block barriers.
+        //                     Column j: every lane forms its entry, the pivot travels by warp shuffle from lane j,
+        //                     the safeguard p <= tau*maxdiag or NaN -> 1e128 is applied by all lanes alike.
+        if (warp == 0) {
             const int i = lane;
-            if (i > j && i < nb) {
-                const double lij = D[i * KBC_LD + j];
-                for (int k = j + 1 + warp; k <= i; k += KBC_NW) D[i * KBC_LD + k] -= lij * D[k * KBC_LD + j];
+            int nfix = 0;
+            for (int j = 0; j < nb; ++j) {
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                const double* ri = D + i * KBC_LD;
+                const double* rj = D + j * KBC_LD;       // broadcast reads
+                int k = 0;
+                for (; k + 3 < j; k += 4) {
+                    s0 += ri[k] * rj[k];
+                    s1 += ri[k + 1] * rj[k + 1];
+                    s2 += ri[k + 2] * rj[k + 2];
+                    s3 += ri[k + 3] * rj[k + 3];
+                }
+                for (; k < j; ++k) s0 += ri[k] * rj[k];
+                const double v = ri[j] - ((s0 + s1) + (s2 + s3));
+                double p = __shfl_sync(0xffffffffu, v, j);
+                const bool bad = !(p > thresh);
+                if (bad) p = kPivotBig;
+                const double l = sqrt(p);
+                const double inv = 1.0 / l;
+                if (i == j) { D[j * KBC_LD + j] = l; dg[j] = inv; nfix += bad ? 1 : 0; }
+                else if (i > j && i < nb) D[i * KBC_LD + j] = v * inv;
+                __syncwarp();
             }
-            __syncthreads();
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) nfix += __shfl_xor_sync(0xffffffffu, nfix, o);
+            if (lane == 0) s_nfix += nfix;               // lane j counted its own pivot
         }
+        __syncthreads();
         // transposed copy of L_JJ so that the substitution below reads 8 consecutive entries per step
         for (int idx = tid; idx < 32 * 32; idx += KBC_NT) {
             const int jj = idx >> 5, kk = idx & 31;
-            DT[kk * KBC_LDT + jj] = (jj < nb && kk < jj) ? D[jj * KBC_LD + kk] : ((jj < nb && kk == jj) ? dg[jj] : 0.0);
+            DT[kk * KBC_LDT + jj] = (jj < nb && kk <= jj) ? D[jj * KBC_LD + kk] : 0.0;
         }
         __syncthreads();
         // ---------------- 3. rows below the block: x L_JJ^T = a, one thread per row, 8 columns at a time
@@ -187,7 +204,7 @@ static __global__ void __launch_bounds__(KBC_NT, 2) kb_chol(const CholBatchedArg
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const double* lrow = DT + (jb + q) * KBC_LDT + jb;
-                    const double xv = x8[q] / lrow[q];
+                    const double xv = x8[q] * dg[jb + q];
                     x8[q] = xv;
 #pragma unroll
                     for (int q2 = q + 1; q2 < 8; ++q2) x8[q2] -= xv * lrow[q2];
@@ -202,8 +219,7 @@ static __global__ void __launch_bounds__(KBC_NT, 2) kb_chol(const CholBatchedArg
             const int pr = idx >> 5, c = idx & 31;
             if (c >= nb) continue;
             if (pr < 32) {
-                if (c < pr) Mb[(size_t)(j0 + pr) * ldm + j0 + c] = D[pr * KBC_LD + c];
-                else if (c == pr) Mb[(size_t)(j0 + pr) * ldm + j0 + c] = dg[pr];
+                if (c <= pr) Mb[(size_t)(j0 + pr) * ldm + j0 + c] = D[pr * KBC_LD + c];
             } else {
                 Mb[(size_t)(j0 + pr) * ldm + j0 + c] = Ps[(size_t)(pr - 32) * KBC_LD + c];
             }

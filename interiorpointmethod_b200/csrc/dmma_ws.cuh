@@ -1,0 +1,242 @@
+// Warp-specialised, persistent FP64 tensor-core "NT" product (second generation of dmma_gemm.cuh).
+//
+//   C[i][j] (op)= sum_k P[i][k] * d[k] * Q[j][k]          lower 128x128 tiles only, batch in the tile index
+//
+// One CTA per SM loops over output tiles.  Warp 8 is the PRODUCER: it streams 128x16 operand slabs (and the
+// matching 16 entries of d) from global memory into a 4-stage shared-memory ring with cp.async (LDGSTS, 16 B
+// per lane, zero-fill for ragged edges) and signals each stage through an mbarrier
+// (cp.async.mbarrier.arrive.noinc).  Warps 0-7 are CONSUMERS: each owns a 32x64 block of the tile
+// (64 DMMA.8x8x4 accumulators), waits on the stage's "full" barrier, applies diag(d) to its A fragments,
+// issues the MMAs and releases the stage on its "empty" barrier.  No __syncthreads in steady state, the
+// producer runs ahead across tile boundaries so the epilogue of tile i overlaps the loads of tile i+1.
+// tcgen05/TMEM are not usable here: the f64 kind does not exist (ptxas rejects tcgen05.mma.kind::f64).
+#pragma once
+#include "common.cuh"
+#include "dmma_gemm.cuh"
+
+namespace ipm {
+
+constexpr int WS_BM = 128, WS_BN = 128, WS_BK = 16, WS_LD = 20, WS_STAGES = 4;
+constexpr int WS_CONSUMER_WARPS = 8;
+constexpr int WS_THREADS = (WS_CONSUMER_WARPS + 1) * 32;
+
+constexpr size_t ws_smem_bytes() {
+    return (size_t)WS_STAGES * ((WS_BM + WS_BN) * WS_LD + WS_BK) * sizeof(double) + 2 * WS_STAGES * sizeof(uint64_t);
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes)
+                 : "memory");
+}
+
+// tile index inside one matrix -> (bi, bj) with bj <= bi
+__device__ __forceinline__ void tri_decode(int t, int& bi, int& bj) {
+    int i = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((i + 1) * (i + 2) / 2 <= t) ++i;
+    while (i * (i + 1) / 2 > t) --i;
+    bi = i;
+    bj = t - i * (i + 1) / 2;
+}
+
+template <int EPI, bool SCALE>
+__global__ void __launch_bounds__(WS_THREADS, 1) dmma_ws_kernel(const DmmaArgs a, int ntri, int total_tiles) {
+    constexpr int LD = WS_LD, S = WS_STAGES;
+    extern __shared__ __align__(128) unsigned char ws_raw[];
+    double* Ps = reinterpret_cast<double*>(ws_raw);            // [S][128][LD]
+    double* Qs = Ps + S * WS_BM * LD;                          // [S][128][LD]
+    double* Ds = Qs + S * WS_BN * LD;                          // [S][16]
+    uint64_t* full = reinterpret_cast<uint64_t*>(Ds + S * WS_BK);
+    uint64_t* empty = full + S;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full + s, 32);                   // 32 producer lanes, one noinc arrival each
+            mbar_init(empty + s, WS_CONSUMER_WARPS);   // one arrival per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int K = a.K;
+    const int nk = (K + WS_BK - 1) / WS_BK;
+    uint32_t it = 0;                                    // ring position, continues across tiles
+
+    if (warp == WS_CONSUMER_WARPS) {
+        // ------------------------------------------------------------------ producer
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int z = tile / ntri;
+            if (a.active && a.active[z] == 0) continue;
+            int bi, bj;
+            tri_decode(tile - z * ntri, bi, bj);
+            const double* P = a.P + (size_t)z * a.strideP;
+            const double* Q = a.Q + (size_t)z * a.strideQ;
+            const double* dv = SCALE ? a.dvec + (size_t)z * a.strideD : nullptr;
+            const int row0 = bi * WS_BM, col0 = bj * WS_BN;
+            for (int kt = 0; kt < nk; ++kt, ++it) {
+                const int s = it % S;
+                mbar_wait(empty + s, ((it / S) & 1) ^ 1);
+                double* ps = Ps + s * WS_BM * LD;
+                double* qs = Qs + s * WS_BN * LD;
+                const int kq = (lane & 7) * 2;          // this lane's column pair inside the slab
+                const int k = kt * WS_BK + kq;
+                const uint32_t kbytes = (k + 1 < K) ? 16u : ((k < K) ? 8u : 0u);
+#pragma unroll 8
+                for (int j = 0; j < 32; ++j) {
+                    const int r = (lane >> 3) + 4 * j;
+                    const int gr = row0 + r;
+                    const uint32_t nb = (gr < a.rowsP) ? kbytes : 0u;
+                    const double* src = nb ? P + (size_t)gr * a.ldp + k : P;
+                    cp_async16_zfill(ps + r * LD + kq, src, nb);
+                }
+#pragma unroll 8
+                for (int j = 0; j < 32; ++j) {
+                    const int r = (lane >> 3) + 4 * j;
+                    const int gr = col0 + r;
+                    const uint32_t nb = (gr < a.rowsQ) ? kbytes : 0u;
+                    const double* src = nb ? Q + (size_t)gr * a.ldq + k : Q;
+                    cp_async16_zfill(qs + r * LD + kq, src, nb);
+                }
+                if (SCALE && lane < 8) cp_async16_zfill(Ds + s * WS_BK + kq, kbytes ? dv + k : dv, kbytes);
+                cp_async_mbar_arrive_noinc(full + s);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ consumers: 4 x 2 warps, 32 x 64 each
+        constexpr int MI = 4, NI = 8;
+        const int g = lane >> 2, t = lane & 3;
+        const int wm0 = (warp >> 1) * 32, wn0 = (warp & 1) * 64;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int z = tile / ntri;
+            if (a.active && a.active[z] == 0) continue;
+            int bi, bj;
+            tri_decode(tile - z * ntri, bi, bj);
+            double acc[MI][NI][2];
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+            for (int kt = 0; kt < nk; ++kt, ++it) {
+                const int s = it % S;
+                mbar_wait(full + s, (it / S) & 1);
+                const double* ps = Ps + s * WS_BM * LD + (wm0 + g) * LD + t;
+                const double* qs = Qs + s * WS_BN * LD + (wn0 + g) * LD + t;
+                const double* ds = Ds + s * WS_BK + t;
+#pragma unroll
+                for (int kk = 0; kk < WS_BK; kk += 4) {
+                    double af[MI], bf[NI];
+#pragma unroll
+                    for (int i = 0; i < MI; ++i) af[i] = ps[i * 8 * LD + kk];
+#pragma unroll
+                    for (int j = 0; j < NI; ++j) bf[j] = qs[j * 8 * LD + kk];
+                    if (SCALE) {
+                        const double dk = ds[kk];
+#pragma unroll
+                        for (int i = 0; i < MI; ++i) af[i] *= dk;
+                    }
+#pragma unroll
+                    for (int i = 0; i < MI; ++i)
+#pragma unroll
+                        for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty + s);
+            }
+            // epilogue (the producer is already filling the ring for the next tile)
+            double* C = a.C + (size_t)z * a.strideC;
+            const int row0 = bi * WS_BM, col0 = bj * WS_BN;
+#pragma unroll
+            for (int i = 0; i < MI; ++i) {
+                const int r = row0 + wm0 + i * 8 + g;
+                if (r >= a.rowsP) continue;
+#pragma unroll
+                for (int j = 0; j < NI; ++j) {
+                    const int c = col0 + wn0 + j * 8 + 2 * t;
+                    if (c >= a.rowsQ) continue;
+                    double* cp = C + (size_t)r * a.ldc + c;
+                    if (c + 1 < a.rowsQ) {
+                        double2 v;
+                        if (EPI == 1) {
+                            v = *reinterpret_cast<double2*>(cp);
+                            v.x -= acc[i][j][0];
+                            v.y -= acc[i][j][1];
+                        } else {
+                            v = make_double2(acc[i][j][0], acc[i][j][1]);
+                        }
+                        *reinterpret_cast<double2*>(cp) = v;
+                    } else {
+                        if (EPI == 1) cp[0] -= acc[i][j][0];
+                        else cp[0] = acc[i][j][0];
+                    }
+                }
+            }
+        }
+    }
+}
+
+// true when the operands satisfy the 16-byte alignment the cp.async path and the vector epilogue need
+inline bool ws_eligible(const DmmaArgs& a) {
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    return al16(a.P) && al16(a.Q) && al16(a.C) && (a.ldp % 2 == 0) && (a.ldq % 2 == 0) && (a.ldc % 2 == 0) &&
+           (a.strideP % 2 == 0) && (a.strideQ % 2 == 0) && (a.strideC % 2 == 0) &&
+           (!a.dvec || (al16(a.dvec) && a.strideD % 2 == 0)) && a.lower_only && a.rowsP == a.rowsQ;
+}
+
+template <int EPI, bool SCALE>
+inline int dmma_ws_launch(const DmmaArgs& a, int batch, cudaStream_t st) {
+    static int configured_dev = -1;
+    int dev = 0;
+    IPM_CUDA_OK(cudaGetDevice(&dev));
+    auto kern = dmma_ws_kernel<EPI, SCALE>;
+    if (configured_dev != dev) {
+        IPM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_smem_bytes()));
+        configured_dev = dev;
+    }
+    if (a.rowsP <= 0 || batch <= 0 || a.K <= 0) return IPM_OK;
+    const int T = ceil_div(a.rowsP, WS_BM);
+    const int ntri = T * (T + 1) / 2;
+    const int64_t total = (int64_t)ntri * batch;
+    if (total > 0x7fffffff) return IPM_ERR_SHAPE;
+    const int grid = (int)std::min<int64_t>(total, kNumSMs);
+    kern<<<grid, WS_THREADS, ws_smem_bytes(), st>>>(a, ntri, (int)total);
+    count_launch();
+    return launch_check();
+}
+
+// SYRK-shaped product with the best available kernel: the warp-specialised one when the alignment allows,
+// the register-staged one (arbitrary leading dimensions) otherwise.
+template <int EPI>
+inline int dmma_syrk_auto(const DmmaArgs& a, int batch, cudaStream_t st) {
+    if (ws_eligible(a)) {
+        if (a.dvec) return dmma_ws_launch<EPI, true>(a, batch, st);
+        return dmma_ws_launch<EPI, false>(a, batch, st);
+    }
+    return dmma_nt_launch<128, 128, 4, 2, EPI>(a, batch, st);
+}
+#endif
+
+}  // namespace ipm

@@ -16,6 +16,7 @@
 #include "chol_batched.cuh"
 #include "common.cuh"
 #include "dmma_gemm.cuh"
+#include "dmma_ws.cuh"
 
 using namespace ipm;
 
@@ -438,7 +439,7 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
         g.dvec = a.d; g.strideD = n;
         g.C = w.M; g.ldc = w.ldm; g.strideC = (int64_t)m * w.ldm;
         g.rowsP = m; g.rowsQ = m; g.K = n; g.lower_only = 1; g.active = a.active;
-        IPM_TRY((dmma_nt_launch<128, 128, 4, 2, 0>(g, B, st)));
+        IPM_TRY((dmma_syrk_auto<0>(g, B, st)));
         g_prof.end_phase(PH_SYRK, st);
         if (m <= KBC_MAX_M)
             IPM_TRY(potrf_batched_fused(w.M, w.ldm, (int64_t)m * w.ldm, m, B, a.scal, S_COUNT, tau, a.active, st));

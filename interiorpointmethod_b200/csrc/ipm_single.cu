@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "dense.cuh"
 #include "dmma_gemm.cuh"
+#include "dmma_ws.cuh"
 #include "sparse.cuh"
 #include "vec.cuh"
 
@@ -172,7 +173,7 @@ int assemble_step(ipm_handle* h) {
         g.dvec = h->d; g.strideD = 0;
         g.C = h->M; g.ldc = h->ldm; g.strideC = 0;
         g.rowsP = h->m; g.rowsQ = h->m; g.K = h->n; g.lower_only = 1; g.active = nullptr;
-        H_TRY((dmma_nt_launch<128, 128, 4, 2, 0>(g, 1, h->st)));
+        H_TRY((dmma_syrk_auto<0>(g, 1, h->st)));
     } else {
         H_CUDA(cudaMemsetAsync(h->M, 0, (size_t)h->m * h->ldm * sizeof(double), h->st));
         k_scale_vals<<<std::max(1, std::min<int>(ceil_div(h->nnz, 256), 8 * kNumSMs)), 256, 0, h->st>>>(
@@ -591,7 +592,7 @@ int ipm_syrk_d(int device_ordinal, int m, int n, const double* A_d, int64_t lda,
     g.dvec = d_d; g.strideD = 0;
     g.C = M_d; g.ldc = ldm; g.strideC = 0;
     g.rowsP = m; g.rowsQ = m; g.K = n; g.lower_only = 1; g.active = nullptr;
-    IPM_TRY((dmma_nt_launch<128, 128, 4, 2, 0>(g, 1, 0)));
+    IPM_TRY((dmma_syrk_auto<0>(g, 1, 0)));
     return IPM_OK;
 }
 
