@@ -313,6 +313,9 @@ def main():
     calls = (ctypes.c_int64 * 4)()
     lp_it = ctypes.c_int64(0)
     lib.ipm_profile_read(ms, calls, ctypes.byref(lp_it))
+    trace_ms = (ctypes.c_double * 512)()
+    trace_ph = (ctypes.c_int * 512)()
+    ntr = lib.ipm_profile_last(trace_ms, trace_ph, 512)
     lib.ipm_profile_enable(0)
     obj_all, it_all, st_all = (t.cpu().numpy() for t in out)
 
@@ -352,6 +355,8 @@ def main():
         "flops_per_launch": syrk_flops / max(1, calls[1]), "avg_launch_ms": ms[1] / max(1, calls[1]),
         "launches": int(calls[1]),
         "share_of_step": syrk_s / t_dev if t_dev > 0 else None,
+        "last_step_syrk_ms_per_iteration": [round(trace_ms[i], 3) for i in range(min(ntr, 512)) if trace_ph[i] == 1],
+        "last_step_cholesky_ms_per_iteration": [round(trace_ms[i], 3) for i in range(min(ntr, 512)) if trace_ph[i] == 2],
         "phase_ms_per_step": {"residual_pass": ms[0] / args.steps, "syrk": ms[1] / args.steps,
                               "cholesky": ms[2] / args.steps, "solves_and_update": ms[3] / args.steps,
                               "sum": phase_total / args.steps * 1e3},

@@ -137,6 +137,8 @@ int64_t ipm_batched_workspace_bytes(int B, int m, int n);
  * lockstep iterations of the number of LPs still active.  ipm_profile_enable resets the accumulators. */
 int ipm_profile_enable(int on);
 int ipm_profile_read(double ms[4], int64_t calls[4], int64_t *lp_iterations);
+/* Intervals of the most recent batched solve in launch order (phase index as above); returns their number. */
+int ipm_profile_last(double *ms, int *phase, int cap);
 
 /* Issue-rate ceiling of DMMA.8x8x4 on this device in TFLOP/s (register-only loop, ~10 ms): the FP64
  * tensor-core peak the SYRK/Cholesky roofline fractions are quoted against. */

@@ -47,6 +47,7 @@ SYMBOLS = {
     "ipm_batched_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
     "ipm_profile_enable": (c_int, [c_int]),
     "ipm_profile_read": (c_int, [c_void_p, c_void_p, POINTER(c_int64)]),
+    "ipm_profile_last": (c_int, [c_void_p, c_void_p, c_int]),
     "ipm_measure_dmma_peak": (c_double, [c_int]),
     "ipm_syrk_d": (c_int, [c_int, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_int64]),
     "ipm_potrf_d": (c_int, [c_int, c_int, c_void_p, c_int64, c_double, _ip]),

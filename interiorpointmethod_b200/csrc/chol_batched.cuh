@@ -113,8 +113,10 @@ static __global__ void __launch_bounds__(KBC_NT, 2) kb_chol(const CholBatchedArg
                 }
 #pragma unroll
                 for (int ti = 0; ti < 4; ++ti)
+                    if (warp + ti * KBC_NW < ntile) {           // warp-uniform: no MMAs for row tiles past the end
 #pragma unroll
-                    for (int ni = 0; ni < 4; ++ni) dmma884(acc[ti][ni][0], acc[ti][ni][1], af0[ti], bf0[ni]);
+                        for (int ni = 0; ni < 4; ++ni) dmma884(acc[ti][ni][0], acc[ti][ni][1], af0[ti], bf0[ni]);
+                    }
                 if (k + 8 < j0) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -124,8 +126,10 @@ static __global__ void __launch_bounds__(KBC_NT, 2) kb_chol(const CholBatchedArg
                 }
 #pragma unroll
                 for (int ti = 0; ti < 4; ++ti)
+                    if (warp + ti * KBC_NW < ntile) {           // warp-uniform: no MMAs for row tiles past the end
 #pragma unroll
-                    for (int ni = 0; ni < 4; ++ni) dmma884(acc[ti][ni][0], acc[ti][ni][1], af1[ti], bf1[ni]);
+                        for (int ni = 0; ni < 4; ++ni) dmma884(acc[ti][ni][0], acc[ti][ni][1], af1[ti], bf1[ni]);
+                    }
             }
         }
         // accumulators -> shared panel (sign restored)

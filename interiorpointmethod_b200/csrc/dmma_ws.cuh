@@ -2,8 +2,8 @@
 //
 //   C[i][j] (op)= sum_k P[i][k] * d[k] * Q[j][k]          lower 128x128 tiles only, batch in the tile index
 //
-// One CTA per SM loops over output tiles.  Warp 8 is the PRODUCER: it streams 128x16 operand slabs (and the
-// matching 16 entries of d) from global memory into a 4-stage shared-memory ring with cp.async (LDGSTS, 16 B
+// One CTA per SM loops over output tiles.  Warps 8 and 9 are PRODUCERS: they stream the 128x16 slabs of the two
+// operands (and the matching 16 entries of d) from global memory into a 4-stage shared-memory ring with cp.async (LDGSTS, 16 B
 // per lane, zero-fill for ragged edges) and signals each stage through an mbarrier
 // (cp.async.mbarrier.arrive.noinc).  Warps 0-7 are CONSUMERS: each owns a 32x64 block of the tile
 // (64 DMMA.8x8x4 accumulators), waits on the stage's "full" barrier, applies diag(d) to its A fragments,
@@ -18,7 +18,8 @@ namespace ipm {
 
 constexpr int WS_BM = 128, WS_BN = 128, WS_BK = 16, WS_LD = 20, WS_STAGES = 4;
 constexpr int WS_CONSUMER_WARPS = 8;
-constexpr int WS_THREADS = (WS_CONSUMER_WARPS + 1) * 32;
+constexpr int WS_PRODUCER_WARPS = 2;    // warp 8 streams P (and d), warp 9 streams Q
+constexpr int WS_THREADS = (WS_CONSUMER_WARPS + WS_PRODUCER_WARPS) * 32;
 
 constexpr size_t ws_smem_bytes() {
     return (size_t)WS_STAGES * ((WS_BM + WS_BN) * WS_LD + WS_BK) * sizeof(double) + 2 * WS_STAGES * sizeof(uint64_t);
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dmma_ws_kernel(const DmmaArgs a
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(full + s, 32);                   // 32 producer lanes, one noinc arrival each
+            mbar_init(full + s, 32 * WS_PRODUCER_WARPS);   // every producer lane arrives once (noinc)
             mbar_init(empty + s, WS_CONSUMER_WARPS);   // one arrival per consumer warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -86,42 +87,46 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dmma_ws_kernel(const DmmaArgs a
     const int nk = (K + WS_BK - 1) / WS_BK;
     uint32_t it = 0;                                    // ring position, continues across tiles
 
-    if (warp == WS_CONSUMER_WARPS) {
-        // ------------------------------------------------------------------ producer
+    if (warp >= WS_CONSUMER_WARPS) {
+        // ------------------------------------------------------------------ producers
+        const bool isQ = (warp != WS_CONSUMER_WARPS);
+        const int rsub = lane >> 3;                 // row inside a group of 4
+        const int kq = (lane & 7) * 2;              // this lane's column pair inside the slab
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int z = tile / ntri;
             if (a.active && a.active[z] == 0) continue;
             int bi, bj;
             tri_decode(tile - z * ntri, bi, bj);
-            const double* P = a.P + (size_t)z * a.strideP;
-            const double* Q = a.Q + (size_t)z * a.strideQ;
-            const double* dv = SCALE ? a.dvec + (size_t)z * a.strideD : nullptr;
-            const int row0 = bi * WS_BM, col0 = bj * WS_BN;
+            const double* base = isQ ? a.Q + (size_t)z * a.strideQ : a.P + (size_t)z * a.strideP;
+            const int64_t ld = isQ ? a.ldq : a.ldp;
+            const int nrows = isQ ? a.rowsQ : a.rowsP;
+            const int r0 = (isQ ? bj : bi) * WS_BM;
+            const double* dv = (SCALE && !isQ) ? a.dvec + (size_t)z * a.strideD : nullptr;
+            const bool rows_full = r0 + WS_BM <= nrows;
+            const double* src0 = base + (size_t)(r0 + rsub) * ld + kq;
+            const size_t rstep = (size_t)4 * ld;
             for (int kt = 0; kt < nk; ++kt, ++it) {
                 const int s = it % S;
                 mbar_wait(empty + s, ((it / S) & 1) ^ 1);
-                double* ps = Ps + s * WS_BM * LD;
-                double* qs = Qs + s * WS_BN * LD;
-                const int kq = (lane & 7) * 2;          // this lane's column pair inside the slab
-                const int k = kt * WS_BK + kq;
-                const uint32_t kbytes = (k + 1 < K) ? 16u : ((k < K) ? 8u : 0u);
-#pragma unroll 8
-                for (int j = 0; j < 32; ++j) {
-                    const int r = (lane >> 3) + 4 * j;
-                    const int gr = row0 + r;
-                    const uint32_t nb = (gr < a.rowsP) ? kbytes : 0u;
-                    const double* src = nb ? P + (size_t)gr * a.ldp + k : P;
-                    cp_async16_zfill(ps + r * LD + kq, src, nb);
+                double* dst = (isQ ? Qs + s * WS_BN * LD : Ps + s * WS_BM * LD) + rsub * LD + kq;
+                const int k0 = kt * WS_BK;
+                if (rows_full && k0 + WS_BK <= K) {
+                    const double* src = src0 + k0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) cp_async16_zfill(dst + j * 4 * LD, src + j * rstep, 16u);
+                    if (dv != nullptr && lane < 8) cp_async16_zfill(Ds + s * WS_BK + kq, dv + k0 + kq, 16u);
+                } else {
+                    const int k = k0 + kq;
+                    const uint32_t kbytes = (k + 1 < K) ? 16u : ((k < K) ? 8u : 0u);
+#pragma unroll 4
+                    for (int j = 0; j < 32; ++j) {
+                        const int gr = r0 + rsub + 4 * j;
+                        const uint32_t nb = (gr < nrows) ? kbytes : 0u;
+                        const double* src = nb ? base + (size_t)gr * ld + k : base;
+                        cp_async16_zfill(dst + j * 4 * LD, src, nb);
+                    }
+                    if (dv != nullptr && lane < 8) cp_async16_zfill(Ds + s * WS_BK + kq, kbytes ? dv + k : dv, kbytes);
                 }
-#pragma unroll 8
-                for (int j = 0; j < 32; ++j) {
-                    const int r = (lane >> 3) + 4 * j;
-                    const int gr = col0 + r;
-                    const uint32_t nb = (gr < a.rowsQ) ? kbytes : 0u;
-                    const double* src = nb ? Q + (size_t)gr * a.ldq + k : Q;
-                    cp_async16_zfill(qs + r * LD + kq, src, nb);
-                }
-                if (SCALE && lane < 8) cp_async16_zfill(Ds + s * WS_BK + kq, kbytes ? dv + k : dv, kbytes);
                 cp_async_mbar_arrive_noinc(full + s);
             }
         }

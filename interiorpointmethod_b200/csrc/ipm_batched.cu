@@ -68,7 +68,10 @@ struct Profiler {
     }
     // events were recorded as: begin, end_phase, end_phase, ... per segment; segments are delimited by begin()
     std::vector<size_t> seg_starts;
+    std::vector<float> last_ms;           // per recorded interval of the most recent solve
+    std::vector<int> last_ph;
     void collect() {
+        last_ms.clear(); last_ph.clear();
         if (!enabled) { used = 0; marks.clear(); seg_starts.clear(); return; }
         size_t mi = 0;
         for (size_t sgi = 0; sgi < seg_starts.size(); ++sgi) {
@@ -79,6 +82,7 @@ struct Profiler {
                 if (cudaEventElapsedTime(&t, pool[e], pool[e + 1]) == cudaSuccess) {
                     ms[marks[mi]] += t;
                     calls[marks[mi]] += 1;
+                    last_ms.push_back(t); last_ph.push_back(marks[mi]);
                 }
             }
         }
@@ -533,6 +537,15 @@ int ipm_potrf_batched_d(int device_ordinal, int B, int m, double* M_d, int64_t l
     }
     cudaFree(scal);
     return rc;
+}
+
+int ipm_profile_last(double* ms, int* phase, int cap) {
+    const int n = (int)g_prof.last_ms.size();
+    for (int i = 0; i < n && i < cap; ++i) {
+        if (ms) ms[i] = g_prof.last_ms[i];
+        if (phase) phase[i] = g_prof.last_ph[i];
+    }
+    return n;
 }
 
 int64_t ipm_batched_workspace_bytes(int B, int m, int n) {

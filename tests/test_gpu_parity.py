@@ -166,7 +166,10 @@ def test_op_level_against_oracle_on_reference_states(ipm, orc, name, ks):
             assert np.allclose(a_aff, orc.predicted_stepsize(dxa, dsa, x, s), rtol=1e-12, atol=0)
             assert np.allclose(alpha, orc.full_stepsize(x, s, dx, ds), rtol=1e-12, atol=0)
             o_mu_aff, o_mu, o_sigma = orc.sigma_mu(x, s, dxa, dsa)
-            assert abs(sigma - o_sigma) <= 1e-9 * abs(o_sigma) and abs(mu_aff - o_mu_aff) <= 1e-10 * abs(o_mu_aff)
+            # mu_aff is a sum with cancellation down to rounding level on some iterates: compare against mu
+            assert abs(mu_aff - o_mu_aff) <= 1e-12 * abs(o_mu), k
+            if o_mu_aff > 1e-6 * o_mu:
+                assert abs(sigma - o_sigma) <= 1e-5 * abs(o_sigma), k
             if k in STRICT[name]:
                 tol = 1e-6
                 assert _rel(dxa, last["dx_aff"]) <= tol and _rel(dsa, last["ds_aff"]) <= tol, k
