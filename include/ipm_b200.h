@@ -151,6 +151,11 @@ int ipm_syrk_d(int device_ordinal, int m, int n, const double *A_d, int64_t lda,
 /* In-place safeguarded Cholesky of a dense row-major device matrix (lower). */
 int ipm_potrf_d(int device_ordinal, int m, double *M_d, int64_t ldm, double pivot_rel_thresh, int *n_fixed);
 
+/* M_i (lower) = A_i diag(d_i) A_i^T for B contiguous row-major matrices A[B][m][n], d[B][n] (nullable), M[B][m][ldm]:
+ * the SYRK launch of the batched solver, asynchronous on stream 0. */
+int ipm_syrk_batched_d(int device_ordinal, int B, int m, int n, const double *A_d, const double *d_d,
+                       double *M_d, int64_t ldm);
+
 /* In-place safeguarded Cholesky of B row-major device matrices (lower), matrix i at M_d + i*strideM.
  * m <= 256 runs the fused one-CTA-per-matrix kernel of the batched solver. */
 int ipm_potrf_batched_d(int device_ordinal, int B, int m, double *M_d, int64_t ldm, int64_t strideM,

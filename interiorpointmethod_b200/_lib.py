@@ -51,6 +51,7 @@ SYMBOLS = {
     "ipm_measure_dmma_peak": (c_double, [c_int]),
     "ipm_syrk_d": (c_int, [c_int, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_int64]),
     "ipm_potrf_d": (c_int, [c_int, c_int, c_void_p, c_int64, c_double, _ip]),
+    "ipm_syrk_batched_d": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64]),
     "ipm_potrf_batched_d": (c_int, [c_int, c_int, c_int, c_void_p, c_int64, c_int64, c_double, _ip]),
 }
 

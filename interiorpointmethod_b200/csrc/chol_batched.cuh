@@ -43,6 +43,7 @@ static __global__ void __launch_bounds__(KBC_NT, 2) kb_chol(const CholBatchedArg
     double* Ps = DT + 32 * KBC_LDT;         // [m-32][33] rows below the diagonal block
     __shared__ double sh[32];
     __shared__ double dg[32];               // 1 / diagonal of L_JJ
+    __shared__ double colb[32];             // column j of L_JJ while it is being folded into the rows
     __shared__ double s_maxdiag;
     __shared__ int s_nfix;
     const int lp = blockIdx.x;
@@ -146,34 +147,37 @@ static __global__ void __launch_bounds__(KBC_NT, 2) kb_chol(const CholBatchedArg
             }
         }
         __syncthreads();
-        // ---------------- 2. diagonal block: warp 0 only, lane i owns row i (left-looking), no block barriers.
-        //                     Column j: every lane forms its entry, the pivot travels by warp shuffle from lane j,
-        //                     the safeguard p <= tau*maxdiag or NaN -> 1e128 is applied by all lanes alike.
+        // ---------------- 2. diagonal block: warp 0 only, lane i keeps row i in REGISTERS (right-looking).
+        //                     Column j: the pivot travels by warp shuffle from lane j, every lane applies the
+        //                     safeguard p <= tau*maxdiag or NaN -> 1e128 alike, scales its entry by 1/sqrt(p),
+        //                     publishes it in a 32-entry shared column and folds the column into its own row.
         if (warp == 0) {
-            const int i = lane;
+            double arow[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) arow[c] = D[lane * KBC_LD + c];
             int nfix = 0;
-            for (int j = 0; j < nb; ++j) {
-                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-                const double* ri = D + i * KBC_LD;
-                const double* rj = D + j * KBC_LD;       // broadcast reads
-                int k = 0;
-                for (; k + 3 < j; k += 4) {
-                    s0 += ri[k] * rj[k];
-                    s1 += ri[k + 1] * rj[k + 1];
-                    s2 += ri[k + 2] * rj[k + 2];
-                    s3 += ri[k + 3] * rj[k + 3];
+            double my_inv = 1.0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                if (j < nb) {
+                    double p = __shfl_sync(0xffffffffu, arow[j], j);
+                    const bool bad = !(p > thresh);
+                    if (bad) p = kPivotBig;
+                    const double inv = rsqrt(p);
+                    const double lij = (lane == j) ? p * inv : arow[j] * inv;
+                    if (lane == j) { my_inv = inv; nfix += bad ? 1 : 0; }
+                    arow[j] = lij;
+                    colb[lane] = lij;
+                    __syncwarp();
+#pragma unroll
+                    for (int k = j + 1; k < 32; ++k) arow[k] = fma(-lij, colb[k], arow[k]);   // entries k > lane are unused
+                    __syncwarp();
                 }
-                for (; k < j; ++k) s0 += ri[k] * rj[k];
-                const double v = ri[j] - ((s0 + s1) + (s2 + s3));
-                double p = __shfl_sync(0xffffffffu, v, j);
-                const bool bad = !(p > thresh);
-                if (bad) p = kPivotBig;
-                const double l = sqrt(p);
-                const double inv = 1.0 / l;
-                if (i == j) { D[j * KBC_LD + j] = l; dg[j] = inv; nfix += bad ? 1 : 0; }
-                else if (i > j && i < nb) D[i * KBC_LD + j] = v * inv;
-                __syncwarp();
             }
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+                if (c <= lane) D[lane * KBC_LD + c] = arow[c];
+            dg[lane] = my_inv;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) nfix += __shfl_xor_sync(0xffffffffu, nfix, o);
             if (lane == 0) s_nfix += nfix;               // lane j counted its own pivot

@@ -16,7 +16,7 @@
 
 namespace ipm {
 
-constexpr int WS_BM = 128, WS_BN = 128, WS_BK = 16, WS_LD = 20, WS_STAGES = 4;
+constexpr int WS_BM = 128, WS_BN = 128, WS_BK = 16, WS_LD = 20, WS_STAGES = 5;
 constexpr int WS_CONSUMER_WARPS = 8;
 constexpr int WS_PRODUCER_WARPS = 2;    // warp 8 streams P (and d), warp 9 streams Q
 constexpr int WS_THREADS = (WS_CONSUMER_WARPS + WS_PRODUCER_WARPS) * 32;

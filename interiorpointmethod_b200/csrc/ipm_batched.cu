@@ -515,6 +515,20 @@ int ipm_profile_read(double ms[4], int64_t calls[4], int64_t* lp_iterations) {
     return IPM_OK;
 }
 
+int ipm_syrk_batched_d(int device_ordinal, int B, int m, int n, const double* A_d, const double* d_d, double* M_d,
+                       int64_t ldm) {
+    if (!A_d || !M_d) return IPM_ERR_ARG;
+    if (B <= 0 || m <= 0 || n <= 0 || ldm < m) return IPM_ERR_SHAPE;
+    IPM_CUDA_OK(cudaSetDevice(device_ordinal));
+    DmmaArgs g;
+    g.P = A_d; g.ldp = n; g.strideP = (int64_t)m * n;
+    g.Q = A_d; g.ldq = n; g.strideQ = (int64_t)m * n;
+    g.dvec = d_d; g.strideD = n;
+    g.C = M_d; g.ldc = ldm; g.strideC = (int64_t)m * ldm;
+    g.rowsP = m; g.rowsQ = m; g.K = n; g.lower_only = 1; g.active = nullptr;
+    return dmma_syrk_auto<0>(g, B, 0);
+}
+
 int ipm_potrf_batched_d(int device_ordinal, int B, int m, double* M_d, int64_t ldm, int64_t strideM,
                         double pivot_rel_thresh, int* n_fixed_total) {
     if (!M_d) return IPM_ERR_ARG;

