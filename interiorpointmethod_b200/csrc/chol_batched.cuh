@@ -21,6 +21,8 @@ constexpr int KBC_NW = KBC_NT / 32;
 constexpr int KBC_MAX_M = 256;      // 4 row tiles x 4 column tiles of accumulators per warp
 constexpr int KBC_LD = 33;
 constexpr int KBC_LDT = 34;     // transposed diagonal block: even so that 128-bit reads stay aligned
+constexpr int KBC_KC = 64;      // columns of L[J, :] staged in shared memory per chunk of the update
+constexpr int KBC_LDB = KBC_KC + 4;   // 68 = 4 mod 16: conflict-free 64-bit fragment reads
 
 struct CholBatchedArgs {
     double* M; int64_t ldm; int64_t strideM;
@@ -32,15 +34,44 @@ struct CholBatchedArgs {
 
 inline size_t kbc_smem_bytes(int m) {
     const int below = m > 32 ? m - 32 : 0;
-    return (size_t)(32 * KBC_LD + 2 + 32 * KBC_LDT + (size_t)below * KBC_LD + 32) * sizeof(double);
+    return (size_t)(32 * KBC_LD + 2 + 32 * KBC_LDT + 32 * KBC_LDB + (size_t)below * KBC_LD + 32) * sizeof(double);
 }
 
 #ifdef __CUDACC__
+// One chunk of the left-looking update for the NTI row tiles of a warp: A fragments straight from global memory
+// (L written by this CTA a moment ago) with a one-step register prefetch, B fragments from the staged chunk.
+template <int NTI>
+__device__ __forceinline__ void kbc_update_chunk(double (&acc)[4][4][2], const double* __restrict__ Mb,
+                                                 const int (&aoff)[4], const bool (&aok)[4], const double* Bs,
+                                                 int k0, int kc, int g, int t) {
+    double af[NTI], afn[NTI];
+#pragma unroll
+    for (int i = 0; i < NTI; ++i) af[i] = aok[i] ? Mb[aoff[i] + k0] : 0.0;
+    const double* bs = Bs + g * KBC_LDB + t;
+#pragma unroll 2
+    for (int kk = 0; kk < kc; kk += 4) {
+        if (kk + 4 < kc) {
+#pragma unroll
+            for (int i = 0; i < NTI; ++i) afn[i] = aok[i] ? Mb[aoff[i] + k0 + kk + 4] : 0.0;
+        }
+        double bf[4];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) bf[ni] = bs[ni * 8 * KBC_LDB + kk];
+#pragma unroll
+        for (int ti = 0; ti < NTI; ++ti)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) dmma884(acc[ti][ni][0], acc[ti][ni][1], af[ti], bf[ni]);
+#pragma unroll
+        for (int i = 0; i < NTI; ++i) af[i] = afn[i];
+    }
+}
+
 static __global__ void __launch_bounds__(KBC_NT, 2) kb_chol(const CholBatchedArgs a) {
     extern __shared__ __align__(16) double smem[];
     double* D = smem;                       // [32][33]  diagonal block, becomes L_JJ
     double* DT = smem + 32 * KBC_LD + 2;    // [32][34]  DT[k][j] = L_JJ[j][k]  (+2 doubles: 16-byte aligned)
-    double* Ps = DT + 32 * KBC_LDT;         // [m-32][33] rows below the diagonal block
+    double* Bs = DT + 32 * KBC_LDT;         // [32][68]  chunk of the J-block rows of L (B operand of the update)
+    double* Ps = Bs + 32 * KBC_LDB;         // [m-32][33] rows below the diagonal block
     __shared__ double sh[32];
     __shared__ double dg[32];               // 1 / diagonal of L_JJ
     __shared__ double colb[32];             // column j of L_JJ while it is being folded into the rows
@@ -70,17 +101,14 @@ static __global__ void __launch_bounds__(KBC_NT, 2) kb_chol(const CholBatchedArg
         // ---------------- 1. left-looking update on the tensor pipe: acc = -M[:,J] + sum_K L[:,K] L[J,K]^T,
         //                     the sign is flipped when the accumulators are spilled to the shared panel.
         double acc[4][4][2];
-        bool aok[4], bok[4];
-        int aoff[4], boff[4];            // 32-bit element offsets (m*ldm <= 2^16 here)
+        bool aok[4];
+        int aoff[4];                     // 32-bit element offsets (m*ldm <= 2^16 here)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int tile = warp + i * KBC_NW;
             const int ra = j0 + tile * 8 + g;
             aok[i] = (tile < ntile) && (ra < m);
             aoff[i] = (aok[i] ? ra : j0) * (int)ldm + t;
-            const int rb = j0 + i * 8 + g;
-            bok[i] = rb < m;
-            boff[i] = (bok[i] ? rb : j0) * (int)ldm + t;
         }
 #pragma unroll
         for (int ti = 0; ti < 4; ++ti) {
@@ -97,40 +125,21 @@ static __global__ void __launch_bounds__(KBC_NT, 2) kb_chol(const CholBatchedArg
                 acc[ti][ni][1] = v1;
             }
         }
-        if (j0 > 0) {
-            // software pipeline over 4-column steps: the loads of step s+1 are issued before the 16 MMAs of step s
-            double af0[4], bf0[4], af1[4], bf1[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                af0[i] = aok[i] ? Mb[aoff[i]] : 0.0;
-                bf0[i] = bok[i] ? Mb[boff[i]] : 0.0;
+        const int nti = (ntile > warp) ? (ntile - warp + KBC_NW - 1) / KBC_NW : 0;   // row tiles of this warp
+        for (int k0 = 0; k0 < j0; k0 += KBC_KC) {
+            const int kc = (j0 - k0 < KBC_KC) ? (j0 - k0) : KBC_KC;
+            __syncthreads();                                   // previous chunk fully consumed
+            for (int idx = tid; idx < 32 * kc; idx += KBC_NT) {
+                const int r = idx / kc, k = idx - r * kc;
+                Bs[r * KBC_LDB + k] = (j0 + r < m) ? Mb[(size_t)(j0 + r) * ldm + k0 + k] : 0.0;
             }
-#pragma unroll 1
-            for (int k = 0; k < j0; k += 8) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    af1[i] = aok[i] ? Mb[aoff[i] + k + 4] : 0.0;
-                    bf1[i] = bok[i] ? Mb[boff[i] + k + 4] : 0.0;
-                }
-#pragma unroll
-                for (int ti = 0; ti < 4; ++ti)
-                    if (warp + ti * KBC_NW < ntile) {           // warp-uniform: no MMAs for row tiles past the end
-#pragma unroll
-                        for (int ni = 0; ni < 4; ++ni) dmma884(acc[ti][ni][0], acc[ti][ni][1], af0[ti], bf0[ni]);
-                    }
-                if (k + 8 < j0) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        af0[i] = aok[i] ? Mb[aoff[i] + k + 8] : 0.0;
-                        bf0[i] = bok[i] ? Mb[boff[i] + k + 8] : 0.0;
-                    }
-                }
-#pragma unroll
-                for (int ti = 0; ti < 4; ++ti)
-                    if (warp + ti * KBC_NW < ntile) {           // warp-uniform: no MMAs for row tiles past the end
-#pragma unroll
-                        for (int ni = 0; ni < 4; ++ni) dmma884(acc[ti][ni][0], acc[ti][ni][1], af1[ti], bf1[ni]);
-                    }
+            __syncthreads();
+            switch (nti) {
+                case 1: kbc_update_chunk<1>(acc, Mb, aoff, aok, Bs, k0, kc, g, t); break;
+                case 2: kbc_update_chunk<2>(acc, Mb, aoff, aok, Bs, k0, kc, g, t); break;
+                case 3: kbc_update_chunk<3>(acc, Mb, aoff, aok, Bs, k0, kc, g, t); break;
+                case 4: kbc_update_chunk<4>(acc, Mb, aoff, aok, Bs, k0, kc, g, t); break;
+                default: break;
             }
         }
         // accumulators -> shared panel (sign restored)

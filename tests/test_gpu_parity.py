@@ -158,7 +158,9 @@ def test_op_level_against_oracle_on_reference_states(ipm, orc, name, ks):
             assert 0 < max(alpha) <= 0.91 and min(alpha) > 0     # quirk Q4: alpha <= eta always
             # structural identities of the elimination (main.py:227-228), whatever the conditioning:
             #   A^T dy + ds = -rc      and      s*dx + x*ds = -rcomp
-            d_scale = np.linalg.norm(abs(As).T @ abs(dya)) + np.linalg.norm(dsa) + np.linalg.norm(orcv)
+            # (ds is formed as -(s/x)dx - s, a difference of terms of size |s|: that is the rounding scale)
+            d_scale = (np.linalg.norm(abs(As).T @ abs(dya)) + np.linalg.norm(dsa) + np.linalg.norm(orcv)
+                       + np.linalg.norm(s * dxa / x) + np.linalg.norm(s))
             assert np.linalg.norm(As.T @ dya + dsa + orcv) <= 1e-12 * d_scale, k
             comp = s * dxa + x * dsa + x * s
             assert np.linalg.norm(comp) <= 1e-12 * (np.linalg.norm(s * dxa) + np.linalg.norm(x * dsa)), k
