@@ -63,6 +63,67 @@ __device__ __forceinline__ void tri_decode(int t, int& bi, int& bj) {
     bj = t - i * (i + 1) / 2;
 }
 
+// Diagonal tile (bi == bj): only the lower triangle is needed.  The 128 rows are cut into 16 strips of 8 rows;
+// strip s needs the 8x8 sub-tiles 0..s.  Consumer warp W takes strips W and 15-W = (W+1) + (16-W) = 17 sub-tiles
+// for every warp, against 32 in a full tile, so a diagonal tile costs 53 % of an off-diagonal one.
+template <int W, int EPI, bool SCALE>
+__device__ __forceinline__ void ws_diag_tile(const DmmaArgs& a, const double* Ps, const double* Qs, const double* Ds,
+                                             uint64_t* full, uint64_t* empty, uint32_t& it, int nk, int z, int row0,
+                                             int lane) {
+    constexpr int LD = WS_LD, S = WS_STAGES;
+    constexpr int N0 = W + 1, N1 = 16 - W;
+    constexpr int R0 = 8 * W, R1 = 8 * (15 - W);
+    const int g = lane >> 2, t = lane & 3;
+    double acc0[N0][2], acc1[N1][2];
+#pragma unroll
+    for (int j = 0; j < N0; ++j) acc0[j][0] = acc0[j][1] = 0.0;
+#pragma unroll
+    for (int j = 0; j < N1; ++j) acc1[j][0] = acc1[j][1] = 0.0;
+    for (int kt = 0; kt < nk; ++kt, ++it) {
+        const int s = it % S;
+        mbar_wait(full + s, (it / S) & 1);
+        const double* ps0 = Ps + s * WS_BM * LD + (R0 + g) * LD + t;
+        const double* ps1 = Ps + s * WS_BM * LD + (R1 + g) * LD + t;
+        const double* qs = Qs + s * WS_BN * LD + g * LD + t;
+        const double* ds = Ds + s * WS_BK + t;
+#pragma unroll
+        for (int kk = 0; kk < WS_BK; kk += 4) {
+            double a0 = ps0[kk], a1 = ps1[kk];
+            if (SCALE) {
+                const double dk = ds[kk];
+                a0 *= dk;
+                a1 *= dk;
+            }
+#pragma unroll
+            for (int j = 0; j < N1; ++j) {
+                const double b = qs[j * 8 * LD + kk];
+                dmma884(acc1[j][0], acc1[j][1], a1, b);
+                if (j < N0) dmma884(acc0[j][0], acc0[j][1], a0, b);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);
+    }
+    double* C = a.C + (size_t)z * a.strideC;
+    auto store = [&](int r, int c, double v0, double v1) {
+        if (r >= a.rowsP || c >= a.rowsQ) return;
+        double* cp = C + (size_t)r * a.ldc + c;
+        if (c + 1 < a.rowsQ) {
+            double2 v;
+            if (EPI == 1) { v = *reinterpret_cast<double2*>(cp); v.x -= v0; v.y -= v1; }
+            else v = make_double2(v0, v1);
+            *reinterpret_cast<double2*>(cp) = v;
+        } else {
+            if (EPI == 1) cp[0] -= v0;
+            else cp[0] = v0;
+        }
+    };
+#pragma unroll
+    for (int j = 0; j < N0; ++j) store(row0 + R0 + g, row0 + 8 * j + 2 * t, acc0[j][0], acc0[j][1]);
+#pragma unroll
+    for (int j = 0; j < N1; ++j) store(row0 + R1 + g, row0 + 8 * j + 2 * t, acc1[j][0], acc1[j][1]);
+}
+
 template <int EPI, bool SCALE>
 __global__ void __launch_bounds__(WS_THREADS, 1) dmma_ws_kernel(const DmmaArgs a, int ntri, int total_tiles) {
     constexpr int LD = WS_LD, S = WS_STAGES;
@@ -140,6 +201,20 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dmma_ws_kernel(const DmmaArgs a
             if (a.active && a.active[z] == 0) continue;
             int bi, bj;
             tri_decode(tile - z * ntri, bi, bj);
+            if (bi == bj) {
+                const int r0d = bi * WS_BM;
+                switch (warp) {
+                    case 0: ws_diag_tile<0, EPI, SCALE>(a, Ps, Qs, Ds, full, empty, it, nk, z, r0d, lane); break;
+                    case 1: ws_diag_tile<1, EPI, SCALE>(a, Ps, Qs, Ds, full, empty, it, nk, z, r0d, lane); break;
+                    case 2: ws_diag_tile<2, EPI, SCALE>(a, Ps, Qs, Ds, full, empty, it, nk, z, r0d, lane); break;
+                    case 3: ws_diag_tile<3, EPI, SCALE>(a, Ps, Qs, Ds, full, empty, it, nk, z, r0d, lane); break;
+                    case 4: ws_diag_tile<4, EPI, SCALE>(a, Ps, Qs, Ds, full, empty, it, nk, z, r0d, lane); break;
+                    case 5: ws_diag_tile<5, EPI, SCALE>(a, Ps, Qs, Ds, full, empty, it, nk, z, r0d, lane); break;
+                    case 6: ws_diag_tile<6, EPI, SCALE>(a, Ps, Qs, Ds, full, empty, it, nk, z, r0d, lane); break;
+                    default: ws_diag_tile<7, EPI, SCALE>(a, Ps, Qs, Ds, full, empty, it, nk, z, r0d, lane); break;
+                }
+                continue;
+            }
             double acc[MI][NI][2];
 #pragma unroll
             for (int i = 0; i < MI; ++i)
