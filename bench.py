@@ -242,6 +242,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"        # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     import interiorpointmethod_b200 as ipm

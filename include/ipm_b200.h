@@ -122,6 +122,8 @@ int ipm_solve_batched_dense(int device_ordinal, int B, int m, int n,
                             const double *A, const double *b, const double *c,
                             double tol, int max_iter,
                             double *obj, int *iters, int *status, double *x);
+/* Frees the device/pinned staging buffers ipm_solve_batched_dense keeps between calls. */
+int ipm_release_cached(void);
 /* Same with everything resident on `device_ordinal`; stream 0 of that device; synchronises before return.
  * work_d: scratch of ipm_batched_workspace_bytes(B,m,n) bytes or NULL (allocated internally). */
 int ipm_solve_batched_dense_d(int device_ordinal, int B, int m, int n,

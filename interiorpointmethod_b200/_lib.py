@@ -44,6 +44,7 @@ SYMBOLS = {
                                         c_void_p, c_void_p, c_void_p, c_void_p]),
     "ipm_solve_batched_dense_d": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_double, c_int,
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, _ip]),
+    "ipm_release_cached": (c_int, []),
     "ipm_batched_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
     "ipm_profile_enable": (c_int, [c_int]),
     "ipm_profile_read": (c_int, [c_void_p, c_void_p, POINTER(c_int64)]),

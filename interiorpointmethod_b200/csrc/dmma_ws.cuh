@@ -75,10 +75,21 @@ __device__ __forceinline__ void ws_diag_tile(const DmmaArgs& a, const double* Ps
     constexpr int R0 = 8 * W, R1 = 8 * (15 - W);
     const int g = lane >> 2, t = lane & 3;
     double acc0[N0][2], acc1[N1][2];
+    double* C = a.C + (size_t)z * a.strideC;
+    // EPI == 1 (C -= P Q^T): the accumulators start from C, loaded here so that the latency hides behind the
+    // first pipeline stages, and the A fragments are negated; the epilogue is then a plain store.
+    auto init = [&](int r, int c, double& v0, double& v1) {
+        v0 = v1 = 0.0;
+        if (EPI == 1 && r < a.rowsP && c < a.rowsQ) {
+            const double* cp = C + (size_t)r * a.ldc + c;
+            if (c + 1 < a.rowsQ) { const double2 v = *reinterpret_cast<const double2*>(cp); v0 = v.x; v1 = v.y; }
+            else v0 = cp[0];
+        }
+    };
 #pragma unroll
-    for (int j = 0; j < N0; ++j) acc0[j][0] = acc0[j][1] = 0.0;
+    for (int j = 0; j < N0; ++j) init(row0 + R0 + g, row0 + 8 * j + 2 * t, acc0[j][0], acc0[j][1]);
 #pragma unroll
-    for (int j = 0; j < N1; ++j) acc1[j][0] = acc1[j][1] = 0.0;
+    for (int j = 0; j < N1; ++j) init(row0 + R1 + g, row0 + 8 * j + 2 * t, acc1[j][0], acc1[j][1]);
     for (int kt = 0; kt < nk; ++kt, ++it) {
         const int s = it % S;
         mbar_wait(full + s, (it / S) & 1);
@@ -90,9 +101,12 @@ __device__ __forceinline__ void ws_diag_tile(const DmmaArgs& a, const double* Ps
         for (int kk = 0; kk < WS_BK; kk += 4) {
             double a0 = ps0[kk], a1 = ps1[kk];
             if (SCALE) {
-                const double dk = ds[kk];
+                const double dk = (EPI == 1) ? -ds[kk] : ds[kk];
                 a0 *= dk;
                 a1 *= dk;
+            } else if (EPI == 1) {
+                a0 = -a0;
+                a1 = -a1;
             }
 #pragma unroll
             for (int j = 0; j < N1; ++j) {
@@ -104,19 +118,11 @@ __device__ __forceinline__ void ws_diag_tile(const DmmaArgs& a, const double* Ps
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + s);
     }
-    double* C = a.C + (size_t)z * a.strideC;
     auto store = [&](int r, int c, double v0, double v1) {
         if (r >= a.rowsP || c >= a.rowsQ) return;
         double* cp = C + (size_t)r * a.ldc + c;
-        if (c + 1 < a.rowsQ) {
-            double2 v;
-            if (EPI == 1) { v = *reinterpret_cast<double2*>(cp); v.x -= v0; v.y -= v1; }
-            else v = make_double2(v0, v1);
-            *reinterpret_cast<double2*>(cp) = v;
-        } else {
-            if (EPI == 1) cp[0] -= v0;
-            else cp[0] = v0;
-        }
+        if (c + 1 < a.rowsQ) *reinterpret_cast<double2*>(cp) = make_double2(v0, v1);
+        else cp[0] = v0;
     };
 #pragma unroll
     for (int j = 0; j < N0; ++j) store(row0 + R0 + g, row0 + 8 * j + 2 * t, acc0[j][0], acc0[j][1]);
@@ -216,10 +222,24 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dmma_ws_kernel(const DmmaArgs a
                 continue;
             }
             double acc[MI][NI][2];
+            double* C = a.C + (size_t)z * a.strideC;
+            const int row0 = bi * WS_BM, col0 = bj * WS_BN;
 #pragma unroll
-            for (int i = 0; i < MI; ++i)
+            for (int i = 0; i < MI; ++i) {
+                const int r = row0 + wm0 + i * 8 + g;
 #pragma unroll
-                for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+                for (int j = 0; j < NI; ++j) {
+                    const int c = col0 + wn0 + j * 8 + 2 * t;
+                    double v0 = 0.0, v1 = 0.0;
+                    if (EPI == 1 && r < a.rowsP && c < a.rowsQ) {       // accumulate on top of C (see ws_diag_tile)
+                        const double* cp = C + (size_t)r * a.ldc + c;
+                        if (c + 1 < a.rowsQ) { const double2 v = *reinterpret_cast<const double2*>(cp); v0 = v.x; v1 = v.y; }
+                        else v0 = cp[0];
+                    }
+                    acc[i][j][0] = v0;
+                    acc[i][j][1] = v1;
+                }
+            }
             for (int kt = 0; kt < nk; ++kt, ++it) {
                 const int s = it % S;
                 mbar_wait(full + s, (it / S) & 1);
@@ -234,9 +254,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dmma_ws_kernel(const DmmaArgs a
 #pragma unroll
                     for (int j = 0; j < NI; ++j) bf[j] = qs[j * 8 * LD + kk];
                     if (SCALE) {
-                        const double dk = ds[kk];
+                        const double dk = (EPI == 1) ? -ds[kk] : ds[kk];
 #pragma unroll
                         for (int i = 0; i < MI; ++i) af[i] *= dk;
+                    } else if (EPI == 1) {
+#pragma unroll
+                        for (int i = 0; i < MI; ++i) af[i] = -af[i];
                     }
 #pragma unroll
                     for (int i = 0; i < MI; ++i)
@@ -247,8 +270,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dmma_ws_kernel(const DmmaArgs a
                 if (lane == 0) mbar_arrive(empty + s);
             }
             // epilogue (the producer is already filling the ring for the next tile)
-            double* C = a.C + (size_t)z * a.strideC;
-            const int row0 = bi * WS_BM, col0 = bj * WS_BN;
 #pragma unroll
             for (int i = 0; i < MI; ++i) {
                 const int r = row0 + wm0 + i * 8 + g;
@@ -258,20 +279,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dmma_ws_kernel(const DmmaArgs a
                     const int c = col0 + wn0 + j * 8 + 2 * t;
                     if (c >= a.rowsQ) continue;
                     double* cp = C + (size_t)r * a.ldc + c;
-                    if (c + 1 < a.rowsQ) {
-                        double2 v;
-                        if (EPI == 1) {
-                            v = *reinterpret_cast<double2*>(cp);
-                            v.x -= acc[i][j][0];
-                            v.y -= acc[i][j][1];
-                        } else {
-                            v = make_double2(acc[i][j][0], acc[i][j][1]);
-                        }
-                        *reinterpret_cast<double2*>(cp) = v;
-                    } else {
-                        if (EPI == 1) cp[0] -= acc[i][j][0];
-                        else cp[0] = acc[i][j][0];
-                    }
+                    if (c + 1 < a.rowsQ) *reinterpret_cast<double2*>(cp) = make_double2(acc[i][j][0], acc[i][j][1]);
+                    else cp[0] = acc[i][j][0];
                 }
             }
         }

@@ -592,17 +592,10 @@ int ipm_solve_batched_dense_d(int device_ordinal, int B, int m, int n, const dou
     return rc;
 }
 
-int ipm_solve_batched_dense(int device_ordinal, int B, int m, int n, const double* A, const double* b,
-                            const double* c, double tol, int max_iter, double* obj, int* iters, int* status,
-                            double* x) {
-    if (!A || !b || !c) return IPM_ERR_ARG;
-    IPM_TRY(check_shape(B, m, n));
-    IPM_CUDA_OK(cudaSetDevice(device_ordinal));
-    // chunking: two device-resident input buffers so the H2D copy of chunk k+1 overlaps the solve of chunk k
-    const int64_t lp_bytes = ((int64_t)m * n + m + n) * 8;
-    int chunk = (int)std::min<int64_t>(B, std::max<int64_t>(1, ((int64_t)1 << 30) / lp_bytes));   // ~1 GiB of inputs
-    if (chunk < B) chunk = ceil_div(B, ceil_div(B, chunk));                                        // balance
-    const int nchunks = ceil_div(B, chunk);
+// Device-side staging of the host-buffer entry point, cached per process (one context per device) so that
+// repeated calls do not pay cudaMalloc / cudaMallocHost / stream creation again.
+struct HostPathCtx {
+    int dev = -1;
     cudaStream_t s_copy = nullptr, s_comp = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     double *dA[2] = {nullptr, nullptr}, *db[2] = {nullptr, nullptr}, *dc[2] = {nullptr, nullptr};
@@ -610,71 +603,139 @@ int ipm_solve_batched_dense(int device_ordinal, int B, int m, int n, const doubl
     int *d_it = nullptr, *d_st = nullptr;
     void* work = nullptr;
     unsigned* h_nact = nullptr;
-    int rc = [&]() -> int {
-        IPM_CUDA_OK(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
-        IPM_CUDA_OK(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
-        const int nbuf = nchunks > 1 ? 2 : 1;
-        for (int i = 0; i < nbuf; ++i) {
-            IPM_CUDA_OK(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
-            IPM_CUDA_OK(cudaEventCreateWithFlags(&ev_free[i], cudaEventDisableTiming));
-            IPM_CUDA_OK(cudaMalloc(&dA[i], (size_t)chunk * m * n * 8));
-            IPM_CUDA_OK(cudaMalloc(&db[i], (size_t)chunk * m * 8));
-            IPM_CUDA_OK(cudaMalloc(&dc[i], (size_t)chunk * n * 8));
+    int64_t capA = 0, capb = 0, capc = 0, capres = 0, capx = 0, capwork = 0;   // bytes
+    void release() {
+        if (dev < 0) return;
+        cudaSetDevice(dev);
+        for (int i = 0; i < 2; ++i) {
+            if (dA[i]) cudaFree(dA[i]);
+            if (db[i]) cudaFree(db[i]);
+            if (dc[i]) cudaFree(dc[i]);
+            if (ev_in[i]) cudaEventDestroy(ev_in[i]);
+            if (ev_free[i]) cudaEventDestroy(ev_free[i]);
         }
-        IPM_CUDA_OK(cudaMalloc(&d_obj, (size_t)chunk * 8));
-        IPM_CUDA_OK(cudaMalloc(&d_it, (size_t)chunk * sizeof(int)));
-        IPM_CUDA_OK(cudaMalloc(&d_st, (size_t)chunk * sizeof(int)));
-        if (x) IPM_CUDA_OK(cudaMalloc(&d_x, (size_t)chunk * n * 8));
-        IPM_CUDA_OK(cudaMalloc(&work, (size_t)ws_bytes(chunk, m, n)));
-        IPM_CUDA_OK(cudaMallocHost(&h_nact, sizeof(unsigned)));
+        if (d_obj) cudaFree(d_obj);
+        if (d_it) cudaFree(d_it);
+        if (d_st) cudaFree(d_st);
+        if (d_x) cudaFree(d_x);
+        if (work) cudaFree(work);
+        if (h_nact) cudaFreeHost(h_nact);
+        if (s_copy) cudaStreamDestroy(s_copy);
+        if (s_comp) cudaStreamDestroy(s_comp);
+        *this = HostPathCtx();
+    }
+};
+static HostPathCtx g_host_ctx[16];
+
+static int ensure_bytes(void** p, int64_t* cap, int64_t need) {
+    if (*cap >= need) return IPM_OK;
+    if (*p) { IPM_CUDA_OK(cudaFree(*p)); *p = nullptr; *cap = 0; }
+    IPM_CUDA_OK(cudaMalloc(p, (size_t)need));
+    *cap = need;
+    return IPM_OK;
+}
+
+int ipm_release_cached(void) {
+    for (auto& c : g_host_ctx) c.release();
+    return IPM_OK;
+}
+
+int ipm_solve_batched_dense(int device_ordinal, int B, int m, int n, const double* A, const double* b,
+                            const double* c, double tol, int max_iter, double* obj, int* iters, int* status,
+                            double* x) {
+    if (!A || !b || !c) return IPM_ERR_ARG;
+    IPM_TRY(check_shape(B, m, n));
+    if (device_ordinal < 0 || device_ordinal >= 16) return IPM_ERR_ARG;
+    IPM_CUDA_OK(cudaSetDevice(device_ordinal));
+    // Chunk schedule: a small first chunk (its H2D copy is the only one nothing can hide), then chunks growing
+    // by 3x up to a quarter of the batch; the copy of chunk k+1 runs on the copy stream while chunk k is solved.
+    std::vector<int> first_of, count_of;
+    {
+        const int cap = std::max(256, ceil_div(B, 4));
+        int next = std::max(256, B / 16), at = 0;
+        while (at < B) {
+            const int cnt = std::min(std::min(next, cap), B - at);
+            first_of.push_back(at);
+            count_of.push_back(cnt);
+            at += cnt;
+            next = std::min(cap, next * 3);
+        }
+    }
+    const int nchunks = (int)first_of.size();
+    int chunk = 0;
+    for (int v : count_of) chunk = std::max(chunk, v);
+    HostPathCtx& C = g_host_ctx[device_ordinal];
+    int rc = [&]() -> int {
+        if (C.dev < 0) {
+            C.dev = device_ordinal;
+            IPM_CUDA_OK(cudaStreamCreateWithFlags(&C.s_copy, cudaStreamNonBlocking));
+            IPM_CUDA_OK(cudaStreamCreateWithFlags(&C.s_comp, cudaStreamNonBlocking));
+            for (int i = 0; i < 2; ++i) {
+                IPM_CUDA_OK(cudaEventCreateWithFlags(&C.ev_in[i], cudaEventDisableTiming));
+                IPM_CUDA_OK(cudaEventCreateWithFlags(&C.ev_free[i], cudaEventDisableTiming));
+            }
+            IPM_CUDA_OK(cudaMallocHost(&C.h_nact, sizeof(unsigned)));
+        }
+        {   // (re)size the cached buffers; capacities are tracked for buffer 0 and applied to both
+            const int64_t nA = (int64_t)chunk * m * n * 8, nb = (int64_t)chunk * m * 8, nc = (int64_t)chunk * n * 8;
+            int64_t capA1 = C.capA, capb1 = C.capb, capc1 = C.capc;
+            IPM_TRY(ensure_bytes((void**)&C.dA[0], &C.capA, nA));
+            IPM_TRY(ensure_bytes((void**)&C.db[0], &C.capb, nb));
+            IPM_TRY(ensure_bytes((void**)&C.dc[0], &C.capc, nc));
+            if (nchunks > 1 || C.dA[1]) {
+                if (!C.dA[1]) { capA1 = capb1 = capc1 = 0; }
+                IPM_TRY(ensure_bytes((void**)&C.dA[1], &capA1, std::max(nA, C.capA)));
+                IPM_TRY(ensure_bytes((void**)&C.db[1], &capb1, std::max(nb, C.capb)));
+                IPM_TRY(ensure_bytes((void**)&C.dc[1], &capc1, std::max(nc, C.capc)));
+            }
+            const int64_t nres = (int64_t)chunk * 8;
+            if (C.capres < nres) {
+                if (C.d_obj) cudaFree(C.d_obj);
+                if (C.d_it) cudaFree(C.d_it);
+                if (C.d_st) cudaFree(C.d_st);
+                C.d_obj = nullptr; C.d_it = C.d_st = nullptr;
+                IPM_CUDA_OK(cudaMalloc(&C.d_obj, (size_t)nres));
+                IPM_CUDA_OK(cudaMalloc(&C.d_it, (size_t)chunk * sizeof(int)));
+                IPM_CUDA_OK(cudaMalloc(&C.d_st, (size_t)chunk * sizeof(int)));
+                C.capres = nres;
+            }
+            if (x) IPM_TRY(ensure_bytes((void**)&C.d_x, &C.capx, (int64_t)chunk * n * 8));
+            IPM_TRY(ensure_bytes(&C.work, &C.capwork, ws_bytes(chunk, m, n)));
+        }
         auto stage = [&](int k) -> int {
-            const int buf = k & 1, first = k * chunk, cnt = std::min(chunk, B - first);
-            if (k >= 2) IPM_CUDA_OK(cudaStreamWaitEvent(s_copy, ev_free[buf], 0));
-            IPM_CUDA_OK(cudaMemcpyAsync(dA[buf], A + (size_t)first * m * n, (size_t)cnt * m * n * 8,
-                                        cudaMemcpyHostToDevice, s_copy));
-            IPM_CUDA_OK(cudaMemcpyAsync(db[buf], b + (size_t)first * m, (size_t)cnt * m * 8, cudaMemcpyHostToDevice,
-                                        s_copy));
-            IPM_CUDA_OK(cudaMemcpyAsync(dc[buf], c + (size_t)first * n, (size_t)cnt * n * 8, cudaMemcpyHostToDevice,
-                                        s_copy));
-            IPM_CUDA_OK(cudaEventRecord(ev_in[buf], s_copy));
+            const int buf = k & 1, first = first_of[k], cnt = count_of[k];
+            if (k >= 2) IPM_CUDA_OK(cudaStreamWaitEvent(C.s_copy, C.ev_free[buf], 0));
+            IPM_CUDA_OK(cudaMemcpyAsync(C.dA[buf], A + (size_t)first * m * n, (size_t)cnt * m * n * 8,
+                                        cudaMemcpyHostToDevice, C.s_copy));
+            IPM_CUDA_OK(cudaMemcpyAsync(C.db[buf], b + (size_t)first * m, (size_t)cnt * m * 8, cudaMemcpyHostToDevice,
+                                        C.s_copy));
+            IPM_CUDA_OK(cudaMemcpyAsync(C.dc[buf], c + (size_t)first * n, (size_t)cnt * n * 8, cudaMemcpyHostToDevice,
+                                        C.s_copy));
+            IPM_CUDA_OK(cudaEventRecord(C.ev_in[buf], C.s_copy));
             return IPM_OK;
         };
         IPM_TRY(stage(0));
         for (int k = 0; k < nchunks; ++k) {
-            const int buf = k & 1, first = k * chunk, cnt = std::min(chunk, B - first);
+            const int buf = k & 1, first = first_of[k], cnt = count_of[k];
             if (k + 1 < nchunks) IPM_TRY(stage(k + 1));
-            IPM_CUDA_OK(cudaStreamWaitEvent(s_comp, ev_in[buf], 0));
-            IPM_TRY(solve_on_device(cnt, m, n, dA[buf], db[buf], dc[buf], tol, max_iter, d_obj, d_it, d_st, d_x, work,
-                                    h_nact, s_comp, nullptr));
-            IPM_CUDA_OK(cudaEventRecord(ev_free[buf], s_comp));
-            if (obj) IPM_CUDA_OK(cudaMemcpyAsync(obj + first, d_obj, (size_t)cnt * 8, cudaMemcpyDeviceToHost, s_comp));
-            if (iters) IPM_CUDA_OK(cudaMemcpyAsync(iters + first, d_it, (size_t)cnt * sizeof(int),
-                                                   cudaMemcpyDeviceToHost, s_comp));
-            if (status) IPM_CUDA_OK(cudaMemcpyAsync(status + first, d_st, (size_t)cnt * sizeof(int),
-                                                    cudaMemcpyDeviceToHost, s_comp));
-            if (x) IPM_CUDA_OK(cudaMemcpyAsync(x + (size_t)first * n, d_x, (size_t)cnt * n * 8,
-                                               cudaMemcpyDeviceToHost, s_comp));
+            IPM_CUDA_OK(cudaStreamWaitEvent(C.s_comp, C.ev_in[buf], 0));
+            IPM_TRY(solve_on_device(cnt, m, n, C.dA[buf], C.db[buf], C.dc[buf], tol, max_iter, C.d_obj, C.d_it, C.d_st,
+                                    x ? C.d_x : nullptr, C.work, C.h_nact, C.s_comp, nullptr));
+            IPM_CUDA_OK(cudaEventRecord(C.ev_free[buf], C.s_comp));
+            if (obj) IPM_CUDA_OK(cudaMemcpyAsync(obj + first, C.d_obj, (size_t)cnt * 8, cudaMemcpyDeviceToHost, C.s_comp));
+            if (iters) IPM_CUDA_OK(cudaMemcpyAsync(iters + first, C.d_it, (size_t)cnt * sizeof(int),
+                                                   cudaMemcpyDeviceToHost, C.s_comp));
+            if (status) IPM_CUDA_OK(cudaMemcpyAsync(status + first, C.d_st, (size_t)cnt * sizeof(int),
+                                                    cudaMemcpyDeviceToHost, C.s_comp));
+            if (x) IPM_CUDA_OK(cudaMemcpyAsync(x + (size_t)first * n, C.d_x, (size_t)cnt * n * 8,
+                                               cudaMemcpyDeviceToHost, C.s_comp));
         }
-        IPM_CUDA_OK(cudaStreamSynchronize(s_comp));
-        IPM_CUDA_OK(cudaStreamSynchronize(s_copy));
+        IPM_CUDA_OK(cudaStreamSynchronize(C.s_comp));
+        IPM_CUDA_OK(cudaStreamSynchronize(C.s_copy));
         return IPM_OK;
     }();
     g_prof.collect();
-    for (int i = 0; i < 2; ++i) {
-        if (dA[i]) cudaFree(dA[i]);
-        if (db[i]) cudaFree(db[i]);
-        if (dc[i]) cudaFree(dc[i]);
-        if (ev_in[i]) cudaEventDestroy(ev_in[i]);
-        if (ev_free[i]) cudaEventDestroy(ev_free[i]);
-    }
-    if (d_obj) cudaFree(d_obj);
-    if (d_it) cudaFree(d_it);
-    if (d_st) cudaFree(d_st);
-    if (d_x) cudaFree(d_x);
-    if (work) cudaFree(work);
-    if (h_nact) cudaFreeHost(h_nact);
-    if (s_copy) cudaStreamDestroy(s_copy);
-    if (s_comp) cudaStreamDestroy(s_comp);
+    if (rc != IPM_OK) C.release();
     return rc;
 }
 
