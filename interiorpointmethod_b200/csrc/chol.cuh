@@ -342,10 +342,10 @@ struct TrsvBatchedArgs {
 constexpr int TRSVB_NT = 256;
 constexpr int TRSVB_NW = TRSVB_NT / 32;
 
-static __global__ void __launch_bounds__(TRSVB_NT, 6) k_trsv_batched(const TrsvBatchedArgs a) {
+static __global__ void __launch_bounds__(TRSVB_NT, 3) k_trsv_batched(const TrsvBatchedArgs a) {
     extern __shared__ __align__(16) double smem_tb[];
-    double* Ls = smem_tb;               // [32][33] current diagonal block
-    double* vec = smem_tb + 32 * 33;    // [m]
+    double* Ls0 = smem_tb;                  // [2][32][33] diagonal blocks, double buffered
+    double* vec = smem_tb + 2 * 32 * 33;    // [m]
     const int bz = blockIdx.x;
     if (a.active && a.active[bz] == 0) return;
     const double* L = a.L + (size_t)bz * a.strideM;
@@ -354,26 +354,53 @@ static __global__ void __launch_bounds__(TRSVB_NT, 6) k_trsv_batched(const TrsvB
     const int64_t ldm = a.ldm;
     for (int i = tid; i < m; i += TRSVB_NT) vec[i] = v[i];
     const int nblk = (m + 31) >> 5;
-    auto load_block = [&](int i0, int nb) {
-        for (int idx = tid; idx < 32 * 32; idx += TRSVB_NT) {
+    // the 4 entries of a 32x32 diagonal block this thread stages (issued one block ahead of their use)
+    auto fetch_block = [&](int I, double (&r)[4]) {
+        const int i0 = I << 5;
+        const int nb = (m - i0 < 32) ? (m - i0) : 32;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int idx = tid + q * TRSVB_NT;
             const int i = idx >> 5, c = idx & 31;
-            Ls[i * 33 + c] = (i < nb && c <= i) ? L[(size_t)(i0 + i) * ldm + i0 + c] : 0.0;
+            r[q] = (i < nb && c <= i) ? L[(size_t)(i0 + i) * ldm + i0 + c] : 0.0;
         }
     };
+    auto put_block = [&](double* Ls, const double (&r)[4]) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int idx = tid + q * TRSVB_NT;
+            Ls[(idx >> 5) * 33 + (idx & 31)] = r[q];
+        }
+    };
+    double blk[4];
+    fetch_block(0, blk);
+    put_block(Ls0, blk);
     __syncthreads();
     // ---- forward
     for (int I = 0; I < nblk; ++I) {
         const int i0 = I << 5;
         const int nb = (m - i0 < 32) ? (m - i0) : 32;
-        load_block(i0, nb);
-        for (int rr = warp; rr < nb && i0 > 0; rr += TRSVB_NW) {
-            const double* row = L + (size_t)(i0 + rr) * ldm;
-            double acc = 0.0;
-            for (int k = lane; k < i0; k += 32) acc += row[k] * vec[k];
-            acc = warp_sum(acc);
-            if (lane == 0) vec[i0 + rr] -= acc;
+        double* Ls = Ls0 + (I & 1) * 32 * 33;
+        if (I + 1 < nblk) fetch_block(I + 1, blk);            // in flight during the GEMV and the solve
+        if (i0 > 0) {
+            // rows warp, warp+8, warp+16, warp+24 of the block at once: all loads issued before any reduction
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int k = lane; k < i0; k += 32) {
+                const double zk = vec[k];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int rr = warp + q * TRSVB_NW;
+                    if (rr < nb) acc[q] += L[(size_t)(i0 + rr) * ldm + k] * zk;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double sum = warp_sum(acc[q]);
+                const int rr = warp + q * TRSVB_NW;
+                if (lane == 0 && rr < nb) vec[i0 + rr] -= sum;
+            }
+            __syncthreads();
         }
-        __syncthreads();
         if (warp == 0) {
             const bool ok = lane < nb;
             double x = ok ? vec[i0 + lane] : 0.0;
@@ -386,14 +413,15 @@ static __global__ void __launch_bounds__(TRSVB_NT, 6) k_trsv_batched(const TrsvB
             }
             if (ok) vec[i0 + lane] = x;
         }
+        if (I + 1 < nblk) put_block(Ls0 + ((I + 1) & 1) * 32 * 33, blk);
         __syncthreads();
     }
-    // ---- backward
+    // ---- backward (the last diagonal block is still in its buffer)
     for (int I = nblk - 1; I >= 0; --I) {
         const int i0 = I << 5;
         const int nb = (m - i0 < 32) ? (m - i0) : 32;
-        load_block(i0, nb);
-        __syncthreads();
+        double* Ls = Ls0 + (I & 1) * 32 * 33;
+        if (I > 0) fetch_block(I - 1, blk);
         if (warp == 0) {
             const bool ok = lane < nb;
             double x = ok ? vec[i0 + lane] : 0.0;
@@ -406,19 +434,24 @@ static __global__ void __launch_bounds__(TRSVB_NT, 6) k_trsv_batched(const TrsvB
             }
             if (ok) vec[i0 + lane] = x;
         }
+        if (I > 0) put_block(Ls0 + ((I - 1) & 1) * 32 * 33, blk);
         __syncthreads();
         for (int k = tid; k < i0; k += TRSVB_NT) {
             const double* col = L + (size_t)i0 * ldm + k;
             double acc = 0.0;
-#pragma unroll 8
-            for (int i = 0; i < nb; ++i) acc += col[(size_t)i * ldm] * vec[i0 + i];
+            if (nb == 32) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc += col[(size_t)i * ldm] * vec[i0 + i];
+            } else {
+                for (int i = 0; i < nb; ++i) acc += col[(size_t)i * ldm] * vec[i0 + i];
+            }
             vec[k] -= acc;
         }
         __syncthreads();
     }
     for (int i = tid; i < m; i += TRSVB_NT) v[i] = vec[i];
 }
-inline size_t trsv_batched_smem(int m) { return (size_t)(32 * 33 + m) * sizeof(double); }
+inline size_t trsv_batched_smem(int m) { return (size_t)(2 * 32 * 33 + m) * sizeof(double); }
 #endif
 
 }  // namespace ipm
