@@ -99,7 +99,7 @@ Profiler g_prof;
 // ---------------------------------------------------------------------------------------------
 // One pass over A_i: Ax (warp per row) and A^T y (column partial sums per warp, combined in warp order).
 template <int NPL>
-__global__ void __launch_bounds__(KB_NT) kb_residual(const BatchArgs a) {
+__global__ void __launch_bounds__(KB_NT, (NPL <= 8) ? 2 : 1) kb_residual(const BatchArgs a) {
     extern __shared__ __align__(16) double smem[];
     double* colred = smem;                 // [KB_NW][n]
     __shared__ double sh[32];
@@ -119,13 +119,15 @@ __global__ void __launch_bounds__(KB_NT) kb_residual(const BatchArgs a) {
     double* scal = a.scal + (size_t)lp * S_COUNT;
     const int n2 = n >> 1;
 
-    double2 xr[NPL], ca[NPL];
+    // x lives in shared memory (after colred) instead of registers: 32 registers less per thread lets two
+    // CTAs share an SM, which is what this HBM-bound pass needs to keep enough loads in flight
+    double* xsh = colred + (size_t)KB_NW * n;
+    for (int k = tid; k < n; k += KB_NT) xsh[k] = x[k];
+    __syncthreads();
+    const double2* xs2 = reinterpret_cast<const double2*>(xsh);
+    double2 ca[NPL];
 #pragma unroll
-    for (int j = 0; j < NPL; ++j) {
-        const int c2 = j * 32 + lane;
-        xr[j] = (c2 < n2) ? reinterpret_cast<const double2*>(x)[c2] : make_double2(0.0, 0.0);
-        ca[j] = make_double2(0.0, 0.0);
-    }
+    for (int j = 0; j < NPL; ++j) ca[j] = make_double2(0.0, 0.0);
     double nrb2 = 0.0;
     for (int r = warp; r < m; r += KB_NW) {
         const double2* row = reinterpret_cast<const double2*>(A + (size_t)r * n);
@@ -136,8 +138,9 @@ __global__ void __launch_bounds__(KB_NT) kb_residual(const BatchArgs a) {
             const int c2 = j * 32 + lane;
             if (c2 < n2) {
                 const double2 v = row[c2];
-                dot0 += v.x * xr[j].x;
-                dot1 += v.y * xr[j].y;
+                const double2 xv = xs2[c2];
+                dot0 += v.x * xv.x;
+                dot1 += v.y * xv.y;
                 ca[j].x += v.x * yr;
                 ca[j].y += v.y * yr;
             }
@@ -413,12 +416,13 @@ template <int NPL>
 int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, int* iterations_run) {
     BatchArgs& a = w.a;
     const size_t smem_col = (size_t)KB_NW * n * sizeof(double);
+    const size_t smem_res = smem_col + (size_t)n * sizeof(double);
     const size_t smem_w = (size_t)n * sizeof(double);
     static int configured_dev = -1;
     int dev = 0;
     IPM_CUDA_OK(cudaGetDevice(&dev));
     if (configured_dev != dev) {
-        IPM_CUDA_OK(cudaFuncSetAttribute(kb_residual<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
+        IPM_CUDA_OK(cudaFuncSetAttribute(kb_residual<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + 8192));
         IPM_CUDA_OK(cudaFuncSetAttribute(kb_dir<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
         IPM_CUDA_OK(cudaFuncSetAttribute(k_trsv_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
         configured_dev = dev;
@@ -429,7 +433,7 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
     for (;;) {
         IPM_CUDA_OK(cudaMemsetAsync(a.n_active, 0, sizeof(unsigned), st));
         g_prof.segment(st);
-        kb_residual<NPL><<<B, KB_NT, smem_col, st>>>(a);
+        kb_residual<NPL><<<B, KB_NT, smem_res, st>>>(a);
         count_launch();
         g_prof.end_phase(PH_RESID, st);
         IPM_CUDA_OK(cudaMemcpyAsync(w.h_nact, a.n_active, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
