@@ -41,15 +41,22 @@ static __global__ void k_maxdiag(const double* M, int64_t ldm, int64_t strideM, 
 
 // ------------------------------------------------------------------------------------------------
 // Factor the diagonal block M[j0:j0+nb, j0:j0+nb] in shared memory.   grid (1,1,batch), NT threads.
-// Column j: every thread reads the pivot (shared-memory broadcast), applies the safeguard
-//   p <= tau*maxdiag or NaN  ->  p = 1e128            
-// and scales its rows; then the trailing block gets the rank-1 update, warps over rows, lanes over columns.
+// Two-level right-looking inside the CTA, 32 columns at a time:
+//   (1) warp 0 factors the 32x32 sub-block with lane i holding row i in registers; the pivot travels by warp
+//       shuffle from lane j, every lane applies the safeguard  p <= tau*maxdiag or NaN -> 1e128
+//       (SURVEY.md App. A.4), divides its entry by sqrt(p), publishes the column through shared memory and
+//       folds it into its own row;
+//   (2) the rows of the block below it are solved one thread per row against the transposed sub-block;
+//   (3) the rest of the block gets the rank-32 update, warps over rows, lanes over columns.
 template <int NB, int NT>
 static __global__ void __launch_bounds__(NT, 1) k_chol_diag(const CholArgs a) {
     constexpr int LD = NB + 1;
     extern __shared__ __align__(16) double smem[];
-    double* S = smem;                 // [NB][LD]
-    double* diag = smem + NB * LD;    // [NB]
+    double* S = smem;                         // [NB][LD]
+    double* DT = smem + NB * LD + (NB * LD & 1);   // [32][34] transposed sub-block, 16-byte aligned
+    double* dinv = DT + 32 * 34;              // [32]
+    double* colb = dinv + 32;                 // [32]
+    __shared__ int s_nfix;
     const int bz = blockIdx.z;
     if (a.active && a.active[bz] == 0) return;
     double* Mb = a.M + (size_t)bz * a.strideM + (size_t)a.j0 * a.ldm + a.j0;
@@ -60,32 +67,111 @@ static __global__ void __launch_bounds__(NT, 1) k_chol_diag(const CholArgs a) {
         const int i = idx / nb, j = idx - i * nb;
         if (j <= i) S[i * LD + j] = Mb[(size_t)i * a.ldm + j];
     }
+    if (tid == 0) s_nfix = 0;
     __syncthreads();
     const double thresh = a.tau * a.scal[(size_t)bz * a.strideScal + S_MAXDIAG];
-    int nfix = 0;
-    for (int j = 0; j < nb; ++j) {
-        double p = S[j * LD + j];
-        const bool bad = !(p > thresh);
-        if (bad) p = kPivotBig;
-        const double l = sqrt(p);
-        for (int i = j + 1 + tid; i < nb; i += NT) S[i * LD + j] = S[i * LD + j] / l;
-        if (tid == 0) { diag[j] = l; nfix += bad ? 1 : 0; }
-        __syncthreads();
-        for (int i = j + 1 + warp; i < nb; i += NW) {
-            const double lij = S[i * LD + j];
-            for (int k = j + 1 + lane; k <= i; k += 32) S[i * LD + k] -= lij * S[k * LD + j];
+    for (int c0 = 0; c0 < nb; c0 += 32) {
+        const int w = (nb - c0 < 32) ? (nb - c0) : 32;
+        // ---- (1) 32x32 sub-block, warp 0
+        if (warp == 0) {
+            double arow[32];
+            const bool ok = lane < w;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) arow[c] = (ok && c <= lane) ? S[(c0 + lane) * LD + c0 + c] : 0.0;
+            int nfix = 0;
+            double my_inv = 1.0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                if (j < w) {
+                    double p = __shfl_sync(0xffffffffu, arow[j], j);
+                    const bool bad = !(p > thresh);
+                    if (bad) p = kPivotBig;
+                    const double l = sqrt(p);
+                    const double lij = (lane == j) ? l : arow[j] / l;
+                    if (lane == j) { my_inv = 1.0 / l; nfix += bad ? 1 : 0; }
+                    arow[j] = lij;
+                    colb[lane] = lij;
+                    __syncwarp();
+#pragma unroll
+                    for (int k = j + 1; k < 32; ++k) arow[k] = fma(-lij, colb[k], arow[k]);
+                    __syncwarp();
+                }
+            }
+            if (ok) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                    if (c <= lane) S[(c0 + lane) * LD + c0 + c] = arow[c];
+                dinv[lane] = my_inv;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) nfix += __shfl_xor_sync(0xffffffffu, nfix, o);
+            if (lane == 0) s_nfix += nfix;
         }
         __syncthreads();
+        const int r0 = c0 + w;                    // first row below the sub-block
+        if (r0 < nb) {
+            for (int idx = tid; idx < 32 * 32; idx += NT) {
+                const int jj = idx >> 5, kk = idx & 31;
+                DT[kk * 34 + jj] = (jj < w && kk <= jj) ? S[(c0 + jj) * LD + c0 + kk] : 0.0;
+            }
+            __syncthreads();
+            // ---- (2) rows below: x L^T = a, 8 columns at a time (w == 32 here: only the last sub-block is ragged)
+            for (int r = r0 + tid; r < nb; r += NT) {
+                double* pr = S + r * LD + c0;
+#pragma unroll 1
+                for (int jb = 0; jb < 32; jb += 8) {
+                    double x8[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) x8[q] = pr[jb + q];
+#pragma unroll 4
+                    for (int k = 0; k < jb; ++k) {
+                        const double xk = pr[k];
+                        const double2* lp = reinterpret_cast<const double2*>(DT + k * 34 + jb);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const double2 lv = lp[q];
+                            x8[2 * q] -= xk * lv.x;
+                            x8[2 * q + 1] -= xk * lv.y;
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const double* lrow = DT + (jb + q) * 34 + jb;
+                        const double xv = x8[q] / lrow[q];
+                        x8[q] = xv;
+#pragma unroll
+                        for (int q2 = q + 1; q2 < 8; ++q2) x8[q2] -= xv * lrow[q2];
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) pr[jb + q] = x8[q];
+                }
+            }
+            __syncthreads();
+            // ---- (3) rank-32 update of the remaining lower triangle
+            for (int i = r0 + warp; i < nb; i += NW) {
+                const double* ri = S + i * LD + c0;
+                for (int k = r0 + lane; k <= i; k += 32) {
+                    const double* rk = S + k * LD + c0;
+                    double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll 8
+                    for (int c = 0; c < 32; c += 2) {
+                        acc0 += ri[c] * rk[c];
+                        acc1 += ri[c + 1] * rk[c + 1];
+                    }
+                    S[i * LD + k] -= acc0 + acc1;
+                }
+            }
+            __syncthreads();
+        }
     }
     for (int idx = tid; idx < nb * nb; idx += NT) {
         const int i = idx / nb, j = idx - i * nb;
-        if (j < i) Mb[(size_t)i * a.ldm + j] = S[i * LD + j];
-        else if (j == i) Mb[(size_t)i * a.ldm + j] = diag[i];
+        if (j <= i) Mb[(size_t)i * a.ldm + j] = S[i * LD + j];
     }
-    if (tid == 0 && nfix) a.scal[(size_t)bz * a.strideScal + S_NFIXED] += (double)nfix;
+    if (tid == 0 && s_nfix) a.scal[(size_t)bz * a.strideScal + S_NFIXED] += (double)s_nfix;
 }
 template <int NB>
-constexpr size_t chol_diag_smem() { return (size_t)(NB * (NB + 1) + NB) * sizeof(double); }
+constexpr size_t chol_diag_smem() { return (size_t)(NB * (NB + 1) + 1 + 32 * 34 + 64) * sizeof(double); }
 
 // ------------------------------------------------------------------------------------------------
 // Rows below the diagonal block: solve X L_JJ^T = A_panel, one thread per row, forward substitution in
@@ -304,7 +390,7 @@ static __global__ void __launch_bounds__(TRSV_NT) k_trsv_bwd(const TrsvArgs a) {
 }
 
 // rhs (destroyed) -> sol.  L is the factor produced by potrf_blocked.
-inline int potrs_single(const double* L, int64_t ldm, int m, double* rhs, double* tmp, double* sol, cudaStream_t st) {
+inline int potrs_single_blocks(const double* L, int64_t ldm, int m, double* rhs, double* tmp, double* sol, cudaStream_t st) {
     TrsvArgs a;
     a.L = L; a.ldm = ldm; a.m = m;
     a.v = rhs; a.out = tmp;
@@ -338,6 +424,7 @@ struct TrsvBatchedArgs {
     double* v; int64_t strideV;      // rhs in, solution out (length m per LP)
     int m;
     const int* active;
+    double* out = nullptr;           // optional separate destination (same stride)
 };
 constexpr int TRSVB_NT = 256;
 constexpr int TRSVB_NW = TRSVB_NT / 32;
@@ -449,9 +536,24 @@ static __global__ void __launch_bounds__(TRSVB_NT, 3) k_trsv_batched(const TrsvB
         }
         __syncthreads();
     }
-    for (int i = tid; i < m; i += TRSVB_NT) v[i] = vec[i];
+    double* dst = a.out ? a.out + (size_t)bz * a.strideV : v;
+    for (int i = tid; i < m; i += TRSVB_NT) dst[i] = vec[i];
 }
 inline size_t trsv_batched_smem(int m) { return (size_t)(2 * 32 * 33 + m) * sizeof(double); }
+
+constexpr int TRSV_ONE_CTA_MAX_M = 2048;
+// rhs (destroyed) -> sol.  Orders up to 2048 run both sweeps in ONE CTA (no launch per block: the small and
+// mid-size Netlib LPs are launch-bound); larger ones use one launch per 64-wide block over all SMs.
+inline int potrs_single(const double* L, int64_t ldm, int m, double* rhs, double* tmp, double* sol, cudaStream_t st) {
+    if (m <= TRSV_ONE_CTA_MAX_M) {
+        TrsvBatchedArgs t;
+        t.L = L; t.ldm = ldm; t.strideM = 0; t.v = rhs; t.strideV = 0; t.m = m; t.active = nullptr; t.out = sol;
+        k_trsv_batched<<<1, TRSVB_NT, trsv_batched_smem(m), st>>>(t);
+        count_launch();
+        return launch_check();
+    }
+    return potrs_single_blocks(L, ldm, m, rhs, tmp, sol, st);
+}
 #endif
 
 }  // namespace ipm
