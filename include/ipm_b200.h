@@ -106,6 +106,22 @@ int ipm_sigma(ipm_handle *h, double out[3]);
 /* x += alpha_p dx; y += alpha_d dy; s += alpha_d ds with the corrector direction (corrected, main.py:694-696). */
 int ipm_update(ipm_handle *h, double alpha_p, double alpha_d);
 
+/* ---------------------------------------------------------------- stateless op level (HOST vectors)
+ * Pure-function seams of the reference that take no matrix.  Each call uploads its vectors, runs the same
+ * kernels the solver uses and copies the result back: for parity tests and reference-style driver loops.
+ * ipm_op_ratio_test: eta <= 0 -> predicted_stepsize (main.py:305-322); eta > 0 -> full_stepsize (main.py:604-626).
+ * ipm_op_sigma: out = { mu_aff, mu, sigma } (predicted + duality_gap, main.py:562-601).
+ * ipm_op_update: x += ap dx; y += ad dy; s += ad ds in place (corrected, main.py:694-696).
+ * ipm_solve_spd: z = M^-1 rhs by the safeguarded Cholesky (solve_linear on main.py:226's matrix, main.py:176-182). */
+int ipm_op_ratio_test(int device_ordinal, int n, const double *x, const double *dx, const double *s,
+                      const double *ds, double eta, double alpha[2]);
+int ipm_op_sigma(int device_ordinal, int n, const double *x, const double *s, const double *dx_aff,
+                 const double *ds_aff, double out[3]);
+int ipm_op_update(int device_ordinal, int m, int n, double *x, double *y, double *s, const double *dx,
+                  const double *dy, const double *ds, double alpha_p, double alpha_d);
+int ipm_solve_spd(int device_ordinal, int m, const double *M_rowmajor, const double *rhs, double pivot_rel_thresh,
+                  double *z, int *n_fixed);
+
 /* ---------------------------------------------------------------- solve level
  * Whole predictor-corrector loop on the device (interior_sparse main.py:760-815 when the problem
  * was loaded with ipm_load_csr, interior main.py:707-757 when loaded dense).  Starts from

@@ -1,11 +1,13 @@
 """B200-native Newton-step hot path of the predictor-corrector interior-point LP solver
 payakorn/InteriorPointMethod: hand-written sm_100a CUDA behind a C ABI (include/ipm_b200.h), with a thin
 Python mirror of the reference's call surface."""
-from .solver import (NewtonStep, Result, check_optimality, direction_corrected_sparse,  # noqa: F401
-                     direction_predicted_sparse, interior, interior_sparse, newton_iteration, solve)
+from .solver import (NewtonStep, Result, check_optimality, corrected, direction_corrected_sparse,  # noqa: F401
+                     direction_predicted_sparse, duality_gap, full_stepsize, interior, interior_sparse,
+                     newton_iteration, predicted_stepsize, solve, solve_linear)
 from .problems import (create_problem_from_mps, load_golden_problem, synthetic_dense_batch,  # noqa: F401
                        synthetic_dense_lp)
 
 __all__ = ["NewtonStep", "Result", "solve", "interior_sparse", "interior", "direction_predicted_sparse",
-           "direction_corrected_sparse", "check_optimality", "newton_iteration", "create_problem_from_mps",
+           "direction_corrected_sparse", "check_optimality", "predicted_stepsize", "full_stepsize", "duality_gap",
+           "corrected", "solve_linear", "newton_iteration", "create_problem_from_mps",
            "load_golden_problem", "synthetic_dense_lp", "synthetic_dense_batch"]

@@ -39,6 +39,11 @@ SYMBOLS = {
     "ipm_ratio_test": (c_int, [c_void_p, c_int, c_double, c_void_p]),
     "ipm_sigma": (c_int, [c_void_p, c_void_p]),
     "ipm_update": (c_int, [c_void_p, c_double, c_double]),
+    "ipm_op_ratio_test": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_void_p]),
+    "ipm_op_sigma": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ipm_op_update": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double,
+                              c_double]),
+    "ipm_solve_spd": (c_int, [c_int, c_int, c_void_p, c_void_p, c_double, c_void_p, _ip]),
     "ipm_solve": (c_int, [c_void_p, c_double, c_int, c_int, c_void_p, c_void_p, c_void_p, _dp, _ip, _ip, c_void_p]),
     "ipm_solve_batched_dense": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_double, c_int,
                                         c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -13,7 +13,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libipm_b200.so")
-SOURCES = ["ipm_single.cu", "ipm_batched.cu", "ipm_tools.cu"]
+SOURCES = ["ipm_single.cu", "ipm_batched.cu", "ipm_tools.cu", "ipm_ops.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

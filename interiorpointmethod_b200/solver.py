@@ -267,6 +267,63 @@ def direction_corrected_sparse(A, b, c, x, y, s, delta_x_aff, delta_y_aff, delta
     return ns.direction(1)
 
 
+def predicted_stepsize(delta_x_aff, delta_y_aff, delta_s_aff, x, s, device: int = 0):
+    """main.py:305-322: (alpha_primal, alpha_dual) = min({-v_i/dv_i : dv_i < 0} U {1}) for (x, dx) and (s, ds)."""
+    return _ratio(x, delta_x_aff, s, delta_s_aff, 0.0, device)
+
+
+def full_stepsize(x, y, s, delta_x, delta_y, delta_s, delta_x_aff=None, delta_y_aff=None, delta_s_aff=None,
+                  device: int = 0):
+    """main.py:604-626: min(1, 0.91 * ratio) for both step lengths (always <= 0.91)."""
+    return _ratio(x, delta_x, s, delta_s, ETA, device)
+
+
+def _ratio(x, dx, s, ds, eta, device):
+    lib = _lib.load()
+    xv, dxv, sv, dsv = _f64(x), _f64(dx), _f64(s), _f64(ds)
+    out = np.empty(2)
+    _lib.check(lib.ipm_op_ratio_test(int(device), xv.size, _ptr(xv), _ptr(dxv), _ptr(sv), _ptr(dsv), float(eta),
+                                     _ptr(out)), None, "ipm_op_ratio_test")
+    return float(out[0]), float(out[1])
+
+
+def duality_gap(A, x, y, s, delta_x_aff, delta_y_aff, delta_s_aff, device: int = 0):
+    """main.py:588-601: (mu_aff, mu_k, centering) with centering = (mu_aff/mu_k)**3, unclamped."""
+    lib = _lib.load()
+    xv, sv, dxv, dsv = _f64(x), _f64(s), _f64(delta_x_aff), _f64(delta_s_aff)
+    out = np.empty(3)
+    _lib.check(lib.ipm_op_sigma(int(device), xv.size, _ptr(xv), _ptr(sv), _ptr(dxv), _ptr(dsv), _ptr(out)), None,
+               "ipm_op_sigma")
+    return float(out[0]), float(out[1]), float(out[2])
+
+
+def corrected(x, y, s, delta_x, delta_y, delta_s, delta_x_aff=None, delta_y_aff=None, delta_s_aff=None,
+              device: int = 0):
+    """main.py:663-697: full_stepsize then x + ap*dx, y + ad*dy, s + ad*ds; returns new (x, y, s) columns."""
+    lib = _lib.load()
+    ap, ad = full_stepsize(x, y, s, delta_x, delta_y, delta_s, device=device)
+    xv, yv, sv = _f64(x).copy(), _f64(y).copy(), _f64(s).copy()
+    dxv, dyv, dsv = _f64(delta_x), _f64(delta_y), _f64(delta_s)
+    _lib.check(lib.ipm_op_update(int(device), yv.size, xv.size, _ptr(xv), _ptr(yv), _ptr(sv), _ptr(dxv), _ptr(dyv),
+                                 _ptr(dsv), ap, ad), None, "ipm_op_update")
+    return _col(xv), _col(yv), _col(sv)
+
+
+def solve_linear(A, b, method="gpu", device: int = 0, tau: float = 1e-30):
+    """main.py:176-182 for the normal-equations matrix of main.py:226 (symmetric positive semidefinite A):
+    safeguarded Cholesky + triangular sweeps on the GPU; returns an (N,1) array like the reference."""
+    lib = _lib.load()
+    if _sp is not None and _sp.issparse(A):
+        A = A.toarray()
+    Ad = np.ascontiguousarray(np.asarray(A, dtype=np.float64))
+    rhs = _f64(b, Ad.shape[0])
+    z = np.empty(Ad.shape[0])
+    nf = ctypes.c_int(0)
+    _lib.check(lib.ipm_solve_spd(int(device), Ad.shape[0], _ptr(Ad), _ptr(rhs), float(tau), _ptr(z), ctypes.byref(nf)),
+               None, "ipm_solve_spd")
+    return _col(z)
+
+
 def newton_iteration(ns: NewtonStep, tau: float = 1e-30):
     """One predictor-corrector iteration through the op-level entry points (main.py:781-805); returns the
     per-op results so parity tests can compare each against the oracle."""

@@ -361,3 +361,30 @@ def test_batched_potrf_safeguard(ipm):
     assert nf.value == 2
     L = torch.tril(M)
     assert L[2, 40, 40].item() == 1e64 and L[4, 255, 255].item() == 1e64 and torch.isfinite(L).all()
+
+
+def test_stateless_reference_shaped_ops(ipm, orc):
+    """predicted_stepsize / duality_gap / full_stepsize / corrected / solve_linear with the reference's signatures
+    (main.py:305, 588, 604, 663, 176) on vectors the reference produced (trace_AFIRO.npz)."""
+    tr = np.load(os.path.join(GOLDEN, "trace_AFIRO.npz"))
+    for k in (0, 10, 60):
+        x, y, s = tr["k%d_x" % k], tr["k%d_y" % k], tr["k%d_s" % k]
+        dxa, dya, dsa = tr["k%d_dx_aff" % k], tr["k%d_dy_aff" % k], tr["k%d_ds_aff" % k]
+        dx, dy, ds = tr["k%d_dx" % k], tr["k%d_dy" % k], tr["k%d_ds" % k]
+        ap, ad = ipm.predicted_stepsize(dxa, dya, dsa, x, s)
+        assert np.allclose((ap, ad), tr["k%d_alpha_aff" % k], rtol=1e-14, atol=0)
+        mu_aff, mu, sigma = ipm.duality_gap(None, x, y, s, dxa, dya, dsa)
+        assert abs(mu - float(tr["k%d_mu" % k])) <= 1e-13 * abs(float(tr["k%d_mu" % k]))
+        assert abs(mu_aff - float(tr["k%d_mu_aff" % k])) <= 1e-9 * abs(float(tr["k%d_mu" % k]))
+        a2 = ipm.full_stepsize(x, y, s, dx, dy, ds, dxa, dya, dsa)
+        assert np.allclose(a2, tr["k%d_alpha" % k], rtol=1e-14, atol=0)
+        nx, ny, ns_ = ipm.corrected(x, y, s, dx, dy, ds, dxa, dya, dsa)
+        assert np.allclose(nx, x + a2[0] * dx, rtol=1e-15) and np.allclose(ny, y + a2[1] * dy, rtol=1e-15)
+        assert np.allclose(ns_, s + a2[1] * ds, rtol=1e-15)
+    rng = np.random.default_rng(5)
+    B = rng.standard_normal((300, 500))
+    M = B @ B.T
+    rhs = rng.standard_normal((300, 1))
+    z = ipm.solve_linear(M, rhs)
+    assert z.shape == (300, 1)
+    assert np.linalg.norm(M @ z - rhs) <= 1e-9 * np.linalg.norm(rhs)
