@@ -266,8 +266,9 @@ static __global__ void __launch_bounds__(KBC_NT, 2) kb_chol(const CholBatchedArg
                 for (int k0 = 0; k0 < j0; k0 += KBC_KC) {
                     const int kc = (j0 - k0 < KBC_KC) ? (j0 - k0) : KBC_KC;
                     kbc_update_bar();                                  // previous chunk fully consumed
+                    const int kshift = (kc == KBC_KC) ? 6 : 5;         // kc is 64 or 32 (j0 is a multiple of 32)
                     for (int idx = tid - 32; idx < 32 * kc; idx += KBC_UW * 32) {
-                        const int r = idx / kc, k = idx - r * kc;
+                        const int r = idx >> kshift, k = idx & (kc - 1);
                         Bs[r * KBC_LDB + k] = (j1 + r < m) ? Mb[(size_t)(j1 + r) * ldm + k0 + k] : 0.0;
                     }
                     kbc_update_bar();

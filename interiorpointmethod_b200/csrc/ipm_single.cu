@@ -1,6 +1,7 @@
 // C ABI (include/ipm_b200.h), single-LP part: handle, problem upload, op-level entry points that mirror the
 // reference's Python seams (main.py:162-322, 562-697) and the device-resident predictor-corrector loop.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -50,6 +51,11 @@ struct ipm_handle {
     double tol = 1e-8;
     double eta = 0.91;            // main.py:607
     double tau = 1e-30;
+    // one predictor-corrector iteration captured as a CUDA graph (the small Netlib LPs are launch-bound)
+    cudaGraphExec_t gexec = nullptr;
+    double g_tol = 0.0, g_tau = 0.0;
+    bool use_graph = true;
+    int64_t launches_per_graph = 0;
     bool have_resid = false, have_M = false, have_factor = false, have_pred = false, have_sigma = false,
          have_corr = false;
     std::string err;
@@ -80,6 +86,7 @@ int cuda_fail(ipm_handle* h) {
 
 void free_problem(ipm_handle* h) {
     cudaSetDevice(h->dev);
+    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
     void* ptrs[] = {h->rowptr, h->colind, h->t_rowptr, h->t_colind, h->val, h->t_val, h->ad, h->out_idx,
                     h->prod_ptr, h->pa, h->pb, h->A_own, h->gemv_partial, h->slab, h->M};
     for (void* p : ptrs)
@@ -270,6 +277,7 @@ int ipm_create(ipm_handle** out, int device_ordinal) {
     }
     ipm_handle* h = new ipm_handle();
     h->dev = device_ordinal;
+    h->use_graph = (getenv("IPM_NO_GRAPH") == nullptr);
     auto init = [&]() -> int {
         IPM_CUDA_OK(cudaSetDevice(h->dev));
         IPM_CUDA_OK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
@@ -553,18 +561,53 @@ int ipm_solve(ipm_handle* h, double tol, int max_iter, int y0_is_one, double* x,
     H_TRY(ipm_init_state(h, y0_is_one));
     int k = 0;
     const double tau = h->tau;
-    for (;;) {
-        H_TRY(residual_step(h));                 // check_optimality, main.py:780
-        H_TRY(fetch_scal(h));
-        if (!(h->h_scal[S_CONT] > 0.5) || k >= max_iter) break;
+    auto body = [&]() -> int {
         H_TRY(assemble_step(h));                 // main.py:223-224
         H_TRY(factor_step(h, tau));              // main.py:176-182 (one factorisation per iteration)
         H_TRY(direction_step(h, 0));             // main.py:783
         H_TRY(sigma_step(h));                    // main.py:795
         H_TRY(direction_step(h, 1));             // main.py:799
         H_TRY(update_step(h, -1.0, -1.0));       // main.py:803
+        H_TRY(residual_step(h));                 // check_optimality of the new iterate, main.py:780
+        H_CUDA(cudaMemcpyAsync(h->h_scal, h->scal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+        return IPM_OK;
+    };
+    if (h->gexec && (h->g_tol != tol || h->g_tau != tau)) {
+        cudaGraphExecDestroy(h->gexec);
+        h->gexec = nullptr;
+    }
+    H_TRY(residual_step(h));                     // check_optimality, main.py:780
+    H_TRY(fetch_scal(h));
+    while (h->h_scal[S_CONT] > 0.5 && k < max_iter) {
+        if (h->use_graph && k >= 1) {
+            // iteration 0 ran eagerly (it also sets the kernels' shared-memory attributes); from here on the
+            // whole iteration, next residual check and the read-back of the scalars are one graph launch
+            if (!h->gexec) {
+                cudaGraph_t graph = nullptr;
+                H_CUDA(cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
+                const int64_t launches_before = g_launches.load();
+                const int rc_body = body();
+                h->launches_per_graph = g_launches.load() - launches_before;
+                cudaError_t ce = cudaStreamEndCapture(h->st, &graph);
+                if (rc_body != IPM_OK) { if (graph) cudaGraphDestroy(graph); return rc_body; }
+                if (ce != cudaSuccess) return fail(h, IPM_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
+                ce = cudaGraphInstantiate(&h->gexec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ce != cudaSuccess) return fail(h, IPM_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(ce));
+                h->g_tol = tol; h->g_tau = tau;
+            } else {
+                count_launch(h->launches_per_graph);
+            }
+            H_CUDA(cudaGraphLaunch(h->gexec, h->st));
+            H_CUDA(cudaStreamSynchronize(h->st));
+        } else {
+            H_TRY(body());
+            H_CUDA(cudaStreamSynchronize(h->st));
+        }
         ++k;
     }
+    h->have_resid = true;
+    h->have_M = h->have_factor = h->have_pred = h->have_sigma = h->have_corr = false;
     const double* hs = h->h_scal;
     const bool finite = std::isfinite(hs[S_NRB]) && std::isfinite(hs[S_NRC]) && std::isfinite(hs[S_XS]) &&
                         std::isfinite(hs[S_OBJ]);
