@@ -429,17 +429,32 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
     }
     kb_init<<<B, 256, 0, st>>>(a);
     count_launch();
-    int it = 0;
-    for (;;) {
+    // The host reads the "LPs still active" counter of check k only after check k+1 has been enqueued, so the
+    // GPU never idles on the host round trip; the price is one empty iteration (every kernel skips inactive LPs)
+    // after the last LP has converged.
+    unsigned* nact_base = a.n_active;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    IPM_CUDA_OK(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+    IPM_CUDA_OK(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    struct EvGuard { cudaEvent_t* e; ~EvGuard() { cudaEventDestroy(e[0]); cudaEventDestroy(e[1]); } } ev_guard{ev};
+    int it = 0, bodies = 0;
+    for (;; ++it) {
+        const int slot = it & 1;
+        a.n_active = nact_base + slot * 16;
         IPM_CUDA_OK(cudaMemsetAsync(a.n_active, 0, sizeof(unsigned), st));
         g_prof.segment(st);
         kb_residual<NPL><<<B, KB_NT, smem_res, st>>>(a);
         count_launch();
         g_prof.end_phase(PH_RESID, st);
-        IPM_CUDA_OK(cudaMemcpyAsync(w.h_nact, a.n_active, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-        IPM_CUDA_OK(cudaStreamSynchronize(st));
-        if (*w.h_nact == 0) break;
-        if (g_prof.enabled) g_prof.lp_iterations += *w.h_nact;
+        IPM_CUDA_OK(cudaMemcpyAsync(w.h_nact + slot, a.n_active, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        IPM_CUDA_OK(cudaEventRecord(ev[slot], st));
+        if (it > 0) {
+            IPM_CUDA_OK(cudaEventSynchronize(ev[slot ^ 1]));
+            const unsigned cnt = w.h_nact[slot ^ 1];
+            if (cnt == 0) break;
+            ++bodies;
+            if (g_prof.enabled) g_prof.lp_iterations += cnt;
+        }
         g_prof.segment(st);
         DmmaArgs g;
         g.P = a.A; g.ldp = n; g.strideP = (int64_t)m * n;
@@ -466,9 +481,10 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
         }
         g_prof.end_phase(PH_SOLVE, st);
         IPM_TRY(launch_check());
-        ++it;
     }
-    if (iterations_run) *iterations_run = it;
+    a.n_active = nact_base;
+    IPM_CUDA_OK(cudaStreamSynchronize(st));
+    if (iterations_run) *iterations_run = bodies;
     return IPM_OK;
 }
 
@@ -584,7 +600,7 @@ int ipm_solve_batched_dense_d(int device_ordinal, int B, int m, int n, const dou
     }
     unsigned* h_nact = nullptr;
     int rc = [&]() -> int {
-        IPM_CUDA_OK(cudaMallocHost(&h_nact, sizeof(unsigned)));
+        IPM_CUDA_OK(cudaMallocHost(&h_nact, 2 * sizeof(unsigned)));
         IPM_TRY(solve_on_device(B, m, n, A_d, b_d, c_d, tol, max_iter, obj_d, iters_d, status_d, x_d, work_d, h_nact,
                                 0, iterations_run));
         IPM_CUDA_OK(cudaStreamSynchronize(0));
@@ -678,7 +694,7 @@ int ipm_solve_batched_dense(int device_ordinal, int B, int m, int n, const doubl
                 IPM_CUDA_OK(cudaEventCreateWithFlags(&C.ev_in[i], cudaEventDisableTiming));
                 IPM_CUDA_OK(cudaEventCreateWithFlags(&C.ev_free[i], cudaEventDisableTiming));
             }
-            IPM_CUDA_OK(cudaMallocHost(&C.h_nact, sizeof(unsigned)));
+            IPM_CUDA_OK(cudaMallocHost(&C.h_nact, 2 * sizeof(unsigned)));
         }
         {   // (re)size the cached buffers; capacities are tracked for buffer 0 and applied to both
             const int64_t nA = (int64_t)chunk * m * n * 8, nb = (int64_t)chunk * m * 8, nc = (int64_t)chunk * n * 8;
