@@ -389,23 +389,144 @@ static __global__ void __launch_bounds__(TRSV_NT) k_trsv_bwd(const TrsvArgs a) {
     a.v[k] -= acc;
 }
 
+// ---- 128-wide variant for large orders: one launch per 128 columns, 256 threads.  Every CTA solves the
+// 128x128 triangular block in shared memory (4 sub-blocks of 32: warp 0 solves, all threads update) and then
+// applies its share of the update to the rest of the vector.
+constexpr int TRSV128_NB = 128;
+constexpr int TRSV128_NT = 256;
+constexpr int TRSV128_LD = TRSV128_NB + 1;
+inline size_t trsv128_smem() { return (size_t)(TRSV128_NB * TRSV128_LD + TRSV128_NB) * sizeof(double); }
+
+__device__ __forceinline__ void trsv128_load(const TrsvArgs& a, double* S, double* vec) {
+    const int tid = threadIdx.x, nb = a.nb;
+    const double* Ld = a.L + (size_t)a.j0 * a.ldm + a.j0;
+    for (int idx = tid; idx < nb * nb; idx += TRSV128_NT) {
+        const int i = idx / nb, j = idx - i * nb;
+        if (j <= i) S[i * TRSV128_LD + j] = Ld[(size_t)i * a.ldm + j];
+    }
+    if (tid < nb) vec[tid] = a.v[a.j0 + tid];
+    __syncthreads();
+}
+
+static __global__ void __launch_bounds__(TRSV128_NT, 1) k_trsv_fwd128(const TrsvArgs a) {
+    extern __shared__ __align__(16) double sm128[];
+    double* S = sm128;
+    double* vec = sm128 + TRSV128_NB * TRSV128_LD;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nb = a.nb, j0 = a.j0;
+    trsv128_load(a, S, vec);
+    for (int c0 = 0; c0 < nb; c0 += 32) {
+        const int w = (nb - c0 < 32) ? (nb - c0) : 32;
+        if (warp == 0) {
+            const bool ok = lane < w;
+            double x = ok ? vec[c0 + lane] : 0.0;
+            const double inv = ok ? 1.0 / S[(c0 + lane) * TRSV128_LD + c0 + lane] : 0.0;
+#pragma unroll 8
+            for (int j = 0; j < w; ++j) {
+                const double zj = __shfl_sync(0xffffffffu, x * inv, j);
+                if (lane == j) x = zj;
+                else if (lane > j && ok) x -= S[(c0 + lane) * TRSV128_LD + c0 + j] * zj;
+            }
+            if (ok) vec[c0 + lane] = x;
+        }
+        __syncthreads();
+        for (int r = c0 + w + tid; r < nb; r += TRSV128_NT) {
+            const double* row = S + r * TRSV128_LD + c0;
+            double acc = 0.0;
+#pragma unroll 8
+            for (int c = 0; c < w; ++c) acc += row[c] * vec[c0 + c];
+            vec[r] -= acc;
+        }
+        __syncthreads();
+    }
+    if (blockIdx.x == 0 && tid < nb) a.out[j0 + tid] = vec[tid];
+    const int r = j0 + nb + blockIdx.x * TRSV128_NT + tid;
+    if (r >= a.m) return;
+    const double* row = a.L + (size_t)r * a.ldm + j0;
+    double acc0 = 0.0, acc1 = 0.0;
+    if (nb == TRSV128_NB) {
+        const double2* rp = reinterpret_cast<const double2*>(row);
+#pragma unroll 16
+        for (int q = 0; q < TRSV128_NB / 2; ++q) {
+            const double2 l = rp[q];
+            acc0 += l.x * vec[2 * q];
+            acc1 += l.y * vec[2 * q + 1];
+        }
+    } else {
+        for (int k = 0; k < nb; ++k) acc0 += row[k] * vec[k];
+    }
+    a.v[r] -= acc0 + acc1;
+}
+
+static __global__ void __launch_bounds__(TRSV128_NT, 1) k_trsv_bwd128(const TrsvArgs a) {
+    extern __shared__ __align__(16) double sm128[];
+    double* S = sm128;
+    double* vec = sm128 + TRSV128_NB * TRSV128_LD;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nb = a.nb, j0 = a.j0;
+    trsv128_load(a, S, vec);
+    const int nsb = (nb + 31) >> 5;
+    for (int sb = nsb - 1; sb >= 0; --sb) {
+        const int c0 = sb << 5;
+        const int w = (nb - c0 < 32) ? (nb - c0) : 32;
+        if (warp == 0) {
+            const bool ok = lane < w;
+            double x = ok ? vec[c0 + lane] : 0.0;
+            const double inv = ok ? 1.0 / S[(c0 + lane) * TRSV128_LD + c0 + lane] : 0.0;
+#pragma unroll 8
+            for (int i = w - 1; i >= 0; --i) {
+                const double yi = __shfl_sync(0xffffffffu, x * inv, i);
+                if (lane == i) x = yi;
+                else if (lane < i) x -= S[(c0 + i) * TRSV128_LD + c0 + lane] * yi;
+            }
+            if (ok) vec[c0 + lane] = x;
+        }
+        __syncthreads();
+        for (int k = tid; k < c0; k += TRSV128_NT) {
+            double acc = 0.0;
+#pragma unroll 8
+            for (int i = 0; i < w; ++i) acc += S[(c0 + i) * TRSV128_LD + k] * vec[c0 + i];
+            vec[k] -= acc;
+        }
+        __syncthreads();
+    }
+    if (blockIdx.x == 0 && tid < nb) a.out[j0 + tid] = vec[tid];
+    const int k = blockIdx.x * TRSV128_NT + tid;
+    if (k >= j0) return;
+    const double* col = a.L + (size_t)j0 * a.ldm + k;
+    double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll 8
+    for (int i = 0; i + 1 < nb; i += 2) {
+        acc0 += col[(size_t)i * a.ldm] * vec[i];
+        acc1 += col[(size_t)(i + 1) * a.ldm] * vec[i + 1];
+    }
+    if (nb & 1) acc0 += col[(size_t)(nb - 1) * a.ldm] * vec[nb - 1];
+    a.v[k] -= acc0 + acc1;
+}
+
 // rhs (destroyed) -> sol.  L is the factor produced by potrf_blocked.
 inline int potrs_single_blocks(const double* L, int64_t ldm, int m, double* rhs, double* tmp, double* sol, cudaStream_t st) {
+    static int configured_dev = -1;
+    int dev = 0;
+    IPM_CUDA_OK(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+        IPM_CUDA_OK(cudaFuncSetAttribute(k_trsv_fwd128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsv128_smem()));
+        IPM_CUDA_OK(cudaFuncSetAttribute(k_trsv_bwd128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsv128_smem()));
+        configured_dev = dev;
+    }
     TrsvArgs a;
     a.L = L; a.ldm = ldm; a.m = m;
     a.v = rhs; a.out = tmp;
-    for (int j0 = 0; j0 < m; j0 += TRSV_NB) {
-        a.j0 = j0; a.nb = (m - j0 < TRSV_NB) ? (m - j0) : TRSV_NB;
+    for (int j0 = 0; j0 < m; j0 += TRSV128_NB) {
+        a.j0 = j0; a.nb = (m - j0 < TRSV128_NB) ? (m - j0) : TRSV128_NB;
         const int below = m - (j0 + a.nb);
-        k_trsv_fwd<<<(below > 0 ? ceil_div(below, TRSV_NT) : 1), TRSV_NT, 0, st>>>(a);
+        k_trsv_fwd128<<<(below > 0 ? ceil_div(below, TRSV128_NT) : 1), TRSV128_NT, trsv128_smem(), st>>>(a);
         count_launch();
     }
     a.v = tmp; a.out = sol;
-    const int nblk = ceil_div(m, TRSV_NB);
+    const int nblk = ceil_div(m, TRSV128_NB);
     for (int jb = nblk - 1; jb >= 0; --jb) {
-        a.j0 = jb * TRSV_NB; a.nb = (m - a.j0 < TRSV_NB) ? (m - a.j0) : TRSV_NB;
+        a.j0 = jb * TRSV128_NB; a.nb = (m - a.j0 < TRSV128_NB) ? (m - a.j0) : TRSV128_NB;
         const int left = a.j0;
-        k_trsv_bwd<<<(left > 0 ? ceil_div(left, TRSV_NT) : 1), TRSV_NT, 0, st>>>(a);
+        k_trsv_bwd128<<<(left > 0 ? ceil_div(left, TRSV128_NT) : 1), TRSV128_NT, trsv128_smem(), st>>>(a);
         count_launch();
     }
     return launch_check();

@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "chol.cuh"
+#include "potrf_auto.cuh"
 #include "common.cuh"
 #include "vec.cuh"
 
@@ -135,7 +136,7 @@ int ipm_solve_spd(int device_ordinal, int m, const double* M_rowmajor, const dou
     IPM_TRY(sc.dev(&scal, S_COUNT));
     IPM_CUDA_OK(cudaMemcpy2D(dM, ldm * sizeof(double), M_rowmajor, (size_t)m * sizeof(double),
                              (size_t)m * sizeof(double), m, cudaMemcpyHostToDevice));
-    IPM_TRY((potrf_blocked<128, 512, 64>(dM, ldm, 0, m, 1, scal, 0, pivot_rel_thresh, nullptr, 0)));
+    IPM_TRY((potrf_single_auto(dM, ldm, m, scal, pivot_rel_thresh, 0)));
     IPM_TRY(potrs_single(dM, ldm, m, dr, dt, dz, 0));
     IPM_CUDA_OK(cudaMemcpy(z, dz, m * sizeof(double), cudaMemcpyDeviceToHost));
     if (n_fixed) {

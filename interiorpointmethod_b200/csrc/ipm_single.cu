@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "chol.cuh"
+#include "potrf_auto.cuh"
 #include "common.cuh"
 #include "dense.cuh"
 #include "dmma_gemm.cuh"
@@ -196,7 +197,7 @@ int assemble_step(ipm_handle* h) {
 }
 
 int factor_step(ipm_handle* h, double tau) {
-    H_TRY((potrf_blocked<128, 512, 64>(h->M, h->ldm, 0, h->m, 1, h->scal, 0, tau, nullptr, h->st)));
+    H_TRY((potrf_single_auto(h->M, h->ldm, h->m, h->scal, tau, h->st)));
     h->have_factor = true;
     h->have_M = false;
     return IPM_OK;
@@ -645,7 +646,7 @@ int ipm_potrf_d(int device_ordinal, int m, double* M_d, int64_t ldm, double pivo
     IPM_CUDA_OK(cudaSetDevice(device_ordinal));
     double* scal = nullptr;
     IPM_CUDA_OK(cudaMalloc(&scal, S_COUNT * sizeof(double)));
-    int rc = potrf_blocked<128, 512, 64>(M_d, ldm, 0, m, 1, scal, 0, pivot_rel_thresh, nullptr, 0);
+    int rc = potrf_single_auto(M_d, ldm, m, scal, pivot_rel_thresh, 0);
     double hs[S_COUNT];
     if (rc == IPM_OK) {
         cudaError_t e = cudaMemcpy(hs, scal, sizeof(hs), cudaMemcpyDeviceToHost);
