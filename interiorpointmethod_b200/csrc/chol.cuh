@@ -63,9 +63,19 @@ static __global__ void __launch_bounds__(NT, 1) k_chol_diag(const CholArgs a) {
     const int nb = a.nb, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = NT / 32;
 
-    for (int idx = tid; idx < nb * nb; idx += NT) {
-        const int i = idx / nb, j = idx - i * nb;
-        if (j <= i) S[i * LD + j] = Mb[(size_t)i * a.ldm + j];
+    if (nb == NB) {
+        // full block: compile-time index math and 8 independent loads in flight per thread
+#pragma unroll 8
+        for (int idx = tid; idx < NB * NB; idx += NT) {
+            const int i = idx / NB, j = idx % NB;
+            if (j <= i) S[i * LD + j] = Mb[(size_t)i * a.ldm + j];
+        }
+    } else {
+#pragma unroll 4
+        for (int idx = tid; idx < nb * nb; idx += NT) {
+            const int i = idx / nb, j = idx - i * nb;
+            if (j <= i) S[i * LD + j] = Mb[(size_t)i * a.ldm + j];
+        }
     }
     if (tid == 0) s_nfix = 0;
     __syncthreads();
@@ -177,8 +187,10 @@ constexpr size_t chol_diag_smem() { return (size_t)(NB * (NB + 1) + 1 + 32 * 34 
 // Rows below the diagonal block: solve X L_JJ^T = A_panel, one thread per row, forward substitution in
 // register blocks of 8 columns; L_JJ^T lives in shared memory (broadcast 128-bit reads), the row's earlier
 // x values in a [k][row] shared array (conflict-free).   grid (ceil(rows/ROWS),1,batch), ROWS threads.
+constexpr int TRSM_NT = 256;      // all threads stage L_JJ^T, the first ROWS of them own one row each
 template <int NB, int ROWS>
-static __global__ void __launch_bounds__(ROWS, 1) k_chol_trsm(const CholArgs a) {
+static __global__ void __launch_bounds__(TRSM_NT, 1) k_chol_trsm(const CholArgs a) {
+    static_assert(ROWS <= TRSM_NT, "one thread per row");
     constexpr int LDT = NB + 2;
     extern __shared__ __align__(16) double smem[];
     double* LsT = smem;                    // [NB][LDT]   LsT[k][j] = L[j][k], j >= k
@@ -189,13 +201,14 @@ static __global__ void __launch_bounds__(ROWS, 1) k_chol_trsm(const CholArgs a) 
     const int tid = threadIdx.x;
     const int j0 = a.j0, j1 = a.j0 + NB;
     const double* Ld = Mb + (size_t)j0 * a.ldm + j0;
-    for (int idx = tid; idx < NB * NB; idx += ROWS) {
-        const int j = idx / NB, k = idx - j * NB;
+#pragma unroll 8
+    for (int idx = tid; idx < NB * NB; idx += TRSM_NT) {
+        const int j = idx / NB, k = idx % NB;
         if (k <= j) LsT[k * LDT + j] = Ld[(size_t)j * a.ldm + k];
     }
     __syncthreads();
     const int r = j1 + blockIdx.x * ROWS + tid;
-    if (r >= a.m) return;
+    if (tid >= ROWS || r >= a.m) return;
     double* row = Mb + (size_t)r * a.ldm + j0;
 #pragma unroll 1
     for (int jb = 0; jb < NB; jb += 8) {
@@ -263,7 +276,7 @@ inline int potrf_blocked(double* M, int64_t ldm, int64_t strideM, int m, int bat
         count_launch();
         const int below = m - (j0 + NB);
         if (below > 0) {
-            kt<<<dim3(ceil_div(below, ROWS), 1, batch), ROWS, chol_trsm_smem<NB, ROWS>(), st>>>(a);
+            kt<<<dim3(ceil_div(below, ROWS), 1, batch), TRSM_NT, chol_trsm_smem<NB, ROWS>(), st>>>(a);
             count_launch();
             DmmaArgs g;
             const double* panel = M + (size_t)(j0 + NB) * ldm + j0;
@@ -400,9 +413,18 @@ inline size_t trsv128_smem() { return (size_t)(TRSV128_NB * TRSV128_LD + TRSV128
 __device__ __forceinline__ void trsv128_load(const TrsvArgs& a, double* S, double* vec) {
     const int tid = threadIdx.x, nb = a.nb;
     const double* Ld = a.L + (size_t)a.j0 * a.ldm + a.j0;
-    for (int idx = tid; idx < nb * nb; idx += TRSV128_NT) {
-        const int i = idx / nb, j = idx - i * nb;
-        if (j <= i) S[i * TRSV128_LD + j] = Ld[(size_t)i * a.ldm + j];
+    if (nb == TRSV128_NB) {
+#pragma unroll 8
+        for (int idx = tid; idx < TRSV128_NB * TRSV128_NB; idx += TRSV128_NT) {
+            const int i = idx / TRSV128_NB, j = idx % TRSV128_NB;
+            if (j <= i) S[i * TRSV128_LD + j] = Ld[(size_t)i * a.ldm + j];
+        }
+    } else {
+#pragma unroll 4
+        for (int idx = tid; idx < nb * nb; idx += TRSV128_NT) {
+            const int i = idx / nb, j = idx - i * nb;
+            if (j <= i) S[i * TRSV128_LD + j] = Ld[(size_t)i * a.ldm + j];
+        }
     }
     if (tid < nb) vec[tid] = a.v[a.j0 + tid];
     __syncthreads();

@@ -116,6 +116,7 @@ static __global__ void __launch_bounds__(KBC_NT, 2) kb_chol(const CholBatchedArg
     {
         double v = red_identity<RED_MAX>();
         for (int i = tid; i < m; i += KBC_NT) v = fmax(v, Mb[(size_t)i * ldm + i]);
+#pragma unroll 8
         for (int idx = tid; idx < m * 32; idx += KBC_NT) {
             const int r = idx >> 5, c = idx & 31;
             const double val = (c < m) ? Mb[(size_t)r * ldm + c] : 0.0;
@@ -267,6 +268,7 @@ static __global__ void __launch_bounds__(KBC_NT, 2) kb_chol(const CholBatchedArg
                     const int kc = (j0 - k0 < KBC_KC) ? (j0 - k0) : KBC_KC;
                     kbc_update_bar();                                  // previous chunk fully consumed
                     const int kshift = (kc == KBC_KC) ? 6 : 5;         // kc is 64 or 32 (j0 is a multiple of 32)
+#pragma unroll 5
                     for (int idx = tid - 32; idx < 32 * kc; idx += KBC_UW * 32) {
                         const int r = idx >> kshift, k = idx & (kc - 1);
                         Bs[r * KBC_LDB + k] = (j1 + r < m) ? Mb[(size_t)(j1 + r) * ldm + k0 + k] : 0.0;
