@@ -344,7 +344,9 @@ def main():
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("syrk_batched_dram_bytes_per_launch")
+            per_lp = json.load(open(tp)).get("syrk_batched_dram_bytes_per_lp")
+            # ncu capture (one launch, all LPs active) scaled to the average number of active LPs per launch
+            traffic = per_lp * float(lp_it.value) / max(1, calls[1]) if per_lp else None
         except Exception:
             traffic = None
     phase_total = sum(ms) * 1e-3
