@@ -615,7 +615,8 @@ static __global__ void __launch_bounds__(TRSVB_NT, 3) k_trsv_batched(const TrsvB
         if (i0 > 0) {
             // rows warp, warp+8, warp+16, warp+24 of the block at once: all loads issued before any reduction
             double acc[4] = {0.0, 0.0, 0.0, 0.0};
-            for (int k = lane; k < i0; k += 32) {
+#pragma unroll 4
+            for (int k = lane; k < i0; k += 32) {       // unrolled: up to 16 independent row loads in flight
                 const double zk = vec[k];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {

@@ -671,8 +671,8 @@ int ipm_solve_batched_dense(int device_ordinal, int B, int m, int n, const doubl
     // by 3x up to a quarter of the batch; the copy of chunk k+1 runs on the copy stream while chunk k is solved.
     std::vector<int> first_of, count_of;
     {
-        const int cap = std::max(256, ceil_div(B, 4));
-        int next = std::max(256, B / 16), at = 0;
+        const int cap = std::max(512, ceil_div(B, 4));       // small chunks leave SMs idle (one CTA per LP)
+        int next = std::max(512, B / 16), at = 0;
         while (at < B) {
             const int cnt = std::min(std::min(next, cap), B - at);
             first_of.push_back(at);
