@@ -683,6 +683,123 @@ static __global__ void __launch_bounds__(TRSVB_NT, 3) k_trsv_batched(const TrsvB
     double* dst = a.out ? a.out + (size_t)bz * a.strideV : v;
     for (int i = tid; i < m; i += TRSVB_NT) dst[i] = vec[i];
 }
+// ---- variant for m <= 256 (at most 8 diagonal blocks): the 32-step substitution chains of the diagonal blocks
+// were the critical path (every other warp waited on warp 0), so each warp first INVERTS one 32x32 diagonal block
+// (lane j solves L x = e_j in registers, no cross-lane traffic) and both sweeps apply the inverse as a 32x32
+// mat-vec.  The off-diagonal part is unchanged (plain substitution by blocks).
+constexpr int TRSVI_MAX_BLK = 8;
+inline size_t trsv_batched_inv_smem(int m) { return (size_t)(TRSVI_MAX_BLK * 32 * 33 + m + 32 * TRSVB_NW) * sizeof(double); }
+
+static __global__ void __launch_bounds__(TRSVB_NT, 3) k_trsv_batched_inv(const TrsvBatchedArgs a) {
+    extern __shared__ __align__(16) double smem_ti[];
+    double* Linv = smem_ti;                              // [8][32][33] block inverses (staging area first)
+    double* vec = smem_ti + TRSVI_MAX_BLK * 32 * 33;     // [m]
+    double* dinv = vec + a.m;                            // [8 warps][32]
+    const int bz = blockIdx.x;
+    if (a.active && a.active[bz] == 0) return;
+    const double* L = a.L + (size_t)bz * a.strideM;
+    double* v = a.v + (size_t)bz * a.strideV;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, m = a.m;
+    const int64_t ldm = a.ldm;
+    const int nblk = (m + 31) >> 5;
+    for (int i = tid; i < m; i += TRSVB_NT) vec[i] = v[i];
+    // ---- block inverses, one warp per block
+    for (int blk = warp; blk < nblk; blk += TRSVB_NW) {
+        const int i0 = blk << 5;
+        const int nb = (m - i0 < 32) ? (m - i0) : 32;
+        double* Ls = Linv + blk * 32 * 33;
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) {
+            // row i of the block, lane = column (coalesced); identity outside the matrix
+            double val = (i == lane) ? 1.0 : 0.0;
+            if (i < nb && lane <= i) val = L[(size_t)(i0 + i) * ldm + i0 + lane];
+            Ls[i * 33 + lane] = val;
+        }
+        __syncwarp();
+        dinv[warp * 32 + lane] = 1.0 / Ls[lane * 33 + lane];
+        __syncwarp();
+        double x[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            double sacc = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = 0; k < i; ++k) sacc = fma(-Ls[i * 33 + k], x[k], sacc);     // broadcast reads of row i
+            x[i] = sacc * dinv[warp * 32 + i];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) Ls[i * 33 + lane] = x[i];                        // column `lane` of the inverse
+    }
+    __syncthreads();
+    // ---- forward
+    for (int I = 0; I < nblk; ++I) {
+        const int i0 = I << 5;
+        const int nb = (m - i0 < 32) ? (m - i0) : 32;
+        if (i0 > 0) {
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 4
+            for (int k = lane; k < i0; k += 32) {
+                const double zk = vec[k];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int rr = warp + q * TRSVB_NW;
+                    if (rr < nb) acc[q] += L[(size_t)(i0 + rr) * ldm + k] * zk;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double sum = warp_sum(acc[q]);
+                const int rr = warp + q * TRSVB_NW;
+                if (lane == 0 && rr < nb) vec[i0 + rr] -= sum;
+            }
+            __syncthreads();
+        }
+        if (warp == 0) {
+            const double* Li = Linv + I * 32 * 33 + lane * 33;          // row `lane` of the inverse
+            double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+                acc0 += Li[j] * ((j < nb) ? vec[i0 + j] : 0.0);
+                acc1 += Li[j + 1] * ((j + 1 < nb) ? vec[i0 + j + 1] : 0.0);
+            }
+            __syncwarp();
+            if (lane < nb) vec[i0 + lane] = acc0 + acc1;
+        }
+        __syncthreads();
+    }
+    // ---- backward
+    for (int I = nblk - 1; I >= 0; --I) {
+        const int i0 = I << 5;
+        const int nb = (m - i0 < 32) ? (m - i0) : 32;
+        if (warp == 0) {
+            const double* Lc = Linv + I * 32 * 33 + lane;               // column `lane` of the inverse
+            double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+                acc0 += Lc[i * 33] * ((i < nb) ? vec[i0 + i] : 0.0);
+                acc1 += Lc[(i + 1) * 33] * ((i + 1 < nb) ? vec[i0 + i + 1] : 0.0);
+            }
+            __syncwarp();
+            if (lane < nb) vec[i0 + lane] = acc0 + acc1;
+        }
+        __syncthreads();
+        for (int k = tid; k < i0; k += TRSVB_NT) {
+            const double* col = L + (size_t)i0 * ldm + k;
+            double acc = 0.0;
+            if (nb == 32) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc += col[(size_t)i * ldm] * vec[i0 + i];
+            } else {
+                for (int i = 0; i < nb; ++i) acc += col[(size_t)i * ldm] * vec[i0 + i];
+            }
+            vec[k] -= acc;
+        }
+        __syncthreads();
+    }
+    double* dst = a.out ? a.out + (size_t)bz * a.strideV : v;
+    for (int i = tid; i < m; i += TRSVB_NT) dst[i] = vec[i];
+}
+
 inline size_t trsv_batched_smem(int m) { return (size_t)(2 * 32 * 33 + m) * sizeof(double); }
 
 constexpr int TRSV_ONE_CTA_MAX_M = 2048;

@@ -425,6 +425,8 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
         IPM_CUDA_OK(cudaFuncSetAttribute(kb_residual<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + 8192));
         IPM_CUDA_OK(cudaFuncSetAttribute(kb_dir<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
         IPM_CUDA_OK(cudaFuncSetAttribute(k_trsv_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        IPM_CUDA_OK(cudaFuncSetAttribute(k_trsv_batched_inv, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)trsv_batched_inv_smem(32 * TRSVI_MAX_BLK)));
         configured_dev = dev;
     }
     kb_init<<<B, 256, 0, st>>>(a);
@@ -475,7 +477,8 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
         t.active = a.active;
         for (int kind = 0; kind < 2; ++kind) {
             kb_rhs<NPL><<<B, KB_NT, smem_w, st>>>(a, kind);
-            k_trsv_batched<<<B, TRSVB_NT, trsv_batched_smem(m), st>>>(t);
+            if (m <= 32 * TRSVI_MAX_BLK) k_trsv_batched_inv<<<B, TRSVB_NT, trsv_batched_inv_smem(m), st>>>(t);
+            else k_trsv_batched<<<B, TRSVB_NT, trsv_batched_smem(m), st>>>(t);
             kb_dir<NPL><<<B, KB_NT, smem_col, st>>>(a, kind);
             count_launch(3);
         }
