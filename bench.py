@@ -351,7 +351,7 @@ def main():
             traffic = None
     phase_total = sum(ms) * 1e-3
     roofline = {
-        "kernel": "dmma_nt_kernel<128,128,4,2,0> (batched SYRK M = A diag(x/s) A^T, DMMA.8x8x4)",
+        "kernel": "dmma_ws_kernel<0,true> (batched SYRK M = A diag(x/s) A^T, warp-specialised persistent, DMMA.8x8x4)",
         "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
         "frac": achieved_tf / peak_tf if peak_tf > 0 else None, "traffic": traffic,
         "peak_source": "FP64 DMMA issue-rate ceiling measured live on this GPU (ipm_measure_dmma_peak); "
