@@ -292,15 +292,12 @@ inline int potrf_blocked(double* M, int64_t ldm, int64_t strideM, int m, int bat
 }
 
 // ------------------------------------------------------------------------------------------------
-// Triangular solves  L z = r  then  L^T y = z  for ONE large matrix, one launch per 64-wide block.
+// Triangular solves  L z = r  then  L^T y = z  for ONE large matrix.
 // Right-looking in both sweeps so that every vector entry is owned by exactly one thread:
 //   forward : z_J = L_JJ^-1 r_J ;  r_i -= sum_{k in J} L[i][k] z_k   for rows i below J   (thread per row)
 //   backward: y_J = L_JJ^-T z_J ;  z_k -= sum_{i in J} L[i][k] y_i   for columns k left of J (thread per column)
-// Every CTA re-solves the 64x64 diagonal system (warp 0, pivot broadcast by warp shuffles) and then
-// applies its share of the update; CTA 0 stores the solved block to `out`.
-constexpr int TRSV_NB = 64;
-constexpr int TRSV_NT = 128;
-
+// Every CTA re-solves the diagonal system (warp 0, pivot broadcast by warp shuffles) and then applies its share
+// of the update; CTA 0 stores the solved block to `out`.
 struct TrsvArgs {
     const double* L; int64_t ldm;
     double* v;        // in/out work vector (r then z), length m
@@ -308,101 +305,7 @@ struct TrsvArgs {
     int m, j0, nb;
 };
 
-__device__ __forceinline__ void trsv_diag_solve(const double* Ls /*[64][65]*/, double* zs /*[64]*/, int nb,
-                                                bool transposed) {
-    // executed by warp 0; lane owns entries lane and lane+32
-    const int lane = threadIdx.x & 31;
-    double v0 = (lane < nb) ? zs[lane] : 0.0;
-    double v1 = (lane + 32 < nb) ? zs[lane + 32] : 0.0;
-    const double i0 = (lane < nb) ? 1.0 / Ls[lane * 65 + lane] : 0.0;
-    const double i1 = (lane + 32 < nb) ? 1.0 / Ls[(lane + 32) * 65 + lane + 32] : 0.0;
-    if (!transposed) {
-        for (int j = 0; j < nb; ++j) {
-            const double cand = (j < 32) ? v0 * i0 : v1 * i1;
-            const double zj = __shfl_sync(0xffffffffu, cand, j & 31);
-            if (j < 32) {
-                if (lane == j) v0 = zj;
-                if (lane > j) v0 -= Ls[lane * 65 + j] * zj;
-                if (lane + 32 < nb) v1 -= Ls[(lane + 32) * 65 + j] * zj;
-            } else {
-                if (lane + 32 == j) v1 = zj;
-                if (lane + 32 > j && lane + 32 < nb) v1 -= Ls[(lane + 32) * 65 + j] * zj;
-            }
-        }
-    } else {
-        for (int j = nb - 1; j >= 0; --j) {
-            const double cand = (j < 32) ? v0 * i0 : v1 * i1;
-            const double yj = __shfl_sync(0xffffffffu, cand, j & 31);
-            if (j >= 32) {
-                if (lane + 32 == j) v1 = yj;
-                if (lane + 32 < j) v1 -= Ls[j * 65 + lane + 32] * yj;
-                v0 -= Ls[j * 65 + lane] * yj;
-            } else {
-                if (lane == j) v0 = yj;
-                if (lane < j) v0 -= Ls[j * 65 + lane] * yj;
-            }
-        }
-    }
-    if (lane < nb) zs[lane] = v0;
-    if (lane + 32 < nb) zs[lane + 32] = v1;
-}
-
-static __global__ void __launch_bounds__(TRSV_NT) k_trsv_fwd(const TrsvArgs a) {
-    __shared__ double Ls[64 * 65];
-    __shared__ double zs[64];
-    const int tid = threadIdx.x, nb = a.nb, j0 = a.j0;
-    const double* Ld = a.L + (size_t)j0 * a.ldm + j0;
-    for (int idx = tid; idx < nb * nb; idx += TRSV_NT) {
-        const int i = idx / nb, j = idx - i * nb;
-        Ls[i * 65 + j] = (j <= i) ? Ld[(size_t)i * a.ldm + j] : 0.0;
-    }
-    if (tid < nb) zs[tid] = a.v[j0 + tid];
-    __syncthreads();
-    if (tid < 32) trsv_diag_solve(Ls, zs, nb, false);
-    __syncthreads();
-    if (blockIdx.x == 0 && tid < nb) a.out[j0 + tid] = zs[tid];
-    const int r = j0 + nb + blockIdx.x * TRSV_NT + tid;
-    if (r >= a.m) return;
-    const double* row = a.L + (size_t)r * a.ldm + j0;
-    double acc = 0.0;
-    if (nb == TRSV_NB) {
-        const double2* rp = reinterpret_cast<const double2*>(row);
-#pragma unroll 8
-        for (int q = 0; q < TRSV_NB / 2; ++q) {
-            const double2 l = rp[q];
-            acc += l.x * zs[2 * q];
-            acc += l.y * zs[2 * q + 1];
-        }
-    } else {
-        for (int k = 0; k < nb; ++k) acc += row[k] * zs[k];
-    }
-    a.v[r] -= acc;
-}
-
-static __global__ void __launch_bounds__(TRSV_NT) k_trsv_bwd(const TrsvArgs a) {
-    __shared__ double Ls[64 * 65];
-    __shared__ double zs[64];
-    const int tid = threadIdx.x, nb = a.nb, j0 = a.j0;
-    const double* Ld = a.L + (size_t)j0 * a.ldm + j0;
-    for (int idx = tid; idx < nb * nb; idx += TRSV_NT) {
-        const int i = idx / nb, j = idx - i * nb;
-        Ls[i * 65 + j] = (j <= i) ? Ld[(size_t)i * a.ldm + j] : 0.0;
-    }
-    if (tid < nb) zs[tid] = a.v[j0 + tid];
-    __syncthreads();
-    if (tid < 32) trsv_diag_solve(Ls, zs, nb, true);
-    __syncthreads();
-    if (blockIdx.x == 0 && tid < nb) a.out[j0 + tid] = zs[tid];
-    const int k = blockIdx.x * TRSV_NT + tid;
-    if (k >= j0) return;
-    const double* col = a.L + (size_t)j0 * a.ldm + k;
-    double acc = 0.0;
-#pragma unroll 8
-    for (int i = 0; i < nb; ++i) acc += col[(size_t)i * a.ldm] * zs[i];
-    a.v[k] -= acc;
-}
-
-// ---- 128-wide variant for large orders: one launch per 128 columns, 256 threads.  Every CTA solves the
+// One launch per 128 columns, 256 threads.  Every CTA solves the
 // 128x128 triangular block in shared memory (4 sub-blocks of 32: warp 0 solves, all threads update) and then
 // applies its share of the update to the rest of the vector.
 constexpr int TRSV128_NB = 128;

@@ -79,9 +79,16 @@ def test_integer_dtypes_as_the_reference_loader_produces_them(ipm, reference_res
     assert res.iterations == reference_results["AFIRO"]["k"]
 
 
+EX3_A = [[10, 7.5, 4, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0], [0, 10, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0],
+         [0.5, 0.4, 0.5, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0], [0, 0.4, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0],
+         [0.5, 0.1, 0.5, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0], [0.4, 0.2, 0.4, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0],
+         [1, 1.5, 0.5, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0], [1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0],
+         [0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0], [0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1]]
 EXAMPLES = {
     "ex1": ([[3, 6, 8], [8, 4, 1]], [30, 44], [-100, -125, -20]),
     "ex2": ([[1, 1.5, 1, 0, 0], [2, 3, 0, 1, 0], [2, 1, 0, 0, 1]], [750, 1500, 1000], [-20, -30, 0, 0, 0]),
+    # ex3 (main.py:1264-1284): the production-planning LP, 10 x 13
+    "ex3": (EX3_A, [4350, 2500, 280, 140, 280, 140, 700, 300, 180, 400], [-300, -500, -200] + [0] * 10),
 }
 
 
@@ -93,7 +100,7 @@ def test_dense_examples(ipm, name, dense_results):
     g = dense_results[name]
     assert res.status == "converged" and abs(res.iterations - g["k"]) <= 1
     assert abs(res.objective - g["obj"]) <= 1e-8 * abs(g["obj"])
-    if name == "ex1":       # ex2's optimal face is not a single point, only the objective is pinned
+    if name in ("ex1", "ex3"):   # ex2's optimal face is not a single point, only the objective is pinned
         assert np.allclose(res.x.ravel(), g["x"], rtol=1e-6, atol=1e-7)
 
 
@@ -389,3 +396,17 @@ def test_stateless_reference_shaped_ops(ipm, orc):
     z = ipm.solve_linear(M, rhs)
     assert z.shape == (300, 1)
     assert np.linalg.norm(M @ z - rhs) <= 1e-9 * np.linalg.norm(rhs)
+
+
+@pytest.mark.parametrize("m,n,seed", [(1, 2, 0), (5, 9, 1), (17, 33, 2), (33, 70, 3), (100, 257, 4), (257, 600, 5),
+                                       (300, 512, 6)])
+def test_dense_ragged_shapes_against_oracle(ipm, orc, m, n, seed):
+    """Shapes that are not multiples of any tile size (odd n exercises the register-staged DMMA kernel, m = 257
+    and 300 the multi-kernel Cholesky) against the oracle's normal-equations path."""
+    A, b, c = ipm.synthetic_dense_lp(m, n, seed)
+    res = ipm.interior(A, b, c, tol=1e-8)
+    o = orc.solve(A, b, c, tol=1e-8, max_iter=50000, y0_is_one=False, linear="normal")
+    assert res.status == "converged" and o["status"] == 0
+    assert abs(res.iterations - o["k"]) <= 1
+    assert abs(res.objective - o["obj"]) <= 1e-8 * max(1.0, abs(o["obj"]))
+    assert np.linalg.norm(A @ res.x - b.reshape(-1, 1)) <= 1.001e-8 * (1 + np.linalg.norm(b))

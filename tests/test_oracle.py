@@ -60,9 +60,15 @@ def test_reference_outcome_on_25fv47_is_nan_at_k1(reference_results):
     assert reference_results["25FV47"]["reference_outcome"] == {"k": 1, "obj": None}
 
 
+EX3_A = [[10, 7.5, 4, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0], [0, 10, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0],
+         [0.5, 0.4, 0.5, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0], [0, 0.4, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0],
+         [0.5, 0.1, 0.5, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0], [0.4, 0.2, 0.4, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0],
+         [1, 1.5, 0.5, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0], [1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0],
+         [0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0], [0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1]]
 EXAMPLES = {
     "ex1": ([[3, 6, 8], [8, 4, 1]], [30, 44], [-100, -125, -20], -775.0),
     "ex2": ([[1, 1.5, 1, 0, 0], [2, 3, 0, 1, 0], [2, 1, 0, 0, 1]], [750, 1500, 1000], [-20, -30, 0, 0, 0], -15000.0),
+    "ex3": (EX3_A, [4350, 2500, 280, 140, 280, 140, 700, 300, 180, 400], [-300, -500, -200] + [0] * 10, -168000.0),
 }
 
 
