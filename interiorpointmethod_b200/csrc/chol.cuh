@@ -712,6 +712,17 @@ inline int potrs_single(const double* L, int64_t ldm, int m, double* rhs, double
     if (m <= TRSV_ONE_CTA_MAX_M) {
         TrsvBatchedArgs t;
         t.L = L; t.ldm = ldm; t.strideM = 0; t.v = rhs; t.strideV = 0; t.m = m; t.active = nullptr; t.out = sol;
+        if (m <= 32 * TRSVI_MAX_BLK) {
+            static int configured_dev = -1;
+            int dev = 0;
+            IPM_CUDA_OK(cudaGetDevice(&dev));
+            if (configured_dev != dev) {
+                IPM_CUDA_OK(cudaFuncSetAttribute(k_trsv_batched_inv, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)trsv_batched_inv_smem(32 * TRSVI_MAX_BLK)));
+                configured_dev = dev;
+            }
+            k_trsv_batched_inv<<<1, TRSVB_NT, trsv_batched_inv_smem(m), st>>>(t);
+        } else
         k_trsv_batched<<<1, TRSVB_NT, trsv_batched_smem(m), st>>>(t);
         count_launch();
         return launch_check();

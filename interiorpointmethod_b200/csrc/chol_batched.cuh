@@ -15,10 +15,12 @@
 
 namespace ipm {
 
-constexpr int KBC_NT = 256;
-constexpr int KBC_NW = KBC_NT / 32;
-constexpr int KBC_UW = KBC_NW - 1;  // update warps
-constexpr int KBC_MAX_M = 256;      // 28 row tiles over 7 update warps = 4 accumulator slots per warp
+constexpr int KBC_NT = 256;         // batched variant: 2 CTAs per SM
+constexpr int KBC_NT_BIG = 512;     // single-matrix variant for 256 < m <= 512: 1 CTA per SM
+// NT/32 - 1 update warps x 4 accumulator slots x 8 rows, plus the 32 rows of the diagonal block
+constexpr int kbc_max_m(int nt) { return 32 + (nt / 32 - 1) * 4 * 8; }
+constexpr int KBC_MAX_M = kbc_max_m(KBC_NT);          // 256
+constexpr int KBC_MAX_M_BIG = kbc_max_m(KBC_NT_BIG);  // 512
 constexpr int KBC_LD = 33;
 constexpr int KBC_LDT = 34;     // transposed diagonal block: even so that 128-bit reads stay aligned
 constexpr int KBC_KC = 64;      // columns of L[J+1, :] staged in shared memory per chunk of the update
@@ -38,8 +40,9 @@ inline size_t kbc_smem_bytes(int m) {
 }
 
 #ifdef __CUDACC__
-__device__ __forceinline__ void kbc_update_bar() {      // barrier among the 7 update warps only
-    asm volatile("bar.sync 1, %0;" ::"n"(KBC_UW * 32) : "memory");
+template <int NT>
+__device__ __forceinline__ void kbc_update_bar() {      // barrier among the update warps only
+    asm volatile("bar.sync 1, %0;" ::"n"(NT - 32) : "memory");
 }
 
 // One chunk of the early update for the NTI row tiles of a warp: A fragments from global memory with a one-step
@@ -70,7 +73,7 @@ __device__ __forceinline__ void kbc_update_chunk(double (&acc)[4][4][2], const d
 
 // K = J term of panel J+1 from shared memory: rows of the new panel are Ps[0..nrows), its own first 32 rows
 // (= rows of the next diagonal block) are the B operand.
-template <int NTI>
+template <int NTI, int KBC_UW>
 __device__ __forceinline__ void kbc_update_late(double (&acc)[4][4][2], const double* Ps, int uw, int nrows, int g,
                                                 int t) {
 #pragma unroll
@@ -93,7 +96,9 @@ __device__ __forceinline__ void kbc_update_late(double (&acc)[4][4][2], const do
     }
 }
 
-static __global__ void __launch_bounds__(KBC_NT, 2) kb_chol(const CholBatchedArgs a) {
+template <int KBC_NT>
+static __global__ void __launch_bounds__(KBC_NT, KBC_NT == 256 ? 2 : 1) kb_chol(const CholBatchedArgs a) {
+    constexpr int KBC_UW = KBC_NT / 32 - 1;   // update warps
     extern __shared__ __align__(16) double smem[];
     double* D = smem;                       // [32][33]  diagonal block, becomes L_JJ
     double* DT = smem + 32 * KBC_LD + 2;    // [32][34]  DT[k][j] = L_JJ[j][k]  (+2 doubles: 16-byte aligned)
@@ -109,6 +114,7 @@ static __global__ void __launch_bounds__(KBC_NT, 2) kb_chol(const CholBatchedArg
     const int m = a.m, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int uw = warp - 1;                // index among the update warps (-1 for the factor warp)
+    static_assert(KBC_NT == 256 || KBC_NT == 512, "two variants");
     double* Mb = a.M + (size_t)lp * a.strideM;
     const int64_t ldm = a.ldm;
 
@@ -266,14 +272,14 @@ static __global__ void __launch_bounds__(KBC_NT, 2) kb_chol(const CholBatchedArg
                 }
                 for (int k0 = 0; k0 < j0; k0 += KBC_KC) {
                     const int kc = (j0 - k0 < KBC_KC) ? (j0 - k0) : KBC_KC;
-                    kbc_update_bar();                                  // previous chunk fully consumed
+                    kbc_update_bar<KBC_NT>();                                  // previous chunk fully consumed
                     const int kshift = (kc == KBC_KC) ? 6 : 5;         // kc is 64 or 32 (j0 is a multiple of 32)
 #pragma unroll 5
                     for (int idx = tid - 32; idx < 32 * kc; idx += KBC_UW * 32) {
                         const int r = idx >> kshift, k = idx & (kc - 1);
                         Bs[r * KBC_LDB + k] = (j1 + r < m) ? Mb[(size_t)(j1 + r) * ldm + k0 + k] : 0.0;
                     }
-                    kbc_update_bar();
+                    kbc_update_bar<KBC_NT>();
                     switch (nti) {
                         case 1: kbc_update_chunk<1>(acc, Mb, aoff, aok, Bs, k0, kc, g, t); break;
                         case 2: kbc_update_chunk<2>(acc, Mb, aoff, aok, Bs, k0, kc, g, t); break;
@@ -292,10 +298,10 @@ static __global__ void __launch_bounds__(KBC_NT, 2) kb_chol(const CholBatchedArg
             if (nrows1 > 0) {
                 // K = J term of panel J+1 straight from shared memory
                 switch (nti) {
-                    case 1: kbc_update_late<1>(acc, Ps, uw, nrows1, g, t); break;
-                    case 2: kbc_update_late<2>(acc, Ps, uw, nrows1, g, t); break;
-                    case 3: kbc_update_late<3>(acc, Ps, uw, nrows1, g, t); break;
-                    case 4: kbc_update_late<4>(acc, Ps, uw, nrows1, g, t); break;
+                    case 1: kbc_update_late<1, KBC_UW>(acc, Ps, uw, nrows1, g, t); break;
+                    case 2: kbc_update_late<2, KBC_UW>(acc, Ps, uw, nrows1, g, t); break;
+                    case 3: kbc_update_late<3, KBC_UW>(acc, Ps, uw, nrows1, g, t); break;
+                    case 4: kbc_update_late<4, KBC_UW>(acc, Ps, uw, nrows1, g, t); break;
                     default: break;
                 }
             }
@@ -325,22 +331,29 @@ static __global__ void __launch_bounds__(KBC_NT, 2) kb_chol(const CholBatchedArg
     }
 }
 
-inline int potrf_batched_fused(double* M, int64_t ldm, int64_t strideM, int m, int batch, double* scal,
-                               int64_t strideScal, double tau, const int* active, cudaStream_t st) {
+template <int NT>
+inline int potrf_batched_fused_nt(double* M, int64_t ldm, int64_t strideM, int m, int batch, double* scal,
+                                  int64_t strideScal, double tau, const int* active, cudaStream_t st) {
     static int configured_dev = -1;
     int dev = 0;
     IPM_CUDA_OK(cudaGetDevice(&dev));
     if (configured_dev != dev) {
-        IPM_CUDA_OK(cudaFuncSetAttribute(kb_chol, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kbc_smem_bytes(KBC_MAX_M)));
+        IPM_CUDA_OK(cudaFuncSetAttribute(kb_chol<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kbc_smem_bytes(kbc_max_m(NT))));
         configured_dev = dev;
     }
     CholBatchedArgs a;
     a.M = M; a.ldm = ldm; a.strideM = strideM; a.scal = scal; a.strideScal = strideScal; a.tau = tau; a.m = m;
     a.active = active;
-    kb_chol<<<batch, KBC_NT, kbc_smem_bytes(m), st>>>(a);
+    kb_chol<NT><<<batch, NT, kbc_smem_bytes(m), st>>>(a);
     count_launch();
     return launch_check();
+}
+// m <= 256: 256-thread CTAs (two per SM); m <= 512: 512-thread CTAs
+inline int potrf_batched_fused(double* M, int64_t ldm, int64_t strideM, int m, int batch, double* scal,
+                               int64_t strideScal, double tau, const int* active, cudaStream_t st) {
+    if (m <= KBC_MAX_M) return potrf_batched_fused_nt<KBC_NT>(M, ldm, strideM, m, batch, scal, strideScal, tau, active, st);
+    return potrf_batched_fused_nt<KBC_NT_BIG>(M, ldm, strideM, m, batch, scal, strideScal, tau, active, st);
 }
 #endif
 

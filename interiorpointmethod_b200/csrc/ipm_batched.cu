@@ -466,7 +466,7 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
         g.rowsP = m; g.rowsQ = m; g.K = n; g.lower_only = 1; g.active = a.active;
         IPM_TRY((dmma_syrk_auto<0>(g, B, st)));
         g_prof.end_phase(PH_SYRK, st);
-        if (m <= KBC_MAX_M)
+        if (m <= KBC_MAX_M_BIG)
             IPM_TRY(potrf_batched_fused(w.M, w.ldm, (int64_t)m * w.ldm, m, B, a.scal, S_COUNT, tau, a.active, st));
         else
             IPM_TRY((potrf_blocked<64, 256, 128>(w.M, w.ldm, (int64_t)m * w.ldm, m, B, a.scal, S_COUNT, tau,
@@ -559,7 +559,7 @@ int ipm_potrf_batched_d(int device_ordinal, int B, int m, double* M_d, int64_t l
     IPM_CUDA_OK(cudaSetDevice(device_ordinal));
     double* scal = nullptr;
     IPM_CUDA_OK(cudaMalloc(&scal, (size_t)B * S_COUNT * sizeof(double)));
-    int rc = (m <= KBC_MAX_M)
+    int rc = (m <= KBC_MAX_M_BIG)
                  ? potrf_batched_fused(M_d, ldm, strideM, m, B, scal, S_COUNT, pivot_rel_thresh, nullptr, 0)
                  : potrf_blocked<64, 256, 128>(M_d, ldm, strideM, m, B, scal, S_COUNT, pivot_rel_thresh, nullptr, 0);
     if (rc == IPM_OK) {

@@ -410,3 +410,25 @@ def test_dense_ragged_shapes_against_oracle(ipm, orc, m, n, seed):
     assert abs(res.iterations - o["k"]) <= 1
     assert abs(res.objective - o["obj"]) <= 1e-8 * max(1.0, abs(o["obj"]))
     assert np.linalg.norm(A @ res.x - b.reshape(-1, 1)) <= 1.001e-8 * (1 + np.linalg.norm(b))
+
+
+@pytest.mark.parametrize("m,B", [(257, 3), (400, 5), (512, 4)])
+def test_batched_potrf_512_thread_variant(ipm, m, B):
+    """256 < m <= 512 runs the 512-thread variant of the fused Cholesky (15 update warps)."""
+    import ctypes
+    import torch
+    from interiorpointmethod_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(m + B)
+    X = torch.randn(B, m, m + 30, dtype=torch.float64, device="cuda", generator=g)
+    M = X @ X.transpose(1, 2) + 1e-3 * torch.eye(m, dtype=torch.float64, device="cuda")
+    ldm = (m + 15) // 16 * 16
+    buf = torch.zeros(B, m, ldm, dtype=torch.float64, device="cuda")
+    buf[:, :, :m] = M
+    torch.cuda.synchronize()
+    nf = ctypes.c_int(-1)
+    rc = lib.ipm_potrf_batched_d(0, B, m, ctypes.c_void_p(buf.data_ptr()), ldm, m * ldm, 1e-30, ctypes.byref(nf))
+    assert rc == 0 and nf.value == 0
+    L = torch.tril(buf[:, :, :m])
+    ref = torch.linalg.cholesky(M)
+    assert (L - ref).abs().max().item() <= 1e-10 * ref.abs().max().item()
