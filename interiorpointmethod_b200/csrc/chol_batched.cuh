@@ -40,32 +40,47 @@ inline size_t kbc_smem_bytes(int m) {
 }
 
 #ifdef __CUDACC__
+#ifdef KBC_PROFILE
+__device__ long long kbc_prof[32];
+#define KBC_T(slot) do { if (lp == 0 && lane == 0 && (warp == 1 || warp == 0)) { long long _t = clock64(); kbc_prof[(warp == 0 ? 16 : 0) + (slot)] += _t - t_last; t_last = _t; } } while (0)
+#else
+#define KBC_T(slot) do {} while (0)
+#endif
 template <int NT>
 __device__ __forceinline__ void kbc_update_bar() {      // barrier among the update warps only
     asm volatile("bar.sync 1, %0;" ::"n"(NT - 32) : "memory");
 }
 
-// One chunk of the early update for the NTI row tiles of a warp: A fragments from global memory with a one-step
-// register prefetch, B fragments from the staged chunk.
+// One chunk of the early update for the NTI row tiles of a warp.  A fragments come straight from global memory
+// as 16-byte loads: lane (g,t) reads A[g][k+2t], A[g][k+2t+1] and feeds them to two consecutive MMAs, i.e. the
+// contraction index is permuted inside every 8-column group - harmless because the B fragments (from the staged
+// shared chunk) are read with the same permutation.  One group (= 2 MMA steps) is prefetched ahead.
 template <int NTI>
 __device__ __forceinline__ void kbc_update_chunk(double (&acc)[4][4][2], const double* __restrict__ Mb,
-                                                 const int (&aoff)[4], const bool (&aok)[4], const double* Bs,
+                                                 const int (&aoff2)[4], const bool (&aok)[4], const double* Bs,
                                                  int k0, int kc, int g, int t) {
-    double af[NTI], afn[NTI];
+    double2 af[NTI], afn[NTI];
 #pragma unroll
-    for (int i = 0; i < NTI; ++i) af[i] = aok[i] ? Mb[aoff[i] + k0] : 0.0;
-    const double* bs = Bs + g * KBC_LDB + t;
+    for (int i = 0; i < NTI; ++i)
+        af[i] = aok[i] ? *reinterpret_cast<const double2*>(Mb + aoff2[i] + k0) : make_double2(0.0, 0.0);
+    const double* bs = Bs + g * KBC_LDB + 2 * t;
 #pragma unroll 2
-    for (int kk = 0; kk < kc; kk += 4) {
+    for (int kk = 0; kk < kc; kk += 8) {
 #pragma unroll
-        for (int i = 0; i < NTI; ++i) afn[i] = (aok[i] && kk + 4 < kc) ? Mb[aoff[i] + k0 + kk + 4] : 0.0;
-        double bf[4];
+        for (int i = 0; i < NTI; ++i)
+            afn[i] = (aok[i] && kk + 8 < kc) ? *reinterpret_cast<const double2*>(Mb + aoff2[i] + k0 + kk + 8)
+                                             : make_double2(0.0, 0.0);
+        double2 bf[4];
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) bf[ni] = bs[ni * 8 * KBC_LDB + kk];
+        for (int ni = 0; ni < 4; ++ni) bf[ni] = *reinterpret_cast<const double2*>(bs + ni * 8 * KBC_LDB + kk);
 #pragma unroll
         for (int ti = 0; ti < NTI; ++ti)
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) dmma884(acc[ti][ni][0], acc[ti][ni][1], af[ti], bf[ni]);
+            for (int ni = 0; ni < 4; ++ni) dmma884(acc[ti][ni][0], acc[ti][ni][1], af[ti].x, bf[ni].x);
+#pragma unroll
+        for (int ti = 0; ti < NTI; ++ti)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) dmma884(acc[ti][ni][0], acc[ti][ni][1], af[ti].y, bf[ni].y);
 #pragma unroll
         for (int i = 0; i < NTI; ++i) af[i] = afn[i];
     }
@@ -134,6 +149,9 @@ static __global__ void __launch_bounds__(KBC_NT, KBC_NT == 256 ? 2 : 1) kb_chol(
         __syncthreads();
     }
     const double thresh = a.tau * s_maxdiag;
+#ifdef KBC_PROFILE
+    long long t_last = clock64();
+#endif
 
     // ---- phases executed by every thread (called from both role loops below)
     auto phase_transpose = [&](int nb) {
@@ -225,14 +243,19 @@ static __global__ void __launch_bounds__(KBC_NT, KBC_NT == 256 ? 2 : 1) kb_chol(
                 for (int o = 16; o > 0; o >>= 1) nfix += __shfl_xor_sync(0xffffffffu, nfix, o);
                 if (lane == 0) s_nfix += nfix;               // lane j counted its own pivot
             }
+            KBC_T(0);
             __syncthreads();                                       // (S1)
+            KBC_T(1);
             phase_transpose(nb);
             __syncthreads();                                       // (S2)
+            KBC_T(2);
             phase_trsm(nrows1);
             __syncthreads();                                       // (S3)
+            KBC_T(3);
             phase_store(j0, rows, nb);
             __syncthreads();                                       // (S4)
             __syncthreads();                                       // (S5)
+            KBC_T(4);
         }
     } else {
         // =================================================================== UPDATE warps
@@ -253,7 +276,7 @@ static __global__ void __launch_bounds__(KBC_NT, KBC_NT == 256 ? 2 : 1) kb_chol(
                     const int tile = uw + i * KBC_UW;
                     const int ra = j1 + tile * 8 + g;
                     aok[i] = (tile < ntile1) && (ra < m);
-                    aoff[i] = (aok[i] ? ra : j1) * (int)ldm + t;
+                    aoff[i] = (aok[i] ? ra : j1) * (int)ldm + 2 * t;     // 16-byte aligned: ldm and k are even
                 }
 #pragma unroll
                 for (int ti = 0; ti < 4; ++ti) {
@@ -289,12 +312,17 @@ static __global__ void __launch_bounds__(KBC_NT, KBC_NT == 256 ? 2 : 1) kb_chol(
                     }
                 }
             }
+            KBC_T(0);
             __syncthreads();                                       // (S1) block factored, early update done
+            KBC_T(1);
             phase_transpose(nb);
             __syncthreads();                                       // (S2)
+            KBC_T(2);
             phase_trsm(nrows1);
             __syncthreads();                                       // (S3) panel J final in shared memory
+            KBC_T(3);
             phase_store(j0, rows, nb);
+            KBC_T(4);
             if (nrows1 > 0) {
                 // K = J term of panel J+1 straight from shared memory
                 switch (nti) {
@@ -305,7 +333,9 @@ static __global__ void __launch_bounds__(KBC_NT, KBC_NT == 256 ? 2 : 1) kb_chol(
                     default: break;
                 }
             }
+            KBC_T(5);
             __syncthreads();                                       // (S4) everyone is done reading D / Ps
+            KBC_T(6);
             if (nrows1 > 0) {
                 // accumulators (sign restored) become the raw panel J+1
 #pragma unroll
@@ -322,6 +352,7 @@ static __global__ void __launch_bounds__(KBC_NT, KBC_NT == 256 ? 2 : 1) kb_chol(
                 }
             }
             __syncthreads();                                       // (S5)
+            KBC_T(7);
         }
     }
     __syncthreads();
