@@ -148,6 +148,18 @@ int ipm_solve_batched_dense_d(int device_ordinal, int B, int m, int n,
                               double *obj_d, int *iters_d, int *status_d, double *x_d,
                               void *work_d, int *iterations_run);
 int64_t ipm_batched_workspace_bytes(int B, int m, int n);
+/* Iteration variant of the batched solver.
+ * three_pass = 1 (default), m <= 256: the critical path of an iteration reads A three times (SYRK, predictor
+ *   direction, corrector direction): the corrector right-hand side comes from the predictor's by linearity of
+ *   main.py:150-152 and the residuals of the new point from the recurrences rb += ap A dx, rc += ad (A^T dy + ds).
+ *   check_optimality (main.py:169-173) is re-evaluated from scratch before an LP is declared finished and in
+ *   every refresh_every-th iteration (default 3; 0 = only at the end).  Without the periodic refresh the
+ *   recurrences drift from the true residuals in the ill-conditioned last iterations (measured: LP 7466 of the
+ *   benchmark batch needs 60 iterations instead of 16; with a refresh every 2, 3 or 4 iterations all 8192 LPs stay
+ *   within +-1 of the six-pass iteration count).
+ * three_pass = 0: six passes, every residual from scratch in every iteration, exactly as main.py:725-751 orders it.
+ * Process-wide; for A/B measurements and parity tests. */
+int ipm_batched_set_variant(int three_pass, int refresh_every);
 
 /* Phase timing of the batched solver (bench.py roofline): CUDA events on the solve stream around the four
  * phases of every lockstep iteration.  ms/calls index: 0 residual pass, 1 SYRK (dmma_nt_kernel, one launch

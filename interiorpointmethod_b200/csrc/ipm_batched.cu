@@ -9,6 +9,13 @@
 //   kb_rhs(0), trsv, kb_dir(0)   predictor: rhs, solves, dx/ds, ratio test, mu_aff, sigma   (main.py:225-228,305-322,588-601)
 //   kb_rhs(1), trsv, kb_dir(1)   corrector: same with r4, eta = 0.91, update of x, y, s     (main.py:142-159,604-626,694-696)
 // = 6 passes over A per iteration, everything else is O(n) or lives in L2.
+//
+// For m <= 256 (the benchmark shape) the iteration is restructured to FOUR passes over A, three of them on the
+// critical path (ipm_batched_fused.cuh):
+//   dmma_ws_kernel         M = A diag(d) A^T                                                 (main.py:224)
+//   kb_chol, kb_rhs(0), trsv, kbf_dir<0>   predictor direction + the corrector right-hand side by linearity
+//   trsv, kbf_dir<1>            corrector direction, update, residuals of the new point by recurrence
+//   kb_residual<.,true>         from-scratch check_optimality, only for LPs the recurrences declare finished
 #include <cmath>
 #include <vector>
 
@@ -17,6 +24,7 @@
 #include "common.cuh"
 #include "dmma_gemm.cuh"
 #include "dmma_ws.cuh"
+#include "ipm_batched_fused.cuh"
 
 using namespace ipm;
 
@@ -25,20 +33,6 @@ namespace {
 constexpr int KB_NT = 512;
 constexpr int KB_NW = KB_NT / 32;
 
-struct BatchArgs {
-    const double* A;   // [B][m][n]
-    const double* b;   // [B][m]
-    const double* c;   // [B][n]
-    double *x, *s, *rc, *d, *w, *rcx, *dxa, *dsa;      // [B][n]
-    double *y, *rb, *dy, *rhs;                         // [B][m]
-    double* scal;      // [B][S_COUNT]
-    int* active;       // [B]
-    int* iters;        // [B]
-    unsigned* n_active;
-    int m, n;
-    double tol, eta;
-    int max_iter;
-};
 
 // ---------------------------------------------------------------------------------------------
 // Phase profiler (bench.py roofline): CUDA events on the solve stream around each phase of every lockstep
@@ -96,16 +90,26 @@ struct Profiler {
 };
 Profiler g_prof;
 
+int g_fresh_every = 3;         // residuals from scratch every 3rd iteration (see ipm_batched_set_variant)
+bool g_allow_fused = true;      // ipm_batched_set_variant(): 0 forces the 6-pass iteration (tests, A/B timing)
+
 // ---------------------------------------------------------------------------------------------
 // One pass over A_i: Ax (warp per row) and A^T y (column partial sums per warp, combined in warp order).
-template <int NPL>
+// CAND (3-pass path): only LPs flagged 2 are evaluated (the others just report themselves as active), and the
+// predictor operands rcx = (x s)/x, w = d (rc - rcx) of main.py:72,225 are produced here as well.
+template <int NPL, bool CAND>
 __global__ void __launch_bounds__(KB_NT, (NPL <= 8) ? 2 : 1) kb_residual(const BatchArgs a) {
     extern __shared__ __align__(16) double smem[];
     double* colred = smem;                 // [KB_NW][n]
     __shared__ double sh[32];
     __shared__ double s_nrb2;
     const int lp = blockIdx.x;
-    if (a.active[lp] == 0) return;
+    const int flag = a.active[lp];
+    if (flag == 0) return;
+    if (CAND && flag == 1) {
+        if (threadIdx.x == 0) atomicAdd(a.n_active, 1u);
+        return;
+    }
     const int m = a.m, n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double* A = a.A + (size_t)lp * m * n;
     const double* x = a.x + (size_t)lp * n;
@@ -166,7 +170,13 @@ __global__ void __launch_bounds__(KB_NT, (NPL <= 8) ? 2 : 1) kb_residual(const B
         const double xi = x[k], si = s[k], ci = c[k];
         const double r = aty + si - ci;
         rc[k] = r;
-        d[k] = xi / si;
+        const double dk = xi / si;
+        d[k] = dk;
+        if (CAND) {
+            const double q = (xi * si) / xi;
+            a.rcx[(size_t)lp * n + k] = q;
+            a.w[(size_t)lp * n + k] = dk * (r - q);
+        }
         nrc2 += r * r;
         xs += xi * si;
         obj += xi * ci;
@@ -184,12 +194,12 @@ __global__ void __launch_bounds__(KB_NT, (NPL <= 8) ? 2 : 1) kb_residual(const B
         scal[S_CONT] = cont ? 1.0 : 0.0;
         const bool go = cont && a.iters[lp] < a.max_iter;
         if (go) atomicAdd(a.n_active, 1u);
-        else a.active[lp] = 0;
+        a.active[lp] = go ? 1 : 0;
     }
 }
 
 // |b|, |c| per LP (once per solve) and state initialisation x = s = 1, y = 0 (main.py:287-302)
-__global__ void __launch_bounds__(256) kb_init(const BatchArgs a) {
+__global__ void __launch_bounds__(256) kb_init(const BatchArgs a, int flag) {
     __shared__ double sh[32];
     const int lp = blockIdx.x, tid = threadIdx.x;
     const int m = a.m, n = a.n;
@@ -212,7 +222,7 @@ __global__ void __launch_bounds__(256) kb_init(const BatchArgs a) {
         for (int i = 0; i < S_COUNT; ++i) scal[i] = 0.0;
         scal[S_NB] = sqrt(nb);
         scal[S_NC] = sqrt(nc);
-        a.active[lp] = 1;
+        a.active[lp] = flag;
         a.iters[lp] = 0;
     }
 }
@@ -387,9 +397,14 @@ struct Workspace {
     unsigned* h_nact;    // pinned
 };
 
+int64_t at_doubles(int B, int m, int n) {        // strip-major copy of A (3-pass path only)
+    if (m > KF_MAX_M) return 0;
+    return (int64_t)B * ceil_div(n, KF_W) * (32 * kf_nrp(m)) * KF_W;
+}
+
 int64_t ws_bytes(int B, int m, int n) {
     const int64_t ldm = round_up(m, 16);
-    int64_t doubles = (int64_t)B * (8 * (int64_t)n + 4 * (int64_t)m + S_COUNT) + (int64_t)B * m * ldm;
+    int64_t doubles = (int64_t)B * (8 * (int64_t)n + 4 * (int64_t)m + S_COUNT) + (int64_t)B * m * ldm + at_doubles(B, m, n);
     int64_t bytes = doubles * 8 + (int64_t)B * 2 * sizeof(int) + 256 + 1024;
     return round_up(bytes, 256);
 }
@@ -400,6 +415,7 @@ void carve(Workspace& w, void* base, int B, int m, int n) {
     const int64_t bn = (int64_t)B * n, bm = (int64_t)B * m;
     w.ldm = round_up(m, 16);
     w.M = take((int64_t)B * m * w.ldm);
+    w.a.At = take(at_doubles(B, m, n));
     w.a.x = take(bn); w.a.s = take(bn); w.a.rc = take(bn); w.a.d = take(bn); w.a.w = take(bn); w.a.rcx = take(bn);
     w.a.dxa = take(bn); w.a.dsa = take(bn);
     w.a.y = take(bm); w.a.rb = take(bm); w.a.dy = take(bm); w.a.rhs = take(bm);
@@ -412,24 +428,58 @@ void carve(Workspace& w, void* base, int B, int m, int n) {
     w.a.m = m; w.a.n = n;
 }
 
+void launch_kbf_dir(int kind, const BatchArgs& a, int B, int m, cudaStream_t st) {
+    const size_t sm = kf_smem_bytes(m, a.n);
+    switch (kf_nrp(m) * 2 + kind) {
+        case 2: kbf_dir<0, 1><<<B, KF_NTT, sm, st>>>(a); break;
+        case 3: kbf_dir<1, 1><<<B, KF_NTT, sm, st>>>(a); break;
+        case 4: kbf_dir<0, 2><<<B, KF_NTT, sm, st>>>(a); break;
+        case 5: kbf_dir<1, 2><<<B, KF_NTT, sm, st>>>(a); break;
+        case 8: kbf_dir<0, 4><<<B, KF_NTT, sm, st>>>(a); break;
+        case 9: kbf_dir<1, 4><<<B, KF_NTT, sm, st>>>(a); break;
+        case 16: kbf_dir<0, 8><<<B, KF_NTT, sm, st>>>(a); break;
+        default: kbf_dir<1, 8><<<B, KF_NTT, sm, st>>>(a); break;
+    }
+}
+
 template <int NPL>
 int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, int* iterations_run) {
     BatchArgs& a = w.a;
     const size_t smem_col = (size_t)KB_NW * n * sizeof(double);
     const size_t smem_res = smem_col + (size_t)n * sizeof(double);
     const size_t smem_w = (size_t)n * sizeof(double);
+    DmmaArgs g;
+    g.P = a.A; g.ldp = n; g.strideP = (int64_t)m * n;
+    g.Q = a.A; g.ldq = n; g.strideQ = (int64_t)m * n;
+    g.dvec = a.d; g.strideD = n;
+    g.C = w.M; g.ldc = w.ldm; g.strideC = (int64_t)m * w.ldm;
+    g.rowsP = m; g.rowsQ = m; g.K = n; g.lower_only = 1; g.active = a.active;
+    // 3-pass iteration (ipm_batched_fused.cuh) when one CTA can hold a column strip of A_i
+    const bool fused = g_allow_fused && m <= KF_MAX_M && (n % 2 == 0) && ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0);
     static int configured_dev = -1;
     int dev = 0;
     IPM_CUDA_OK(cudaGetDevice(&dev));
     if (configured_dev != dev) {
-        IPM_CUDA_OK(cudaFuncSetAttribute(kb_residual<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + 8192));
+        IPM_CUDA_OK(cudaFuncSetAttribute(kb_residual<NPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + 8192));
+        IPM_CUDA_OK(cudaFuncSetAttribute(kb_residual<NPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + 8192));
         IPM_CUDA_OK(cudaFuncSetAttribute(kb_dir<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
+        IPM_CUDA_OK(cudaFuncSetAttribute(kbf_dir<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kf_smem_bytes(256, 1024)));
+        IPM_CUDA_OK(cudaFuncSetAttribute(kbf_dir<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kf_smem_bytes(256, 1024)));
+        IPM_CUDA_OK(cudaFuncSetAttribute(kbf_dir<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kf_smem_bytes(128, 1024)));
+        IPM_CUDA_OK(cudaFuncSetAttribute(kbf_dir<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kf_smem_bytes(128, 1024)));
+        IPM_CUDA_OK(cudaFuncSetAttribute(kbf_dir<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kf_smem_bytes(64, 1024)));
+        IPM_CUDA_OK(cudaFuncSetAttribute(kbf_dir<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kf_smem_bytes(64, 1024)));
         IPM_CUDA_OK(cudaFuncSetAttribute(k_trsv_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
         IPM_CUDA_OK(cudaFuncSetAttribute(k_trsv_batched_inv, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)trsv_batched_inv_smem(32 * TRSVI_MAX_BLK)));
         configured_dev = dev;
     }
-    kb_init<<<B, 256, 0, st>>>(a);
+    kb_init<<<B, 256, 0, st>>>(a, fused ? 2 : 1);
+    if (fused) {
+        const int nstrips = ceil_div(n, KF_W);
+        kbf_repack<<<dim3(nstrips, B), 256, 0, st>>>(a, 32 * kf_nrp(m), nstrips);
+        count_launch();
+    }
     count_launch();
     // The host reads the "LPs still active" counter of check k only after check k+1 has been enqueued, so the
     // GPU never idles on the host round trip; the price is one empty iteration (every kernel skips inactive LPs)
@@ -445,7 +495,8 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
         a.n_active = nact_base + slot * 16;
         IPM_CUDA_OK(cudaMemsetAsync(a.n_active, 0, sizeof(unsigned), st));
         g_prof.segment(st);
-        kb_residual<NPL><<<B, KB_NT, smem_res, st>>>(a);
+        if (fused) kb_residual<NPL, true><<<B, KB_NT, smem_res, st>>>(a);
+        else kb_residual<NPL, false><<<B, KB_NT, smem_res, st>>>(a);
         count_launch();
         g_prof.end_phase(PH_RESID, st);
         IPM_CUDA_OK(cudaMemcpyAsync(w.h_nact + slot, a.n_active, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
@@ -458,12 +509,6 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
             if (g_prof.enabled) g_prof.lp_iterations += cnt;
         }
         g_prof.segment(st);
-        DmmaArgs g;
-        g.P = a.A; g.ldp = n; g.strideP = (int64_t)m * n;
-        g.Q = a.A; g.ldq = n; g.strideQ = (int64_t)m * n;
-        g.dvec = a.d; g.strideD = n;
-        g.C = w.M; g.ldc = w.ldm; g.strideC = (int64_t)m * w.ldm;
-        g.rowsP = m; g.rowsQ = m; g.K = n; g.lower_only = 1; g.active = a.active;
         IPM_TRY((dmma_syrk_auto<0>(g, B, st)));
         g_prof.end_phase(PH_SYRK, st);
         if (m <= KBC_MAX_M_BIG)
@@ -475,12 +520,14 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
         TrsvBatchedArgs t;
         t.L = w.M; t.ldm = w.ldm; t.strideM = (int64_t)m * w.ldm; t.v = a.rhs; t.strideV = m; t.m = m;
         t.active = a.active;
+        if (fused) t.out = a.dy;           // the right-hand side survives: the corrector's is built on top of it
         for (int kind = 0; kind < 2; ++kind) {
-            kb_rhs<NPL><<<B, KB_NT, smem_w, st>>>(a, kind);
+            if (!fused || kind == 0) kb_rhs<NPL><<<B, KB_NT, smem_w, st>>>(a, kind);
             if (m <= 32 * TRSVI_MAX_BLK) k_trsv_batched_inv<<<B, TRSVB_NT, trsv_batched_inv_smem(m), st>>>(t);
             else k_trsv_batched<<<B, TRSVB_NT, trsv_batched_smem(m), st>>>(t);
-            kb_dir<NPL><<<B, KB_NT, smem_col, st>>>(a, kind);
-            count_launch(3);
+            if (!fused) kb_dir<NPL><<<B, KB_NT, smem_col, st>>>(a, kind);
+            else launch_kbf_dir(kind, a, B, m, st);
+            count_launch((fused && kind == 1) ? 2 : 3);
         }
         g_prof.end_phase(PH_SOLVE, st);
         IPM_TRY(launch_check());
@@ -499,6 +546,7 @@ int solve_on_device(int B, int m, int n, const double* A_d, const double* b_d, c
     w.h_nact = h_nact;
     w.a.A = A_d; w.a.b = b_d; w.a.c = c_d;
     w.a.tol = tol; w.a.eta = 0.91; w.a.max_iter = max_iter;
+    w.a.fresh_every = g_fresh_every;
     const double tau = 1e-30;
     if (n <= 512) IPM_TRY(run_batched<8>(w, B, m, n, tau, st, iterations_run));
     else IPM_TRY(run_batched<16>(w, B, m, n, tau, st, iterations_run));
@@ -520,6 +568,13 @@ int check_shape(int B, int m, int n) {
 }  // namespace
 
 extern "C" {
+
+int ipm_batched_set_variant(int three_pass, int refresh_every) {
+    if (refresh_every < 0) return IPM_ERR_ARG;
+    g_allow_fused = three_pass != 0;
+    g_fresh_every = refresh_every;
+    return IPM_OK;
+}
 
 int ipm_profile_enable(int on) {
     g_prof.collect();

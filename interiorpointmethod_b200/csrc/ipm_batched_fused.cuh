@@ -1,0 +1,331 @@
+// Batched direction kernels of the 3-pass iteration (m <= 256): one CTA per LP walks A_i in column strips of 16
+// (m x 16 doubles, a ring of six buffers in shared memory filled by bulk copies, four strips in flight), so that ONE trip of A_i through HBM serves
+// both products every direction needs:
+//     u = A^T dy          (column sums over the strip, needed first)
+//     q = A e             (row sums, where e depends on u through the elementwise direction formulas)
+// kind 0 (predictor, main.py:225-228, 305-322, 582-600):
+//     dxa = d u + w, dsa = -s dxa / x - rcx, ratio test, mu_aff, sigma, and the corrector right-hand side by
+//     linearity of main.py:150-152 in r4 = x s + dxa dsa - sigma mu:
+//         rhs_corr = -rb - A d (rc - r4/x) = rhs_pred + A (d dxa dsa / x) - sigma mu A (d / x)
+// kind 1 (corrector, main.py:142-159, 604-626, 694-696):
+//     dx, ds, eta-damped ratio test, x += ap dx, y += ad dy, s += ad ds, and the residuals of the NEW point from
+//     q = A dx and u:   rb += ap q,  rc += ad (u + ds)   (exact identities; check_optimality main.py:169-173 is
+//     re-evaluated from scratch by kb_residual for every LP these recurrences declare converged),
+//     then d = x/s and the predictor operand w = d (rc - (x s)/x) for the next assembly.
+// With the predictor right-hand side (kb_rhs, one pass) an iteration reads A four times instead of six.
+#pragma once
+#include "common.cuh"
+#include "dmma_ws.cuh"
+
+namespace ipm {
+
+constexpr int KF_NT = 512;                  // streaming threads
+constexpr int KF_NTT = KF_NT + 32;          // + warp E (elementwise formulas)
+constexpr int KF_W = 16;                    // strip width (columns)
+constexpr int KF_RG = KF_NT / KF_W;         // 32 row groups
+constexpr int KF_RPT = 8;                   // rows per thread
+constexpr int KF_MAX_M = KF_RG * KF_RPT;    // 256
+
+struct BatchArgs {
+    const double* A;   // [B][m][n]
+    double* At;        // [B][ceil(n/16)][32*nrp][16]  strip-major copy of A (3-pass path, kbf_repack)
+    const double* b;   // [B][m]
+    const double* c;   // [B][n]
+    double *x, *s, *rc, *d, *w, *rcx, *dxa, *dsa;      // [B][n]
+    double *y, *rb, *dy, *rhs;                         // [B][m]
+    double* scal;      // [B][S_COUNT]
+    int* active;       // [B]   0 = finished, 1 = iterating, 2 = to be checked from scratch (3-pass path)
+    int* iters;        // [B]
+    unsigned* n_active;
+    int m, n;
+    double tol, eta;
+    int max_iter;
+    int fresh_every;   // 3-pass path: residuals are re-evaluated from scratch every fresh_every-th iteration (0 = only
+                       // when the recurrences report convergence)
+};
+
+constexpr int KF_NBUF = 5;                  // strip buffers: row sums of s-2, s-1 (pending), column sums of s, loads ahead
+constexpr int KF_AHEAD = KF_NBUF - 2;       // strips in flight: one CTA per SM keeps 3 x 32 KB on the wire
+
+inline int kf_nrp(int m) { return m <= 32 ? 1 : m <= 64 ? 2 : m <= 128 ? 4 : 8; }     // rows per thread
+inline size_t kf_smem_bytes(int m, int n) {
+    const int mr = 32 * kf_nrp(m);
+    const int npad = (n + KF_W - 1) / KF_W * KF_W;
+    return (size_t)(KF_NBUF * mr * KF_W + 3 * mr + 4 * (KF_NT / 32) * KF_W + 8 * KF_W + 5 * npad) * sizeof(double);
+}
+
+#ifdef __CUDACC__
+// One CTA per SM, 17 warps.  Thread 0 keeps four strips (4 x 32 KB) in flight with bulk copies (UBLKCP) from the
+// strip-major copy of A into a ring of six buffers, each with its own mbarrier.  Per strip s the 16 streaming
+// warps form the column sums (-> part[s & 3], mbarrier pfull), warp E turns them into dx, ds and the row-sum
+// operand e (-> ev[s & 3], mbarrier efull) and the streaming warps add the row sums of strip s-2, so E's chain
+// of dependent FP64 operations (long latency on this part) is two strips off the critical path.
+// NRP = rows per thread is a template parameter (rows are padded to 32 NRP with zeros), which turns every
+// shared-memory offset of the inner loops into an immediate: the first version was issue-bound on index
+// arithmetic (ncu: 300 warp instructions per strip and warp, 75 % of them integer).
+template <int KIND, int NRP>
+__global__ void __launch_bounds__(KF_NTT, 1) kbf_dir(const BatchArgs a) {
+    constexpr int MR = 32 * NRP;                  // padded rows
+    constexpr int SB = MR * KF_W;                 // doubles per strip buffer
+    extern __shared__ __align__(16) double smem[];
+    __shared__ double sh[32];
+    __shared__ double s_val[4];
+    __shared__ __align__(8) uint64_t full[KF_NBUF], pfull[4], efull[4];
+    const int lp = blockIdx.x;
+    if (a.active[lp] == 0) return;
+    const int m = a.m, n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int mr = MR;
+    double* strip = smem;                         // [KF_NBUF][MR][16]
+    double* dys = strip + KF_NBUF * SB;           // [MR]   dy
+    double* q1s = dys + MR;                       // [MR]   A e1
+    double* q2s = q1s + MR;                       // [MR]   A e2 (kind 0)
+    double* part = q2s + MR;                      // [4][16 warps][16] column partial sums (ring of 4 strips)
+    double* ev1 = part + 4 * (KF_NT / 32) * KF_W; // [4][16]
+    double* ev2 = ev1 + 4 * KF_W;                 // [4][16]
+    double* gsm = ev2 + 4 * KF_W;                 // [5][npad] per-column coefficients that do not depend on u
+    const double* A = a.A + (size_t)lp * m * n;
+    const size_t on = (size_t)lp * n, om = (size_t)lp * m;
+    double* scal = a.scal + (size_t)lp * S_COUNT;
+    const int c = tid & (KF_W - 1), rg = tid >> 4;
+    const int nstrips = (n + KF_W - 1) / KF_W;
+
+    // strip s of this LP is one contiguous block of the strip-major copy: a single bulk (TMA) copy per strip,
+    // completion signalled on the buffer's mbarrier
+    const double* At = a.At + (size_t)lp * nstrips * SB;
+    if (tid == 0) {
+        for (int k = 0; k < KF_NBUF; ++k) mbar_init(full + k, 1);
+        for (int k = 0; k < 4; ++k) { mbar_init(pfull + k, KF_NT / 32); mbar_init(efull + k, 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int sidx, int boff_d, int slot) {     // thread 0 only
+        const uint32_t bar = smem_u32(full + slot);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(SB * 8)) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(strip + boff_d)), "l"(At + (size_t)sidx * SB), "r"((uint32_t)(SB * 8)), "r"(bar)
+                     : "memory");
+    };
+    if (tid == 0) {
+        for (int k = 0; k < KF_AHEAD && k < nstrips; ++k) issue(k, k * SB, k);
+    }
+    for (int i = tid; i < mr; i += KF_NTT) dys[i] = (i < m) ? a.dy[om + i] : 0.0;
+    const double sigma_mu = (KIND == 1) ? scal[S_SIGMA_MU] : 0.0;
+    // Everything of the elementwise formulas that does not depend on u (it holds the divisions), for all columns,
+    // by all threads, while the first strips are on their way:
+    //   kind 0: dx = d u + w,        ds = g2 dx - rcx,   e1 = g3 dx ds, e2 = g3      (g2 = -s/x, g3 = d/x)
+    //   kind 1: dx = d u + w_corr,   ds = g2 dx - rcx_corr
+    const int npad = nstrips * KF_W;
+    for (int k = tid; k < npad; k += KF_NTT) {
+        double di = 0.0, v0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
+        if (k < n) {
+            const double xi = a.x[on + k], si = a.s[on + k];
+            di = a.d[on + k];
+            g2 = -si / xi;
+            if (KIND == 0) {
+                v0 = a.w[on + k];
+                g1 = a.rcx[on + k];
+                g3 = di / xi;
+            } else {
+                const double rcomp = xi * si + a.dxa[on + k] * a.dsa[on + k] - sigma_mu;
+                g1 = rcomp / xi;
+                v0 = di * (a.rc[on + k] - g1);
+            }
+        }
+        gsm[k] = di; gsm[npad + k] = v0; gsm[2 * npad + k] = g1; gsm[3 * npad + k] = g2; gsm[4 * npad + k] = g3;
+    }
+    __syncthreads();
+
+    double acc1[NRP], acc2[NRP];
+#pragma unroll
+    for (int i = 0; i < NRP; ++i) acc1[i] = acc2[i] = 0.0;
+
+    const int toff = rg * KF_W + c;               // this thread's element inside a strip buffer
+    // Role split.  Warps 0..15 (512 threads) stream the strips: column sums of strip s, row sums of strip s-2.
+    // Warp 16 (E) turns the column sums of a strip into the direction entries of its 16 columns and runs up to two
+    // strips behind the streaming warps, so its chain of dependent FP64 operations never stalls them.
+    auto stream_bar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(KF_NT) : "memory"); };
+
+    if (warp == KF_NT / 32) {
+        // ------------------------------------------------------------------ E: u -> dx, ds, e
+        for (int sidx = 0; sidx < nstrips; ++sidx) {
+            const int j = sidx & 3;
+            mbar_wait(pfull + j, (uint32_t)(sidx >> 2) & 1u);
+            // u: 16 warp partials per column, two lanes per column (8 each, pairwise), fixed order
+            const double* pp = part + j * (KF_NT / 32) * KF_W + (lane >> 4) * 8 * KF_W + (lane & 15);
+            const double t0 = pp[0] + pp[KF_W], t1 = pp[2 * KF_W] + pp[3 * KF_W];
+            const double t2 = pp[4 * KF_W] + pp[5 * KF_W], t3 = pp[6 * KF_W] + pp[7 * KF_W];
+            double u = (t0 + t1) + (t2 + t3);
+            u += __shfl_xor_sync(0xffffffffu, u, 16);
+            const int col = sidx * KF_W + lane;
+            if (lane < KF_W) {
+                const double* gq = gsm + col;
+                const double di = gq[0], v0 = gq[npad], g1 = gq[2 * npad], g2 = gq[3 * npad], g3 = gq[4 * npad];
+                const double dxi = di * u + v0;
+                const double dsi = g2 * dxi - g1;
+                double e1, e2 = 0.0;
+                if (KIND == 0) { e1 = g3 * (dxi * dsi); e2 = g3; }
+                else e1 = dxi;
+                if (col < n) {
+                    a.dxa[on + col] = dxi;          // kind 1: the final direction replaces the predictor's
+                    a.dsa[on + col] = dsi;
+                    if (KIND == 1) a.w[on + col] = u + dsi;       // A^T dy + ds: change of rc per unit dual step
+                } else {
+                    e1 = e2 = 0.0;
+                }
+                ev1[j * KF_W + lane] = e1;
+                ev2[j * KF_W + lane] = e2;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(efull + j);
+        }
+    } else {
+        // ------------------------------------------------------------------ streaming warps
+        auto row_sums = [&](int boff_d, int sidx) {
+            const int j = sidx & 3;
+            mbar_wait(efull + j, (uint32_t)(sidx >> 2) & 1u);
+            const double* sb = strip + boff_d + toff;
+            const double f1 = ev1[j * KF_W + c], f2 = ev2[j * KF_W + c];
+#pragma unroll
+            for (int i = 0; i < NRP; ++i) {
+                const double v = sb[i * KF_RG * KF_W];
+                acc1[i] = fma(v, f1, acc1[i]);
+                if (KIND == 0) acc2[i] = fma(v, f2, acc2[i]);
+            }
+        };
+        // buffer offsets (doubles) of strips s-2, s-1, s and s+KF_AHEAD rotate through the ring
+        auto nextb = [](int bo) { return (bo + SB == KF_NBUF * SB) ? 0 : bo + SB; };
+        int b_prev2 = (KF_NBUF - 2) * SB, b_prev = (KF_NBUF - 1) * SB, b_cur = 0;
+        int slot = 0;
+        uint32_t parity = 0;
+        for (int sidx = 0; sidx < nstrips; ++sidx) {
+            mbar_wait(full + slot, parity);                     // strip sidx has landed
+            {
+                const double* sb = strip + b_cur + toff;
+                const double* dq = dys + rg;
+                double p0 = 0.0, p1 = 0.0;                      // two chains: FP64 latency is long on this part
+#pragma unroll
+                for (int i = 0; i < NRP; i += 2) {
+                    p0 = fma(sb[i * KF_RG * KF_W], dq[KF_RG * i], p0);
+                    if (i + 1 < NRP) p1 = fma(sb[(i + 1) * KF_RG * KF_W], dq[KF_RG * (i + 1)], p1);
+                }
+                double p = p0 + p1;
+                p += __shfl_xor_sync(0xffffffffu, p, 16);       // the warp's two row groups
+                if (lane < KF_W) part[(sidx & 3) * (KF_NT / 32) * KF_W + warp * KF_W + lane] = p;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(pfull + (sidx & 3));
+            }
+            if (sidx >= 2) row_sums(b_prev2, sidx - 2);
+            stream_bar();                                       // strip sidx-2 is no longer read by anyone
+            if (tid == 0 && sidx + KF_AHEAD < nstrips) issue(sidx + KF_AHEAD, b_prev2, (slot + KF_AHEAD) % KF_NBUF);
+            b_prev2 = b_prev; b_prev = b_cur; b_cur = nextb(b_cur);
+            if (++slot == KF_NBUF) { slot = 0; parity ^= 1u; }
+        }
+        if (nstrips >= 2) row_sums(b_prev2, nstrips - 2);
+        row_sums(b_prev, nstrips - 1);
+    }
+    __syncthreads();
+    // row sums: combine the 16 column lanes of every row group
+#pragma unroll
+    for (int i = 0; i < NRP; ++i) {
+        double v = acc1[i], v2 = acc2[i];
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (KIND == 0) v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+        }
+        const int r = rg + KF_RG * i;
+        if (tid < KF_NT && c == 0 && r < mr) { q1s[r] = v; q2s[r] = v2; }
+    }
+    // ratio test over all columns (main.py:305-322)
+    double minp = 1.0, mind = 1.0;
+    for (int k = tid; k < n; k += KF_NTT) {
+        const double dxi = a.dxa[on + k], dsi = a.dsa[on + k];
+        if (dxi < 0.0) minp = fmin(minp, -a.x[on + k] / dxi);
+        if (dsi < 0.0) mind = fmin(mind, -a.s[on + k] / dsi);
+    }
+    minp = block_red<RED_MIN>(minp, sh);
+    if (tid == 0) s_val[0] = minp;
+    mind = block_red<RED_MIN>(mind, sh);
+    if (tid == 0) s_val[1] = mind;
+    __syncthreads();
+    double ap = s_val[0], ad = s_val[1];
+    if (KIND == 0) {
+        double partsum = 0.0;
+        for (int k = tid; k < n; k += KF_NTT)
+            partsum += (a.x[on + k] + ap * a.dxa[on + k]) * (a.s[on + k] + ad * a.dsa[on + k]);
+        partsum = block_red<RED_SUM>(partsum, sh);
+        if (tid == 0) {
+            const double mu_aff = partsum / (double)n, mu = scal[S_XS] / (double)n;
+            const double r = mu_aff / mu, sigma = r * r * r;
+            scal[S_AP_AFF] = ap; scal[S_AD_AFF] = ad; scal[S_MU_AFF] = mu_aff; scal[S_MU] = mu;
+            scal[S_SIGMA] = sigma; scal[S_SIGMA_MU] = sigma * mu;
+            s_val[2] = sigma * mu;
+        }
+        __syncthreads();
+        const double sm = s_val[2];
+        for (int i = tid; i < m; i += KF_NTT) a.rhs[om + i] = a.rhs[om + i] + q1s[i] - sm * q2s[i];
+    } else {
+        ap = fmin(1.0, a.eta * ap);
+        ad = fmin(1.0, a.eta * ad);
+        double nrc2 = 0.0, xs = 0.0, obj = 0.0, nrb2 = 0.0;
+        for (int k = tid; k < n; k += KF_NTT) {
+            const double xn = a.x[on + k] + ap * a.dxa[on + k];
+            const double sn = a.s[on + k] + ad * a.dsa[on + k];
+            const double rcn = a.rc[on + k] + ad * a.w[on + k];
+            const double dn = xn / sn;
+            const double q = (xn * sn) / xn;
+            a.x[on + k] = xn; a.s[on + k] = sn; a.rc[on + k] = rcn; a.d[on + k] = dn;
+            a.rcx[on + k] = q;
+            a.w[on + k] = dn * (rcn - q);
+            nrc2 += rcn * rcn;
+            xs += xn * sn;
+            obj += xn * a.c[on + k];
+        }
+        for (int i = tid; i < m; i += KF_NTT) {
+            a.y[om + i] = a.y[om + i] + ad * dys[i];
+            const double r = a.rb[om + i] + ap * q1s[i];
+            a.rb[om + i] = r;
+            nrb2 += r * r;
+        }
+        nrb2 = block_red<RED_SUM>(nrb2, sh);
+        if (tid == 0) s_val[2] = nrb2;
+        nrc2 = block_red<RED_SUM>(nrc2, sh);
+        xs = block_red<RED_SUM>(xs, sh);
+        obj = block_red<RED_SUM>(obj, sh);
+        if (tid == 0) {
+            nrb2 = s_val[2];
+            const double nrb = sqrt(nrb2), nrc = sqrt(nrc2);
+            scal[S_NRB2] = nrb2; scal[S_NRB] = nrb; scal[S_NRC2] = nrc2; scal[S_NRC] = nrc;
+            scal[S_XS] = xs; scal[S_OBJ] = obj; scal[S_AP] = ap; scal[S_AD] = ad;
+            const bool cont = (a.tol * (1.0 + scal[S_NB]) < nrb) || (a.tol * (1.0 + scal[S_NC]) < nrc) || (a.tol < xs);
+            scal[S_CONT] = cont ? 1.0 : 0.0;
+            const int it = a.iters[lp] + 1;
+            a.iters[lp] = it;
+            // stop candidates (and the iteration cap) are decided by kb_residual on residuals computed from scratch
+            if (!cont || it >= a.max_iter || (a.fresh_every > 0 && it % a.fresh_every == 0)) a.active[lp] = 2;
+        }
+    }
+}
+// Strip-major copy of A for kbf_dir: At[lp][s][r][c] = A[lp][r][16 s + c], rows padded to mr = 32 nrp and columns to
+// a multiple of 16 with zeros, so that a column strip is ONE contiguous block (DRAM pages are read whole and a
+// strip is a single bulk copy).  One CTA per (strip, LP), one thread per row; runs once per solve.
+__global__ void __launch_bounds__(256) kbf_repack(const BatchArgs a, int mr, int nstrips) {
+    const int s = blockIdx.x, lp = blockIdx.y;
+    const int m = a.m, n = a.n;
+    const double* A = a.A + (size_t)lp * m * n;
+    double* dst = a.At + ((size_t)lp * nstrips + s) * mr * KF_W;
+    for (int r = threadIdx.x; r < mr; r += blockDim.x) {
+        double2 v[KF_W / 2];
+#pragma unroll
+        for (int q = 0; q < KF_W / 2; ++q) {
+            const int col = s * KF_W + 2 * q;
+            v[q] = (r < m && col < n) ? *reinterpret_cast<const double2*>(A + (size_t)r * n + col) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int q = 0; q < KF_W / 2; ++q) reinterpret_cast<double2*>(dst + (size_t)r * KF_W)[q] = v[q];
+    }
+}
+
+#endif
+
+}  // namespace ipm

@@ -89,3 +89,45 @@ def test_batched_device_entry_point_large_batch_properties(ipm):
         xh = rng.uniform(0.1, 1.1, n)
         xh_obj.append(c[i] @ xh)
     assert (obj1[::97] <= np.array(xh_obj) + 1e-6).all()
+
+
+@pytest.mark.parametrize("m,n,B", [(256, 512, 64), (48, 100, 40), (130, 70, 9), (200, 1000, 5)])
+def test_three_pass_iteration_matches_six_pass(ipm, m, n, B):
+    """The 3-pass iteration (right-hand sides by linearity, residuals by recurrence, from-scratch check before an LP
+    is declared finished) against the 6-pass one that evaluates main.py:725-751 literally: same iteration count
+    +-1, same objective to 1e-8, and the returned x satisfies the reference's stopping rule (main.py:170)."""
+    from interiorpointmethod_b200 import _lib
+    from interiorpointmethod_b200.batch import solve_batched_host
+    lib = _lib.load()
+    A, b, c = ipm.synthetic_dense_batch(7, B, m, n)
+    try:
+        lib.ipm_batched_set_variant(0, 3)
+        o6, k6, s6 = solve_batched_host(A, b, c, tol=1e-8)
+        lib.ipm_batched_set_variant(1, 3)
+        o3, k3, s3, x3 = solve_batched_host(A, b, c, tol=1e-8, want_x=True)
+    finally:
+        lib.ipm_batched_set_variant(1, 3)
+    assert (s6 == 0).all() and (s3 == 0).all()
+    assert np.abs(k3.astype(int) - k6.astype(int)).max() <= 1
+    assert (np.abs(o3 - o6) <= 1e-8 * np.abs(o6)).all()      # the parity bar of SURVEY 8(c)
+    rb = np.einsum("bmn,bn->bm", A, x3) - b
+    assert (np.linalg.norm(rb, axis=1) <= 1.001e-8 * (1 + np.linalg.norm(b, axis=1))).all()
+
+
+def test_three_pass_refresh_keeps_ill_conditioned_lp_on_track(ipm):
+    """LP 7466 of the benchmark batch: with residuals carried by recurrence only, the 3-pass iteration needs 60
+    iterations (measured on B200) where the six-pass one needs 16; the default refresh period must keep it
+    within +-1."""
+    from interiorpointmethod_b200 import _lib
+    from interiorpointmethod_b200.batch import solve_batched_host
+    lib = _lib.load()
+    A, b, c = ipm.synthetic_dense_batch(7464, 4, 256, 512)
+    try:
+        lib.ipm_batched_set_variant(0, 3)
+        o6, k6, s6 = solve_batched_host(A, b, c, tol=1e-8)
+    finally:
+        lib.ipm_batched_set_variant(1, 3)
+    o3, k3, s3 = solve_batched_host(A, b, c, tol=1e-8)
+    assert (s6 == 0).all() and (s3 == 0).all()
+    assert np.abs(k3.astype(int) - k6.astype(int)).max() <= 1
+    assert (np.abs(o3 - o6) <= 1e-7 * np.abs(o6)).all()     # rb is at its noise floor here: 1e-8 is not attainable
