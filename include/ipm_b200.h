@@ -76,6 +76,13 @@ int ipm_load_dense_d(ipm_handle *h, int m, int n, const double *A_d, int64_t lda
 /* ---------------------------------------------------------------- iterate */
 /* x = s = 1; y = 1 (initial_vector_sparse, sparse_interior.py:193-200) or y = 0 (initial_vector, main.py:287-302). */
 int ipm_init_state(ipm_handle *h, int y0_is_one);
+/* NOT in the reference (opt-in): Mehrotra's starting point, x = A^T (A A^T)^-1 b and
+ * s = c - A^T y with y = (A A^T)^-1 A c, both shifted into the positive orthant (SIAM J. Optim. 2 (1992) sec. 7),
+ * computed on the device with the solver's own SYRK/SpGEMM, Cholesky and triangular-solve kernels.  It changes the
+ * iteration count (AFIRO 93 -> 15) and lets the LPs converge on which the reference's start x = s = 1 fails
+ * (25FV47: NaN after 331 iterations -> Netlib optimum in 33), so iteration parity with the reference does not
+ * apply to it. */
+int ipm_start_mehrotra(ipm_handle *h);
 int ipm_set_state(ipm_handle *h, const double *x, const double *y, const double *s);
 int ipm_get_state(ipm_handle *h, double *x, double *y, double *s);
 
@@ -125,9 +132,16 @@ int ipm_solve_spd(int device_ordinal, int m, const double *M_rowmajor, const dou
 /* ---------------------------------------------------------------- solve level
  * Whole predictor-corrector loop on the device (interior_sparse main.py:760-815 when the problem
  * was loaded with ipm_load_csr, interior main.py:707-757 when loaded dense).  Starts from
- * ipm_init_state(y0_is_one).  e1 = e2 = e3 = tol as in both drivers.
+ * ipm_init_state(y0_is_one) for y0_is_one = 0 / 1 (the reference's two drivers); IPM_START_KEEP and
+ * IPM_START_MEHROTRA select the other starting points.  e1 = e2 = e3 = tol as in both drivers.
  * Outputs (each may be NULL): x (n), y (m), s (n), obj = c^T x (the caller subtracts cTlb),
  * iters, status, resid = { |rb|, |rc|, x^T s, |b|, |c| } at exit. */
+enum {
+    IPM_START_Y0 = 0,        /* x = s = 1, y = 0   (initial_vector, main.py:287-302) */
+    IPM_START_Y1 = 1,        /* x = s = 1, y = 1   (initial_vector_sparse, sparse_interior.py:193-200) */
+    IPM_START_KEEP = 2,      /* the iterate already in the handle (ipm_set_state / ipm_start_mehrotra) */
+    IPM_START_MEHROTRA = 3   /* ipm_start_mehrotra first; not in the reference */
+};
 int ipm_solve(ipm_handle *h, double tol, int max_iter, int y0_is_one,
               double *x, double *y, double *s, double *obj, int *iters, int *status, double resid[5]);
 

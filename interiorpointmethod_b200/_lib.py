@@ -44,6 +44,7 @@ SYMBOLS = {
     "ipm_op_update": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double,
                               c_double]),
     "ipm_solve_spd": (c_int, [c_int, c_int, c_void_p, c_void_p, c_double, c_void_p, _ip]),
+    "ipm_start_mehrotra": (c_int, [c_void_p]),
     "ipm_solve": (c_int, [c_void_p, c_double, c_int, c_int, c_void_p, c_void_p, c_void_p, _dp, _ip, _ip, c_void_p]),
     "ipm_solve_batched_dense": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_double, c_int,
                                         c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -433,6 +433,30 @@ int ipm_init_state(ipm_handle* h, int y0_is_one) {
     return IPM_OK;
 }
 
+int ipm_start_mehrotra(ipm_handle* h) {
+    H_TRY(check_handle(h));
+    const int m = h->m, n = h->n;
+    // d = 1: M = A A^T, factored once with the same safeguarded Cholesky the iterations use
+    k_fill<<<vec_grid(n), VEC_NT, 0, h->st>>>(h->d, n, 1.0);
+    count_launch();
+    H_TRY(assemble_step(h));
+    H_TRY(factor_step(h, h->tau));
+    // x = A^T (A A^T)^-1 b
+    H_CUDA(cudaMemcpyAsync(h->rhs, h->b, (size_t)m * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+    H_TRY(potrs_single(h->M, h->ldm, m, h->rhs, h->tmp_m, h->dy, h->st));
+    H_TRY(matvec_AT(h, h->dy, h->x));
+    // y = (A A^T)^-1 A c,  s = c - A^T y
+    H_TRY(matvec_A(h, h->c, h->rhs));
+    H_TRY(potrs_single(h->M, h->ldm, m, h->rhs, h->tmp_m, h->y, h->st));
+    H_TRY(matvec_AT(h, h->y, h->tn));
+    k_sub<<<vec_grid(n), VEC_NT, 0, h->st>>>(h->c, h->tn, h->s, n);
+    k_mehrotra_shift<<<1, 1024, 0, h->st>>>(h->x, h->s, n);
+    count_launch(2);
+    H_TRY(launch_check());
+    h->have_resid = h->have_M = h->have_factor = h->have_pred = h->have_sigma = h->have_corr = false;
+    return IPM_OK;
+}
+
 int ipm_set_state(ipm_handle* h, const double* x, const double* y, const double* s) {
     H_TRY(check_handle(h));
     if (!x || !y || !s) return fail(h, IPM_ERR_ARG, "null pointer");
@@ -559,7 +583,13 @@ int ipm_solve(ipm_handle* h, double tol, int max_iter, int y0_is_one, double* x,
     H_TRY(check_handle(h));
     if (max_iter < 0) return fail(h, IPM_ERR_ARG, "max_iter < 0");
     h->tol = tol;
-    H_TRY(ipm_init_state(h, y0_is_one));
+    if (y0_is_one == IPM_START_KEEP) {            // iterate set by ipm_set_state / ipm_start_mehrotra
+        h->have_resid = h->have_M = h->have_factor = h->have_pred = h->have_sigma = h->have_corr = false;
+    } else if (y0_is_one == IPM_START_MEHROTRA) {
+        H_TRY(ipm_start_mehrotra(h));
+    } else {
+        H_TRY(ipm_init_state(h, y0_is_one));
+    }
     int k = 0;
     const double tau = h->tau;
     auto body = [&]() -> int {

@@ -167,6 +167,50 @@ static __global__ void k_fill(double* v, int64_t len, double val) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x)
         v[i] = val;
 }
+// Starting point heuristic of Mehrotra (SIAM J. Optim. 2 (1992), sec. 7) - NOT in the reference, opt-in
+// (SURVEY.md 8(f) row 4).  On entry x = A^T (A A^T)^-1 b and s = c - A^T y with y = (A A^T)^-1 A c; one CTA shifts
+// both into the positive orthant:  dx = max(-1.5 min x, 0), ds likewise, then the second shift
+// 0.5 (x^T s) / sum(s) resp. / sum(x) that balances the complementarity products.
+static __global__ void __launch_bounds__(1024) k_mehrotra_shift(double* x, double* s, int n) {
+    __shared__ double sh[32];
+    __shared__ double bc[2];
+    const int tid = threadIdx.x;
+    double mx = red_identity<RED_MIN>(), ms = red_identity<RED_MIN>();
+    for (int i = tid; i < n; i += blockDim.x) { mx = fmin(mx, x[i]); ms = fmin(ms, s[i]); }
+    mx = block_red<RED_MIN>(mx, sh);
+    if (tid == 0) bc[0] = fmax(-1.5 * mx, 0.0);
+    ms = block_red<RED_MIN>(ms, sh);
+    if (tid == 0) bc[1] = fmax(-1.5 * ms, 0.0);
+    __syncthreads();
+    const double dx = bc[0], ds = bc[1];
+    double xs = 0.0, sx = 0.0, ss = 0.0;
+    for (int i = tid; i < n; i += blockDim.x) {
+        const double xi = x[i] + dx, si = s[i] + ds;
+        xs += xi * si; sx += xi; ss += si;
+    }
+    __shared__ double tot[3];
+    xs = block_red<RED_SUM>(xs, sh);
+    if (tid == 0) tot[0] = xs;
+    sx = block_red<RED_SUM>(sx, sh);
+    if (tid == 0) tot[1] = sx;
+    ss = block_red<RED_SUM>(ss, sh);
+    if (tid == 0) {
+        // second shift: x gets 0.5 x^T s / sum(s), s gets 0.5 x^T s / sum(x)
+        bc[0] = dx + 0.5 * tot[0] / fmax(ss, 1e-300);
+        bc[1] = ds + 0.5 * tot[0] / fmax(tot[1], 1e-300);
+    }
+    __syncthreads();
+    const double tx = bc[0], ts = bc[1];
+    for (int i = tid; i < n; i += blockDim.x) {
+        x[i] = fmax(x[i] + tx, 1e-10);
+        s[i] = fmax(s[i] + ts, 1e-10);
+    }
+}
+// out = c - v  (dual slack of the starting point)
+static __global__ void k_sub(const double* c, const double* v, double* out, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = c[i] - v[i];
+}
+
 #endif
 
 }  // namespace ipm

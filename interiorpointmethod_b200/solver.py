@@ -177,13 +177,21 @@ class NewtonStep:
         self._check(self._lib.ipm_update(self._h, float(alpha_p), float(alpha_d)), "ipm_update")
 
     # ------------------------------------------------------------------ solve level
-    def solve(self, tol: float = 1e-8, max_iter: int = 5000, y0_is_one: bool = True, cTlb: float = 0.0) -> Result:
+    def start_mehrotra(self):
+        """Opt-in starting point that is NOT in the reference (include/ipm_b200.h, ipm_start_mehrotra)."""
+        self._check(self._lib.ipm_start_mehrotra(self._h), "ipm_start_mehrotra")
+
+    def solve(self, tol: float = 1e-8, max_iter: int = 5000, y0_is_one: bool = True, cTlb: float = 0.0,
+              start: str = "reference") -> Result:
+        """start="reference": x = s = 1 and y per `y0_is_one` (the reference's two drivers);
+        "mehrotra": ipm_start_mehrotra (not in the reference, no iteration parity); "keep": the current iterate."""
+        mode = {"reference": int(bool(y0_is_one)), "keep": 2, "mehrotra": 3}[start]
         x, y, s = np.empty(self.n), np.empty(self.m), np.empty(self.n)
         obj = ctypes.c_double(0.0)
         it = ctypes.c_int(0)
         st = ctypes.c_int(0)
         res = np.empty(5)
-        self._check(self._lib.ipm_solve(self._h, float(tol), int(max_iter), int(bool(y0_is_one)), _ptr(x), _ptr(y),
+        self._check(self._lib.ipm_solve(self._h, float(tol), int(max_iter), mode, _ptr(x), _ptr(y),
                                         _ptr(s), ctypes.byref(obj), ctypes.byref(it), ctypes.byref(st), _ptr(res)),
                     "ipm_solve")
         return Result(x=_col(x), y=_col(y), s=_col(s), objective=float(obj.value) - float(cTlb),
@@ -193,13 +201,14 @@ class NewtonStep:
 
 # ====================================================================== reference-shaped functions
 def solve(A, b, c, tol: float = 1e-8, cTlb: float = 0.0, device: int = 0, max_iter: int = 5000,
-          y0_is_one: bool | None = None) -> Result:
-    """Load `benchmarks/*.mat`-style data, solve min c^T x s.t. Ax=b, x>=0; returns x, objective, iterations."""
+          y0_is_one: bool | None = None, start: str = "reference") -> Result:
+    """Load `benchmarks/*.mat`-style data, solve min c^T x s.t. Ax=b, x>=0; returns x, objective, iterations.
+    start="mehrotra" selects the opt-in starting point that is not in the reference (NewtonStep.solve)."""
     is_sparse = _sp is not None and _sp.issparse(A)
     if y0_is_one is None:
         y0_is_one = is_sparse          # sparse driver starts y=1 (sparse_interior.py:193-200), dense y=0 (main.py:287-302)
     with NewtonStep(A, b, c, device=device) as ns:
-        return ns.solve(tol=tol, max_iter=max_iter, y0_is_one=y0_is_one, cTlb=cTlb)
+        return ns.solve(tol=tol, max_iter=max_iter, y0_is_one=y0_is_one, cTlb=cTlb, start=start)
 
 
 def interior_sparse(A, b, c, cTlb, tol: float = 1e-20, device: int = 0, return_result: bool = False):

@@ -59,6 +59,25 @@ def initial_point(m, n, y0_is_one=True):
     return x, y, s
 
 
+def mehrotra_start(A, b, c, tau=PIVOT_TAU):
+    """NOT in the reference: Mehrotra's starting point (SIAM J. Optim. 2 (1992) sec. 7), the oracle of the product's
+    opt-in `ipm_start_mehrotra`.  x = A^T (A A^T)^-1 b, y = (A A^T)^-1 A c, s = c - A^T y,
+    then dx = max(-1.5 min x, 0), ds likewise, and the second shift 0.5 x^T s / sum(s) resp. / sum(x)."""
+    m, n = A.shape
+    one = np.ones((n, 1))
+    L, _ = cholesky_safeguarded(normal_matrix(A, one, one), tau)
+    x = A.T @ solve_with_factor(L, b)
+    y = solve_with_factor(L, A @ c)
+    s = c - A.T @ y
+    x = x + max(-1.5 * float(x.min()), 0.0)
+    s = s + max(-1.5 * float(s.min()), 0.0)
+    xs = float((x * s).sum())
+    sx, ss = float(x.sum()), float(s.sum())
+    x = np.maximum(x + 0.5 * xs / max(ss, 1e-300), 1e-10)
+    s = np.maximum(s + 0.5 * xs / max(sx, 1e-300), 1e-10)
+    return x, y, s
+
+
 # --------------------------------------------------------------------------- residuals / convergence
 def residuals(A, b, c, x, y, s):
     """rb = A x - b, rc = A^T y + s - c  (main.py:67-70)."""
@@ -274,7 +293,8 @@ def newton_iteration(A, b, c, x, y, s, linear="normal", dense=False, tau=PIVOT_T
     return x + ap * dx, y + ad * dy, s + ad * ds       # main.py:694-696
 
 
-def solve(A, b, c, cTlb=0.0, tol=1e-8, max_iter=5000, y0_is_one=True, linear="normal", tau=PIVOT_TAU):
+def solve(A, b, c, cTlb=0.0, tol=1e-8, max_iter=5000, y0_is_one=True, linear="normal", tau=PIVOT_TAU,
+          start="reference"):
     """Whole solve with `interior_sparse` semantics (main.py:760-815) when y0_is_one, `interior`
     semantics (main.py:707-757; cap 50000, y0 = 0) otherwise.
 
@@ -289,6 +309,11 @@ def solve(A, b, c, cTlb=0.0, tol=1e-8, max_iter=5000, y0_is_one=True, linear="no
     c = as_column(c)
     m, n = A.shape
     x, y, s = initial_point(m, n, y0_is_one)
+    if start == "mehrotra":
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            with np.errstate(all="ignore"):
+                x, y, s = mehrotra_start(A, b, c, tau)
     k = 0
     info = {}
     with warnings.catch_warnings():

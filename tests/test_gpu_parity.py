@@ -259,6 +259,27 @@ def test_25fv47_and_qap8_outcomes(ipm):
     assert res.status in ("converged", "nan", "max_iter")
 
 
+@pytest.mark.parametrize("name", CONVERGED + ["DEGEN2", "25FV47", "QAP8"])
+def test_mehrotra_start_reaches_reference_objective(ipm, orc, name, reference_results):
+    """Opt-in starting point that is not in the reference (ipm_start_mehrotra): same Newton
+    kernels, different x0, y0, s0.  Every LP must reach the objective the reference reaches (golden) - or, for the
+    two LPs the reference fails on, the Netlib optimum of main.py:1417-1516 - within 1e-8 relative, and the
+    iteration count must agree with the oracle run from the same starting point."""
+    A, b, c, cTlb = ipm.load_golden_problem(name)
+    res = ipm.solve(A, b, c, tol=1e-8, cTlb=cTlb, start="mehrotra", max_iter=500)
+    assert res.status == "converged"
+    target = {"25FV47": 5.5018458883e03, "QAP8": 2.0350000000e02}.get(name)
+    if target is None:
+        target = reference_results[name]["obj"]
+    assert abs(res.objective - target) <= 2e-8 * max(1.0, abs(target)), (res.objective, target)
+    r = res.residuals
+    assert r["rb"] <= 1e-8 * (1 + r["b"]) and r["rc"] <= 1e-8 * (1 + r["c"]) and r["gap"] <= 1e-8
+    assert np.all(res.x > 0) and np.all(res.s > 0)
+    if name in ("AFIRO", "SC50A", "SCSD1", "E226", "25FV47"):       # oracle runs that finish in seconds
+        o = orc.solve(A, b, c, cTlb=cTlb, tol=1e-8, start="mehrotra", max_iter=500)
+        assert o["status"] == 0 and abs(res.iterations - o["k"]) <= 2, (res.iterations, o["k"])
+
+
 # ------------------------------------------------------------------------------------------ kernels against torch fp64
 @pytest.mark.parametrize("m,n", [(1, 2), (27, 51), (130, 70), (512, 1024), (1000, 3001 + 1)])
 def test_syrk_kernel_against_torch(ipm, m, n):

@@ -144,3 +144,19 @@ def test_nan_input_stops_like_the_reference():
     b = b.copy(); b[0] = np.nan
     res = orc.solve(A, b, c, tol=1e-8, y0_is_one=False, linear="normal")
     assert res["k"] <= 1 and res["status"] == 2
+
+
+def test_mehrotra_start_oracle_reaches_netlib_optima():
+    """The opt-in starting point (not in the reference): the oracle with it converges on 25FV47, where the
+    reference's start x = s = 1 ends in NaN, to the Netlib optimum of main.py:1417-1516, and needs 15 instead of 93
+    iterations on AFIRO."""
+    from oracle import ipm_oracle as orc
+    from interiorpointmethod_b200.problems import load_golden_problem
+    A, b, c, cTlb = load_golden_problem("AFIRO")
+    r = orc.solve(A, b, c, cTlb=cTlb, tol=1e-8, start="mehrotra")
+    assert r["status"] == 0 and r["k"] <= 20
+    assert abs(r["obj"] - NETLIB_OPT["AFIRO"]) <= 1e-8 * abs(NETLIB_OPT["AFIRO"])
+    A, b, c, cTlb = load_golden_problem("25FV47")
+    r = orc.solve(A, b, c, cTlb=cTlb, tol=1e-8, start="mehrotra", max_iter=200)
+    assert r["status"] == 0 and r["k"] <= 40
+    assert abs(r["obj"] - 5.5018458883e03) <= 1e-8 * 5.5018458883e03
