@@ -21,7 +21,8 @@ constexpr int KBC_NT_BIG = 512;     // single-matrix variant for 256 < m <= 512:
 constexpr int kbc_max_m(int nt) { return 32 + (nt / 32 - 1) * 4 * 8; }
 constexpr int KBC_MAX_M = kbc_max_m(KBC_NT);          // 256
 constexpr int KBC_MAX_M_BIG = kbc_max_m(KBC_NT_BIG);  // 512
-constexpr int KBC_LD = 33;
+constexpr int KBC_LD = 34;     // 2-way conflicts for both access patterns (MMA fragments (g,t) and one row per thread); 33 made the
+                                // fragment reads 4-way (ncu: 53 M shared bank conflicts per 2048 LPs), 36 the row reads
 constexpr int KBC_LDT = 34;     // transposed diagonal block: even so that 128-bit reads stay aligned
 constexpr int KBC_KC = 64;      // columns of L[J+1, :] staged in shared memory per chunk of the update
 constexpr int KBC_LDB = KBC_KC + 4;   // 68 = 4 mod 16: conflict-free 64-bit fragment reads
