@@ -5,9 +5,11 @@
 
 Workload (BASELINE.json configs[4]): a batch of 8192 synthetic dense LPs, m=256, n=512, LP i drawn from
 numpy default_rng(i) (SURVEY.md §8d generator), solved to tol=1e-8 with the dense-driver semantics of the
-reference (`interior`, main.py:707-757).  One step = one solve of the whole batch.  The batch is partitioned
-statically over the N ranks (total work fixed => "strong" scaling), no data-path collective; the objectives,
-iteration counts and statuses are all-gathered once per step.
+reference (`interior`, main.py:707-757).  One step = one solve of the whole batch.  LPs are partitioned
+statically over the N ranks with no data-path collective; the objectives, iteration counts and statuses are
+all-gathered once per step.  --scaling weak (default, the rule for partitioned paths): every GPU solves 8192 LPs
+(rank r owns LP seeds 8192 r .. 8192 r + 8191); --scaling strong: 8192 LPs in total, 8192/N per GPU
+(BASELINE.json's literal "sharded across 1/2/4/8").
 
   value  LPs/s with the inputs resident in HBM, device-timed (CUDA events), max over ranks
   e2e    LPs/s through the C-ABI call that takes HOST buffers (pinned): H2D of A, b, c and D2H of the
@@ -91,7 +93,7 @@ def run_reference_arm(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "LPs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "batch of 8192 synthetic dense LPs m=256 n=512 (BASELINE.json configs[4])",
                    "batch": args.batch, "m": M_LP, "n": N_LP, "tol": TOL,
                    "step": "bounded sample: %d LPs per step (one per host core), extrapolated as LPs/s" % cores},
@@ -233,6 +235,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=8192)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default): every GPU solves --batch LPs (LP seeds rank*batch + i), no data-path "
+                         "collective; strong: --batch LPs in total, block-partitioned over the GPUs")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -265,7 +270,9 @@ def main():
     build.build()
     lib = _lib.load()
 
-    B = args.batch
+    # weak scaling (tier rule for partitioned paths): per-GPU work fixed, the batch grows with the GPU count;
+    # strong: BASELINE.json's literal "8192 LPs sharded across 1/2/4/8"
+    B = args.batch * world if args.scaling == "weak" else args.batch
     first, count = shard_range(B, rank, world)
     # ---- inputs: generated on the host (exactly the reference-side generator), pinned for the e2e arm
     t0 = time.perf_counter()
@@ -402,8 +409,9 @@ def main():
     line = {
         "metric": METRIC, "value": B * args.steps / t_dev, "unit": "LPs/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "batch of 8192 synthetic dense LPs m=256 n=512 (BASELINE.json configs[4])",
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "batch of 8192 synthetic dense LPs m=256 n=512 (BASELINE.json configs[4])"
+                               + (" on every GPU, LP seeds 0..%d" % (B - 1) if world > 1 and args.scaling == "weak" else ""),
                    "batch": B, "m": M_LP, "n": N_LP, "tol": TOL, "partition": "static block, %d LPs per GPU" % count,
                    "l2": "inputs per GPU (%.2f GB) exceed L2, no flush" % (count * M_LP * N_LP * 8 / 1e9),
                    "newton_iterations_per_step": int(it_all.sum()), "lockstep_iterations": int(it_all.max())},
