@@ -12,6 +12,7 @@
 #include "dmma_gemm.cuh"
 #include "dmma_ws.cuh"
 #include "sparse.cuh"
+#include "trsv_pipe.cuh"
 #include "vec.cuh"
 
 namespace ipm {
@@ -20,6 +21,8 @@ thread_local std::string g_last_error;
 }  // namespace ipm
 
 using namespace ipm;
+
+constexpr int PIPE_MIN_M = 256;      // above this order the triangular solves run as pipelined persistent kernels
 
 struct ipm_handle {
     int dev = 0;
@@ -45,6 +48,7 @@ struct ipm_handle {
     double *b, *c, *x, *y, *s, *rb, *rc, *d, *w, *rcx, *dxa, *dya, *dsa, *dx, *dy, *ds, *tm, *tn, *rhs, *tmp_m;
     double* M = nullptr;
     int64_t ldm = 0;
+    TrsvPipeWs pipe;              // m > PIPE_MIN_M: inverses of the diagonal blocks + flags of the pipelined solves
     double* scal = nullptr;
     double* partials = nullptr;
     unsigned* counter = nullptr;
@@ -89,7 +93,8 @@ void free_problem(ipm_handle* h) {
     cudaSetDevice(h->dev);
     if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
     void* ptrs[] = {h->rowptr, h->colind, h->t_rowptr, h->t_colind, h->val, h->t_val, h->ad, h->out_idx,
-                    h->prod_ptr, h->pa, h->pb, h->A_own, h->gemv_partial, h->slab, h->M};
+                    h->prod_ptr, h->pa, h->pb, h->A_own, h->gemv_partial, h->slab, h->M, h->pipe.Linv, h->pipe.flags};
+    h->pipe = TrsvPipeWs();
     for (void* p : ptrs)
         if (p) cudaFree(p);
     h->rowptr = h->colind = h->t_rowptr = h->t_colind = nullptr;
@@ -115,7 +120,18 @@ int alloc_common(ipm_handle* h, int m, int n) {
     h->rcx = take(pn); h->dxa = take(pn); h->dsa = take(pn); h->dx = take(pn); h->ds = take(pn); h->tn = take(pn);
     h->ldm = pm;
     H_CUDA(cudaMalloc(&h->M, (size_t)m * h->ldm * sizeof(double)));
+    if (m > PIPE_MIN_M) {
+        h->pipe.nblk = ceil_div(m, TP_NB);
+        H_CUDA(cudaMalloc(&h->pipe.Linv, (size_t)h->pipe.nblk * TP_NB * TP_NB * sizeof(double)));
+        H_CUDA(cudaMalloc(&h->pipe.flags, (size_t)2 * h->pipe.nblk * sizeof(int)));
+    }
     return IPM_OK;
+}
+
+// triangular solves with the current factor: pipelined persistent kernels for large m, one CTA otherwise
+int solve_factored(ipm_handle* h, double* rhs, double* sol) {
+    if (h->pipe.Linv) return potrs_pipe(h->M, h->ldm, h->m, h->pipe, rhs, h->tmp_m, sol, h->st);
+    return potrs_single(h->M, h->ldm, h->m, rhs, h->tmp_m, sol, h->st);
 }
 
 int finish_load(ipm_handle* h) {
@@ -198,6 +214,7 @@ int assemble_step(ipm_handle* h) {
 
 int factor_step(ipm_handle* h, double tau) {
     H_TRY((potrf_single_auto(h->M, h->ldm, h->m, h->scal, tau, h->st)));
+    if (h->pipe.Linv) H_TRY(trinv_blocks(h->M, h->ldm, h->m, h->pipe, h->st));
     h->have_factor = true;
     h->have_M = false;
     return IPM_OK;
@@ -213,7 +230,7 @@ int direction_step(ipm_handle* h, int kind) {
     H_TRY(matvec_A(h, h->w, h->tm));
     k_make_rhs<<<vec_grid(h->m), VEC_NT, 0, h->st>>>(h->rb, h->tm, h->rhs, h->m);
     count_launch();
-    H_TRY(potrs_single(h->M, h->ldm, h->m, h->rhs, h->tmp_m, dyo, h->st));
+    H_TRY(solve_factored(h, h->rhs, dyo));
     H_TRY(matvec_AT(h, dyo, h->tn));
     k_direction<<<vec_grid(h->n), VEC_NT, 0, h->st>>>(kind, h->tn, h->d, h->w, h->rcx, h->x, h->s, dxo, dso, h->n,
                                                       h->eta, h->scal, h->partials, h->counter);
@@ -443,11 +460,11 @@ int ipm_start_mehrotra(ipm_handle* h) {
     H_TRY(factor_step(h, h->tau));
     // x = A^T (A A^T)^-1 b
     H_CUDA(cudaMemcpyAsync(h->rhs, h->b, (size_t)m * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
-    H_TRY(potrs_single(h->M, h->ldm, m, h->rhs, h->tmp_m, h->dy, h->st));
+    H_TRY(solve_factored(h, h->rhs, h->dy));
     H_TRY(matvec_AT(h, h->dy, h->x));
     // y = (A A^T)^-1 A c,  s = c - A^T y
     H_TRY(matvec_A(h, h->c, h->rhs));
-    H_TRY(potrs_single(h->M, h->ldm, m, h->rhs, h->tmp_m, h->y, h->st));
+    H_TRY(solve_factored(h, h->rhs, h->y));
     H_TRY(matvec_AT(h, h->y, h->tn));
     k_sub<<<vec_grid(n), VEC_NT, 0, h->st>>>(h->c, h->tn, h->s, n);
     k_mehrotra_shift<<<1, 1024, 0, h->st>>>(h->x, h->s, n);
