@@ -249,6 +249,22 @@ template <int NB, int ROWS>
 constexpr size_t chol_trsm_smem() { return (size_t)(NB * (NB + 2) + NB * ROWS) * sizeof(double); }
 
 // ------------------------------------------------------------------------------------------------
+// side stream of the look-ahead (one per device, created on first use)
+struct CholSide {
+    cudaStream_t st = nullptr;
+    cudaEvent_t strip_done = nullptr, rest_done = nullptr;
+    int ensure() {
+        if (st) return IPM_OK;
+        IPM_CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        IPM_CUDA_OK(cudaEventCreateWithFlags(&strip_done, cudaEventDisableTiming));
+        IPM_CUDA_OK(cudaEventCreateWithFlags(&rest_done, cudaEventDisableTiming));
+        return IPM_OK;
+    }
+};
+static CholSide g_chol_side[16];
+static bool g_chol_lookahead = true;
+
+// ------------------------------------------------------------------------------------------------
 // Host driver: in-place factorisation of `batch` matrices of order m.
 template <int NB, int NT_DIAG, int ROWS>
 inline int potrf_blocked(double* M, int64_t ldm, int64_t strideM, int m, int batch, double* scal,
@@ -269,6 +285,21 @@ inline int potrf_blocked(double* M, int64_t ldm, int64_t strideM, int m, int bat
     CholArgs a;
     a.M = M; a.ldm = ldm; a.strideM = strideM; a.scal = scal; a.strideScal = strideScal; a.tau = tau;
     a.m = m; a.active = active;
+    // Look-ahead (one large matrix, 128-wide panels): the trailing update of panel j is split into the tile column
+    // the next panel lives in ("strip", a few microseconds) and the rest, which runs on a side stream on all SMs
+    // but one while the main stream already factors the next diagonal block (one CTA, latency-bound, about as
+    // long as the rest of the update).  Same operations on the same entries in the same order: bitwise identical.
+    DmmaArgs probe;
+    probe.P = M; probe.Q = M; probe.C = M; probe.ldp = probe.ldq = probe.ldc = ldm;
+    probe.strideP = probe.strideQ = probe.strideC = 0; probe.dvec = nullptr; probe.strideD = 0;
+    probe.lower_only = 1; probe.rowsP = probe.rowsQ = m;
+    const bool lookahead = (batch == 1) && (NB == WS_BM) && (m >= 8 * NB) && ws_eligible(probe) && g_chol_lookahead;
+    CholSide* side = nullptr;
+    if (lookahead) {
+        side = &g_chol_side[dev < 16 ? dev : 0];
+        IPM_TRY(side->ensure());
+    }
+    bool rest_pending = false;
     for (int j0 = 0; j0 < m; j0 += NB) {
         a.j0 = j0;
         a.nb = (m - j0 < NB) ? (m - j0) : NB;
@@ -285,9 +316,33 @@ inline int potrf_blocked(double* M, int64_t ldm, int64_t strideM, int m, int bat
             g.dvec = nullptr; g.strideD = 0;
             g.C = M + (size_t)(j0 + NB) * ldm + (j0 + NB); g.ldc = ldm; g.strideC = strideM;
             g.rowsP = below; g.rowsQ = below; g.K = NB; g.lower_only = 1; g.active = active;
-            IPM_TRY((dmma_syrk_auto<1>(g, batch, st)));
+            if (!lookahead) {
+                IPM_TRY((dmma_syrk_auto<1>(g, batch, st)));
+                continue;
+            }
+            // strip: tile column 0 of the update, after the rest of the previous panel has left those entries
+            if (rest_pending) IPM_CUDA_OK(cudaStreamWaitEvent(st, side->rest_done, 0));
+            g.col0_only = 1;
+            IPM_TRY((dmma_ws_launch<1, false>(g, 1, st)));
+            IPM_CUDA_OK(cudaEventRecord(side->strip_done, st));
+            // rest: the same update one tile further down and right, on the side stream, one SM left free
+            if (below > NB) {
+                DmmaArgs r = g;
+                r.col0_only = 0;
+                r.P = panel + (size_t)NB * ldm; r.Q = r.P;
+                r.C = g.C + (size_t)NB * ldm + NB;
+                r.rowsP = r.rowsQ = below - NB;
+                r.max_ctas = kNumSMs - 1;
+                IPM_CUDA_OK(cudaStreamWaitEvent(side->st, side->strip_done, 0));
+                IPM_TRY((dmma_ws_launch<1, false>(r, 1, side->st)));
+                IPM_CUDA_OK(cudaEventRecord(side->rest_done, side->st));
+                rest_pending = true;
+            } else {
+                rest_pending = false;
+            }
         }
     }
+    if (rest_pending) IPM_CUDA_OK(cudaStreamWaitEvent(st, side->rest_done, 0));
     return launch_check();
 }
 

@@ -23,6 +23,9 @@ struct DmmaArgs {
     int rowsP, rowsQ, K;
     int lower_only;        // skip tiles strictly above the block diagonal (square tiles, P/Q share row space)
     const int* active;     // nullable: per-batch flag, 0 => skip this LP
+    int col0_only = 0;     // warp-specialised kernel only: compute just the first tile column (tiles (bi, 0)) - the
+                           // part of a Cholesky trailing update the next panel needs (look-ahead, chol.cuh)
+    int max_ctas = 0;      // warp-specialised kernel only: cap of the persistent grid (0 = one CTA per SM)
 };
 
 constexpr int DMMA_BK = 16;

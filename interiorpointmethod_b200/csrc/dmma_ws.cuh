@@ -163,7 +163,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dmma_ws_kernel(const DmmaArgs a
             const int z = tile / ntri;
             if (a.active && a.active[z] == 0) continue;
             int bi, bj;
-            tri_decode(tile - z * ntri, bi, bj);
+            if (a.col0_only) { bi = tile - z * ntri; bj = 0; }
+            else tri_decode(tile - z * ntri, bi, bj);
             const double* base = isQ ? a.Q + (size_t)z * a.strideQ : a.P + (size_t)z * a.strideP;
             const int64_t ld = isQ ? a.ldq : a.ldp;
             const int nrows = isQ ? a.rowsQ : a.rowsP;
@@ -206,7 +207,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dmma_ws_kernel(const DmmaArgs a
             const int z = tile / ntri;
             if (a.active && a.active[z] == 0) continue;
             int bi, bj;
-            tri_decode(tile - z * ntri, bi, bj);
+            if (a.col0_only) { bi = tile - z * ntri; bj = 0; }
+            else tri_decode(tile - z * ntri, bi, bj);
             if (bi == bj) {
                 const int r0d = bi * WS_BM;
                 switch (warp) {
@@ -307,10 +309,11 @@ inline int dmma_ws_launch(const DmmaArgs& a, int batch, cudaStream_t st) {
     }
     if (a.rowsP <= 0 || batch <= 0 || a.K <= 0) return IPM_OK;
     const int T = ceil_div(a.rowsP, WS_BM);
-    const int ntri = T * (T + 1) / 2;
+    const int ntri = a.col0_only ? T : T * (T + 1) / 2;      // tiles per matrix
     const int64_t total = (int64_t)ntri * batch;
     if (total > 0x7fffffff) return IPM_ERR_SHAPE;
-    const int grid = (int)std::min<int64_t>(total, kNumSMs);
+    const int cap = (a.max_ctas > 0 && a.max_ctas < kNumSMs) ? a.max_ctas : kNumSMs;
+    const int grid = (int)std::min<int64_t>(total, cap);
     kern<<<grid, WS_THREADS, ws_smem_bytes(), st>>>(a, ntri, (int)total);
     count_launch();
     return launch_check();
