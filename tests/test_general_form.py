@@ -19,8 +19,9 @@ NAMES = sorted(META)
 # typo: 904.29998619 for 904.29695380) and STANDGUB is listed as "(see NOTES)".
 OPT = {k: v["highs_optimum"] for k, v in META.items()}
 TABLE_DISAGREES = {"BNL1", "FINNIS", "FORPLAN", "GANGES", "SCAGR7", "SCRS8", "STANDGUB"}
-# degenerate LP on which the normal equations stall at rb = 3e-6 (objective correct to 1e-9): same mechanism as
-# QAP15
+# degenerate LP on which the normal equations can stall at rb = 3e-6 with the objective correct to 1e-9 (same
+# mechanism as QAP15): it did with the per-block substitution solves and converges with the
+# inverse-block pipelined ones
 STALLS_AT_OPTIMUM = {"DEGEN3"}
 
 
@@ -135,7 +136,7 @@ def test_new_interior_sparse_reaches_netlib_optimum_on_gpu(built_library, name):
     c, Aineq, bineq, Aeq, beq, lb, ub = gf.load_golden_general(name)
     res = gf.new_interior_sparse(c, Aeq=Aeq, beq=beq, Aineq=Aineq, bineq=bineq, lb=lb, ub=ub, tol=1e-8)
     if name in STALLS_AT_OPTIMUM:
-        assert res.status == "max_iter"
+        assert res.status in ("max_iter", "converged")      # depends on the rounding of the triangular solves
     else:
         assert res.status == "converged", (name, res.status, res.iterations)
     assert abs(res.objective - OPT[name]) <= 1e-6 * max(1.0, abs(OPT[name])), (res.objective, OPT[name])
