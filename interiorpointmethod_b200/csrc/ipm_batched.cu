@@ -199,9 +199,9 @@ __global__ void __launch_bounds__(KB_NT, (NPL <= 8) ? 2 : 1) kb_residual(const B
 }
 
 // |b|, |c| per LP (once per solve) and state initialisation x = s = 1, y = 0 (main.py:287-302)
-__global__ void __launch_bounds__(256) kb_init(const BatchArgs a, int flag) {
+__global__ void __launch_bounds__(256) kb_init(const BatchArgs a, int flag, int lp0) {
     __shared__ double sh[32];
-    const int lp = blockIdx.x, tid = threadIdx.x;
+    const int lp = lp0 + blockIdx.x, tid = threadIdx.x;
     const int m = a.m, n = a.n;
     double nb = 0.0, nc = 0.0;
     for (int i = tid; i < m; i += blockDim.x) {
@@ -428,6 +428,17 @@ void carve(Workspace& w, void* base, int B, int m, int n) {
     w.a.m = m; w.a.n = n;
 }
 
+// Host-buffer entry point: the batch arrives in chunks on a copy stream while the lockstep loop is already
+// running; a chunk's LPs join the loop (kb_init, strip-major copy) at the first iteration after its copy has
+// landed.  Every LP keeps its own iteration counter, so joining late changes nothing for it.
+struct Arrival {
+    int nchunks = 0;
+    const int* first = nullptr;
+    const int* count = nullptr;
+    cudaEvent_t* landed = nullptr;      // recorded on the copy stream behind chunk k
+    int next = 0;                       // first chunk that has not joined yet
+};
+
 void launch_kbf_dir(int kind, const BatchArgs& a, int B, int m, cudaStream_t st) {
     const size_t sm = kf_smem_bytes(m, a.n);
     switch (kf_nrp(m) * 2 + kind) {
@@ -443,7 +454,7 @@ void launch_kbf_dir(int kind, const BatchArgs& a, int B, int m, cudaStream_t st)
 }
 
 template <int NPL>
-int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, int* iterations_run) {
+int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, int* iterations_run, Arrival* arr) {
     BatchArgs& a = w.a;
     const size_t smem_col = (size_t)KB_NW * n * sizeof(double);
     const size_t smem_res = smem_col + (size_t)n * sizeof(double);
@@ -474,11 +485,33 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
                                          (int)trsv_batched_inv_smem(32 * TRSVI_MAX_BLK)));
         configured_dev = dev;
     }
-    kb_init<<<B, 256, 0, st>>>(a, fused ? 2 : 1);
-    if (fused) {
-        const int nstrips = ceil_div(n, KF_W);
-        kbf_repack<<<dim3(nstrips, B), 256, 0, st>>>(a, 32 * kf_nrp(m), nstrips);
+    auto join = [&](int lp0, int cnt) {             // LPs lp0 .. lp0+cnt-1 enter the loop
+        kb_init<<<cnt, 256, 0, st>>>(a, fused ? 2 : 1, lp0);
         count_launch();
+        if (fused) {
+            const int nstrips = ceil_div(n, KF_W);
+            kbf_repack<<<dim3(nstrips, cnt), 256, 0, st>>>(a, 32 * kf_nrp(m), nstrips, lp0);
+            count_launch();
+        }
+    };
+    auto join_landed = [&](bool block_for_one) -> int {
+        // chunks whose copy has completed (cudaEventQuery: the loop never waits for data it can do without)
+        while (arr->next < arr->nchunks) {
+            cudaError_t q = block_for_one ? cudaEventSynchronize(arr->landed[arr->next]) : cudaEventQuery(arr->landed[arr->next]);
+            if (q == cudaErrorNotReady) { (void)cudaGetLastError(); break; }     // not an error: clear it
+            IPM_CUDA_OK(q);
+            IPM_CUDA_OK(cudaStreamWaitEvent(st, arr->landed[arr->next], 0));
+            join(arr->first[arr->next], arr->count[arr->next]);
+            ++arr->next;
+            block_for_one = false;
+        }
+        return IPM_OK;
+    };
+    if (arr) {
+        IPM_CUDA_OK(cudaMemsetAsync(a.active, 0, (size_t)B * sizeof(int), st));
+        IPM_TRY(join_landed(true));
+    } else {
+        join(0, B);
     }
     count_launch();
     // The host reads the "LPs still active" counter of check k only after check k+1 has been enqueued, so the
@@ -490,8 +523,18 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
     IPM_CUDA_OK(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
     struct EvGuard { cudaEvent_t* e; ~EvGuard() { cudaEventDestroy(e[0]); cudaEventDestroy(e[1]); } } ev_guard{ev};
     int it = 0, bodies = 0;
+    bool all_joined[2] = {true, true};          // per check slot: had every chunk joined when the check was enqueued?
+    bool joined_pending = false;                // a chunk joined after the last check was enqueued
     for (;; ++it) {
         const int slot = it & 1;
+        if (arr && it > 0) {
+            const int before = arr->next;
+            IPM_TRY(join_landed(false));
+            if (arr->next != before) joined_pending = true;
+        }
+        const bool counted_join = joined_pending;       // those LPs pass through this iteration's check first
+        joined_pending = false;
+        all_joined[slot] = !arr || arr->next == arr->nchunks;
         a.n_active = nact_base + slot * 16;
         IPM_CUDA_OK(cudaMemsetAsync(a.n_active, 0, sizeof(unsigned), st));
         g_prof.segment(st);
@@ -504,7 +547,16 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
         if (it > 0) {
             IPM_CUDA_OK(cudaEventSynchronize(ev[slot ^ 1]));
             const unsigned cnt = w.h_nact[slot ^ 1];
-            if (cnt == 0) break;
+            if (cnt == 0) {
+                if (all_joined[slot ^ 1]) break;
+                if (!counted_join) {
+                    // nothing is active until the next chunk lands (only when the copies are slower than the
+                    // solves): wait for it, let it join, and send it through the next check before any body runs
+                    if (arr->next < arr->nchunks) IPM_TRY(join_landed(true));
+                    joined_pending = true;
+                    continue;
+                }
+            }
             ++bodies;
             if (g_prof.enabled) g_prof.lp_iterations += cnt;
         }
@@ -540,7 +592,7 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
 
 int solve_on_device(int B, int m, int n, const double* A_d, const double* b_d, const double* c_d, double tol,
                     int max_iter, double* obj_d, int* iters_d, int* status_d, double* x_d, void* work_d,
-                    unsigned* h_nact, cudaStream_t st, int* iterations_run) {
+                    unsigned* h_nact, cudaStream_t st, int* iterations_run, Arrival* arr = nullptr) {
     Workspace w;
     carve(w, work_d, B, m, n);
     w.h_nact = h_nact;
@@ -548,8 +600,8 @@ int solve_on_device(int B, int m, int n, const double* A_d, const double* b_d, c
     w.a.tol = tol; w.a.eta = 0.91; w.a.max_iter = max_iter;
     w.a.fresh_every = g_fresh_every;
     const double tau = 1e-30;
-    if (n <= 512) IPM_TRY(run_batched<8>(w, B, m, n, tau, st, iterations_run));
-    else IPM_TRY(run_batched<16>(w, B, m, n, tau, st, iterations_run));
+    if (n <= 512) IPM_TRY(run_batched<8>(w, B, m, n, tau, st, iterations_run, arr));
+    else IPM_TRY(run_batched<16>(w, B, m, n, tau, st, iterations_run, arr));
     kb_finalize<<<ceil_div(B, 256), 256, 0, st>>>(w.a, B, obj_d, iters_d, status_d);
     count_launch();
     if (x_d) IPM_CUDA_OK(cudaMemcpyAsync(x_d, w.a.x, (size_t)B * n * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -675,8 +727,8 @@ int ipm_solve_batched_dense_d(int device_ordinal, int B, int m, int n, const dou
 struct HostPathCtx {
     int dev = -1;
     cudaStream_t s_copy = nullptr, s_comp = nullptr;
-    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
-    double *dA[2] = {nullptr, nullptr}, *db[2] = {nullptr, nullptr}, *dc[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> landed;                 // one per chunk: its H2D copy has completed
+    double *dA = nullptr, *db = nullptr, *dc = nullptr;
     double *d_obj = nullptr, *d_x = nullptr;
     int *d_it = nullptr, *d_st = nullptr;
     void* work = nullptr;
@@ -685,18 +737,11 @@ struct HostPathCtx {
     void release() {
         if (dev < 0) return;
         cudaSetDevice(dev);
-        for (int i = 0; i < 2; ++i) {
-            if (dA[i]) cudaFree(dA[i]);
-            if (db[i]) cudaFree(db[i]);
-            if (dc[i]) cudaFree(dc[i]);
-            if (ev_in[i]) cudaEventDestroy(ev_in[i]);
-            if (ev_free[i]) cudaEventDestroy(ev_free[i]);
-        }
-        if (d_obj) cudaFree(d_obj);
-        if (d_it) cudaFree(d_it);
-        if (d_st) cudaFree(d_st);
-        if (d_x) cudaFree(d_x);
-        if (work) cudaFree(work);
+        for (cudaEvent_t e : landed) cudaEventDestroy(e);
+        landed.clear();
+        void* ptrs[] = {dA, db, dc, d_obj, d_it, d_st, d_x, work};
+        for (void* p : ptrs)
+            if (p) cudaFree(p);
         if (h_nact) cudaFreeHost(h_nact);
         if (s_copy) cudaStreamDestroy(s_copy);
         if (s_comp) cudaStreamDestroy(s_comp);
@@ -725,89 +770,67 @@ int ipm_solve_batched_dense(int device_ordinal, int B, int m, int n, const doubl
     IPM_TRY(check_shape(B, m, n));
     if (device_ordinal < 0 || device_ordinal >= 16) return IPM_ERR_ARG;
     IPM_CUDA_OK(cudaSetDevice(device_ordinal));
-    // Chunk schedule: a small first chunk (its H2D copy is the only one nothing can hide), then chunks growing
-    // by 3x up to a quarter of the batch; the copy of chunk k+1 runs on the copy stream while chunk k is solved.
+    // The whole batch gets device buffers; it is copied in chunks on a copy stream (a small first chunk: its copy
+    // is the only one nothing can hide) and ONE lockstep loop runs from the moment the first chunk has landed:
+    // the LPs of a chunk join the loop at the first iteration after their copy has completed (Arrival).  Solving
+    // chunk after chunk instead paid the latency-bound last iterations of a lockstep solve once per chunk.
     std::vector<int> first_of, count_of;
     {
-        const int cap = std::max(512, ceil_div(B, 4));       // small chunks leave SMs idle (one CTA per LP)
-        int next = std::max(512, B / 16), at = 0;
+        int next = std::min(B, 256), at = 0;
         while (at < B) {
-            const int cnt = std::min(std::min(next, cap), B - at);
+            const int cnt = std::min(next, B - at);
             first_of.push_back(at);
             count_of.push_back(cnt);
             at += cnt;
-            next = std::min(cap, next * 3);
+            next = 1024;
         }
     }
     const int nchunks = (int)first_of.size();
-    int chunk = 0;
-    for (int v : count_of) chunk = std::max(chunk, v);
     HostPathCtx& C = g_host_ctx[device_ordinal];
     int rc = [&]() -> int {
         if (C.dev < 0) {
             C.dev = device_ordinal;
             IPM_CUDA_OK(cudaStreamCreateWithFlags(&C.s_copy, cudaStreamNonBlocking));
             IPM_CUDA_OK(cudaStreamCreateWithFlags(&C.s_comp, cudaStreamNonBlocking));
-            for (int i = 0; i < 2; ++i) {
-                IPM_CUDA_OK(cudaEventCreateWithFlags(&C.ev_in[i], cudaEventDisableTiming));
-                IPM_CUDA_OK(cudaEventCreateWithFlags(&C.ev_free[i], cudaEventDisableTiming));
-            }
             IPM_CUDA_OK(cudaMallocHost(&C.h_nact, 2 * sizeof(unsigned)));
         }
-        {   // (re)size the cached buffers; capacities are tracked for buffer 0 and applied to both
-            const int64_t nA = (int64_t)chunk * m * n * 8, nb = (int64_t)chunk * m * 8, nc = (int64_t)chunk * n * 8;
-            int64_t capA1 = C.capA, capb1 = C.capb, capc1 = C.capc;
-            IPM_TRY(ensure_bytes((void**)&C.dA[0], &C.capA, nA));
-            IPM_TRY(ensure_bytes((void**)&C.db[0], &C.capb, nb));
-            IPM_TRY(ensure_bytes((void**)&C.dc[0], &C.capc, nc));
-            if (nchunks > 1 || C.dA[1]) {
-                if (!C.dA[1]) { capA1 = capb1 = capc1 = 0; }
-                IPM_TRY(ensure_bytes((void**)&C.dA[1], &capA1, std::max(nA, C.capA)));
-                IPM_TRY(ensure_bytes((void**)&C.db[1], &capb1, std::max(nb, C.capb)));
-                IPM_TRY(ensure_bytes((void**)&C.dc[1], &capc1, std::max(nc, C.capc)));
-            }
-            const int64_t nres = (int64_t)chunk * 8;
-            if (C.capres < nres) {
-                if (C.d_obj) cudaFree(C.d_obj);
-                if (C.d_it) cudaFree(C.d_it);
-                if (C.d_st) cudaFree(C.d_st);
-                C.d_obj = nullptr; C.d_it = C.d_st = nullptr;
-                IPM_CUDA_OK(cudaMalloc(&C.d_obj, (size_t)nres));
-                IPM_CUDA_OK(cudaMalloc(&C.d_it, (size_t)chunk * sizeof(int)));
-                IPM_CUDA_OK(cudaMalloc(&C.d_st, (size_t)chunk * sizeof(int)));
-                C.capres = nres;
-            }
-            if (x) IPM_TRY(ensure_bytes((void**)&C.d_x, &C.capx, (int64_t)chunk * n * 8));
-            IPM_TRY(ensure_bytes(&C.work, &C.capwork, ws_bytes(chunk, m, n)));
+        while ((int)C.landed.size() < nchunks) {
+            cudaEvent_t e = nullptr;
+            IPM_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            C.landed.push_back(e);
         }
-        auto stage = [&](int k) -> int {
-            const int buf = k & 1, first = first_of[k], cnt = count_of[k];
-            if (k >= 2) IPM_CUDA_OK(cudaStreamWaitEvent(C.s_copy, C.ev_free[buf], 0));
-            IPM_CUDA_OK(cudaMemcpyAsync(C.dA[buf], A + (size_t)first * m * n, (size_t)cnt * m * n * 8,
-                                        cudaMemcpyHostToDevice, C.s_copy));
-            IPM_CUDA_OK(cudaMemcpyAsync(C.db[buf], b + (size_t)first * m, (size_t)cnt * m * 8, cudaMemcpyHostToDevice,
-                                        C.s_copy));
-            IPM_CUDA_OK(cudaMemcpyAsync(C.dc[buf], c + (size_t)first * n, (size_t)cnt * n * 8, cudaMemcpyHostToDevice,
-                                        C.s_copy));
-            IPM_CUDA_OK(cudaEventRecord(C.ev_in[buf], C.s_copy));
-            return IPM_OK;
-        };
-        IPM_TRY(stage(0));
+        IPM_TRY(ensure_bytes((void**)&C.dA, &C.capA, (int64_t)B * m * n * 8));
+        IPM_TRY(ensure_bytes((void**)&C.db, &C.capb, (int64_t)B * m * 8));
+        IPM_TRY(ensure_bytes((void**)&C.dc, &C.capc, (int64_t)B * n * 8));
+        if (C.capres < (int64_t)B * 8) {
+            if (C.d_obj) cudaFree(C.d_obj);
+            if (C.d_it) cudaFree(C.d_it);
+            if (C.d_st) cudaFree(C.d_st);
+            C.d_obj = nullptr; C.d_it = C.d_st = nullptr; C.capres = 0;
+            IPM_CUDA_OK(cudaMalloc(&C.d_obj, (size_t)B * 8));
+            IPM_CUDA_OK(cudaMalloc(&C.d_it, (size_t)B * sizeof(int)));
+            IPM_CUDA_OK(cudaMalloc(&C.d_st, (size_t)B * sizeof(int)));
+            C.capres = (int64_t)B * 8;
+        }
+        if (x) IPM_TRY(ensure_bytes((void**)&C.d_x, &C.capx, (int64_t)B * n * 8));
+        IPM_TRY(ensure_bytes(&C.work, &C.capwork, ws_bytes(B, m, n)));
+        // the previous call's solve has drained (the call synchronises before returning): the buffers are free
         for (int k = 0; k < nchunks; ++k) {
-            const int buf = k & 1, first = first_of[k], cnt = count_of[k];
-            if (k + 1 < nchunks) IPM_TRY(stage(k + 1));
-            IPM_CUDA_OK(cudaStreamWaitEvent(C.s_comp, C.ev_in[buf], 0));
-            IPM_TRY(solve_on_device(cnt, m, n, C.dA[buf], C.db[buf], C.dc[buf], tol, max_iter, C.d_obj, C.d_it, C.d_st,
-                                    x ? C.d_x : nullptr, C.work, C.h_nact, C.s_comp, nullptr));
-            IPM_CUDA_OK(cudaEventRecord(C.ev_free[buf], C.s_comp));
-            if (obj) IPM_CUDA_OK(cudaMemcpyAsync(obj + first, C.d_obj, (size_t)cnt * 8, cudaMemcpyDeviceToHost, C.s_comp));
-            if (iters) IPM_CUDA_OK(cudaMemcpyAsync(iters + first, C.d_it, (size_t)cnt * sizeof(int),
-                                                   cudaMemcpyDeviceToHost, C.s_comp));
-            if (status) IPM_CUDA_OK(cudaMemcpyAsync(status + first, C.d_st, (size_t)cnt * sizeof(int),
-                                                    cudaMemcpyDeviceToHost, C.s_comp));
-            if (x) IPM_CUDA_OK(cudaMemcpyAsync(x + (size_t)first * n, C.d_x, (size_t)cnt * n * 8,
-                                               cudaMemcpyDeviceToHost, C.s_comp));
+            const size_t first = (size_t)first_of[k], cnt = (size_t)count_of[k];
+            IPM_CUDA_OK(cudaMemcpyAsync(C.dA + first * m * n, A + first * m * n, cnt * m * n * 8, cudaMemcpyHostToDevice,
+                                        C.s_copy));
+            IPM_CUDA_OK(cudaMemcpyAsync(C.db + first * m, b + first * m, cnt * m * 8, cudaMemcpyHostToDevice, C.s_copy));
+            IPM_CUDA_OK(cudaMemcpyAsync(C.dc + first * n, c + first * n, cnt * n * 8, cudaMemcpyHostToDevice, C.s_copy));
+            IPM_CUDA_OK(cudaEventRecord(C.landed[k], C.s_copy));
         }
+        Arrival arr;
+        arr.nchunks = nchunks; arr.first = first_of.data(); arr.count = count_of.data(); arr.landed = C.landed.data();
+        IPM_TRY(solve_on_device(B, m, n, C.dA, C.db, C.dc, tol, max_iter, C.d_obj, C.d_it, C.d_st, x ? C.d_x : nullptr,
+                                C.work, C.h_nact, C.s_comp, nullptr, &arr));
+        if (obj) IPM_CUDA_OK(cudaMemcpyAsync(obj, C.d_obj, (size_t)B * 8, cudaMemcpyDeviceToHost, C.s_comp));
+        if (iters) IPM_CUDA_OK(cudaMemcpyAsync(iters, C.d_it, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, C.s_comp));
+        if (status) IPM_CUDA_OK(cudaMemcpyAsync(status, C.d_st, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, C.s_comp));
+        if (x) IPM_CUDA_OK(cudaMemcpyAsync(x, C.d_x, (size_t)B * n * 8, cudaMemcpyDeviceToHost, C.s_comp));
         IPM_CUDA_OK(cudaStreamSynchronize(C.s_comp));
         IPM_CUDA_OK(cudaStreamSynchronize(C.s_copy));
         return IPM_OK;

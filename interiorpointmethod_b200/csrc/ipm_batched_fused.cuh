@@ -309,8 +309,8 @@ __global__ void __launch_bounds__(KF_NTT, 1) kbf_dir(const BatchArgs a) {
 // Strip-major copy of A for kbf_dir: At[lp][s][r][c] = A[lp][r][16 s + c], rows padded to mr = 32 nrp and columns to
 // a multiple of 16 with zeros, so that a column strip is ONE contiguous block (DRAM pages are read whole and a
 // strip is a single bulk copy).  One CTA per (strip, LP), one thread per row; runs once per solve.
-__global__ void __launch_bounds__(256) kbf_repack(const BatchArgs a, int mr, int nstrips) {
-    const int s = blockIdx.x, lp = blockIdx.y;
+__global__ void __launch_bounds__(256) kbf_repack(const BatchArgs a, int mr, int nstrips, int lp0) {
+    const int s = blockIdx.x, lp = lp0 + blockIdx.y;
     const int m = a.m, n = a.n;
     const double* A = a.A + (size_t)lp * m * n;
     double* dst = a.At + ((size_t)lp * nstrips + s) * mr * KF_W;
