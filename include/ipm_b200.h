@@ -61,11 +61,39 @@ int ipm_set_pivot_threshold(ipm_handle *h, double pivot_rel_thresh);
 
 /* ---------------------------------------------------------------- problem data
  * Replaces what create_problem_from_mps hands to the drivers (sparse_interior.py:211-216):
- * A (scipy CSC there; CSR here — the Python shim converts), b (m), c (n).
- * The symbolic pattern of M = A A^T is built once here. */
+ * A (scipy CSC there; ipm_load_csc takes it as it is, ipm_load_csr takes the row-compressed form), b (m), c (n). */
 int ipm_load_csr(ipm_handle *h, int m, int n, int64_t nnz,
                  const int32_t *rowptr, const int32_t *colind, const double *val,
                  const double *b, const double *c);
+/* The same problem handed over in the orientation the reference's loader holds it in: `create_problem_from_mps`
+ * returns the scipy csc_matrix that loadmat read from benchmarks/<name>.mat (sparse_interior.py:139-167, 211-216):
+ * colptr (n+1), rowind (nnz, strictly ascending inside a column), val (nnz).  No host-side conversion is needed.
+ *
+ * Both loaders do all structure-dependent work ON THE DEVICE: the other orientation by a
+ * stable transposition, and the symbolic pattern of the lower triangle of M = A diag(d) A^T (entry list + term
+ * lists ordered by the shared column index, the summation order of scipy's csr_matmat for main.py:224).  The
+ * result is cached per (device, orientation, m, n, structure arrays) in a process-wide LRU cache: loading the same
+ * structure again - the same LP, or new values / right-hand sides on the same pattern - only uploads val, b, c. */
+int ipm_load_csc(ipm_handle *h, int m, int n, int64_t nnz,
+                 const int32_t *colptr, const int32_t *rowind, const double *val,
+                 const double *b, const double *c);
+/* host_symbolic != 0: build the SpGEMM pattern with the host routine instead (cross-check of the device pass; it
+ * is also what orders m beyond the 224 KB shared-memory marker, m > 57344, fall back to).  use_cache == 0: bypass
+ * the pattern cache.  Process-wide; default (0, 1). */
+int ipm_set_ingest_mode(int host_symbolic, int use_cache);
+/* out = { entries of tril(M), terms (scalar products) of the numeric SpGEMM, 1 if the last load hit the cache,
+ *         1 if the pattern was built on the device, build time of the pattern in us, time of the last load in us } */
+int ipm_pattern_info(ipm_handle *h, int64_t out[6]);
+/* Debug/parity: copies of the device-resident structure (any pointer may be NULL): CSR of A (m+1, nnz), CSR of
+ * A^T = CSC of A (n+1, nnz), and the pattern (out_idx[nent] = i*ldm + j with ldm = 16*ceil(m/16),
+ * prod_ptr[nent+1], pa/pb[nterms] = positions in the CSR value array of the two factors of every term). */
+int ipm_get_pattern(ipm_handle *h, int32_t *rowptr, int32_t *colind, int32_t *t_rowptr, int32_t *t_colind,
+                    int64_t *out_idx, int64_t *prod_ptr, int32_t *pa, int32_t *pb);
+/* Debug/parity: the value arrays in CSR order and in CSC order as the device holds them. */
+int ipm_get_values(ipm_handle *h, double *val_csr, double *val_csc);
+/* out = { cached structures, hits, misses, device bytes held by the cache } */
+int ipm_pattern_cache_stats(int64_t out[4]);
+int ipm_pattern_cache_clear(void);
 /* Dense A, row-major with leading dimension lda >= n (the `interior` caller, main.py:707-757). */
 int ipm_load_dense(ipm_handle *h, int m, int n, const double *A, int64_t lda,
                    const double *b, const double *c);

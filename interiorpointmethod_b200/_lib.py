@@ -25,6 +25,14 @@ SYMBOLS = {
     "ipm_launch_count": (c_int64, []),
     "ipm_set_pivot_threshold": (c_int, [c_void_p, c_double]),
     "ipm_load_csr": (c_int, [c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ipm_load_csc": (c_int, [c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ipm_set_ingest_mode": (c_int, [c_int, c_int]),
+    "ipm_pattern_info": (c_int, [c_void_p, c_void_p]),
+    "ipm_get_pattern": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p]),
+    "ipm_get_values": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "ipm_pattern_cache_stats": (c_int, [c_void_p]),
+    "ipm_pattern_cache_clear": (c_int, []),
     "ipm_load_dense": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
     "ipm_load_dense_d": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
     "ipm_init_state": (c_int, [c_void_p, c_int]),

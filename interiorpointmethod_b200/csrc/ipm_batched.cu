@@ -760,6 +760,7 @@ static int ensure_bytes(void** p, int64_t* cap, int64_t need) {
 
 int ipm_release_cached(void) {
     for (auto& c : g_host_ctx) c.release();
+    ipm_pattern_cache_clear();
     return IPM_OK;
 }
 

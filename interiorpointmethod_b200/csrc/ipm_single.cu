@@ -1,5 +1,7 @@
 // C ABI (include/ipm_b200.h), single-LP part: handle, problem upload, op-level entry points that mirror the
 // reference's Python seams (main.py:162-322, 562-697) and the device-resident predictor-corrector loop.
+#include <chrono>
+#include <climits>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -11,6 +13,7 @@
 #include "dense.cuh"
 #include "dmma_gemm.cuh"
 #include "dmma_ws.cuh"
+#include "ingest.cuh"
 #include "sparse.cuh"
 #include "trsv_pipe.cuh"
 #include "vec.cuh"
@@ -31,7 +34,12 @@ struct ipm_handle {
     bool loaded = false, dense = false;
     // sparse A (CSR) and A^T (CSR)
     int64_t nnz = 0;
+    // structure (both orientations + SpGEMM pattern): owned by `pat`, shared through the pattern cache (ingest.cuh)
+    std::shared_ptr<DevPattern> pat;
+    bool pat_hit = false;
+    double load_ms = 0.0;
     int32_t *rowptr = nullptr, *colind = nullptr, *t_rowptr = nullptr, *t_colind = nullptr;
+    double* vslab = nullptr;      // val | t_val | ad
     double *val = nullptr, *t_val = nullptr, *ad = nullptr;
     // SpGEMM pattern
     int64_t nent = 0;
@@ -92,11 +100,12 @@ int cuda_fail(ipm_handle* h) {
 void free_problem(ipm_handle* h) {
     cudaSetDevice(h->dev);
     if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
-    void* ptrs[] = {h->rowptr, h->colind, h->t_rowptr, h->t_colind, h->val, h->t_val, h->ad, h->out_idx,
-                    h->prod_ptr, h->pa, h->pb, h->A_own, h->gemv_partial, h->slab, h->M, h->pipe.Linv, h->pipe.flags};
+    void* ptrs[] = {h->vslab, h->A_own, h->gemv_partial, h->slab, h->M, h->pipe.Linv, h->pipe.flags};
     h->pipe = TrsvPipeWs();
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    h->pat.reset();               // the structure arrays live on in the cache (or die with the last user)
+    h->vslab = nullptr;
     h->rowptr = h->colind = h->t_rowptr = h->t_colind = nullptr;
     h->val = h->t_val = h->ad = nullptr;
     h->out_idx = h->prod_ptr = nullptr;
@@ -335,69 +344,123 @@ int ipm_set_pivot_threshold(ipm_handle* h, double pivot_rel_thresh) {
     return IPM_OK;
 }
 
-int ipm_load_csr(ipm_handle* h, int m, int n, int64_t nnz, const int32_t* rowptr, const int32_t* colind,
-                 const double* val, const double* b, const double* c) {
+// Sparse A in either compressed orientation (from_csc: ptr = column pointers, idx = row indices).  Structure work
+// (other orientation, symbolic SpGEMM) happens on the device and is cached per structure (ingest.cuh).
+static int load_sparse(ipm_handle* h, int m, int n, int64_t nnz, const int32_t* ptr, const int32_t* idx,
+                       const double* val, const double* b, const double* c, bool from_csc) {
+    const auto t_begin = std::chrono::steady_clock::now();
     H_TRY(check_handle(h, false));
-    if (!rowptr || !colind || !val || !b || !c) return fail(h, IPM_ERR_ARG, "null pointer");
-    if (m <= 0 || n <= 0 || nnz < 0 || rowptr[0] != 0 || rowptr[m] != nnz)
-        return fail(h, IPM_ERR_SHAPE, "bad CSR header");
-    for (int i = 0; i < m; ++i) {
-        if (rowptr[i + 1] < rowptr[i]) return fail(h, IPM_ERR_SHAPE, "rowptr not monotone");
-        for (int64_t p = rowptr[i]; p < rowptr[i + 1]; ++p) {
-            if (colind[p] < 0 || colind[p] >= n) return fail(h, IPM_ERR_SHAPE, "column index out of range");
-            if (p > rowptr[i] && colind[p] <= colind[p - 1])
-                return fail(h, IPM_ERR_SHAPE, "column indices must be strictly ascending inside a row");
+    if (!ptr || !idx || !val || !b || !c) return fail(h, IPM_ERR_ARG, "null pointer");
+    const int nseg = from_csc ? n : m, nother = from_csc ? m : n;
+    if (m <= 0 || n <= 0 || nnz < 0 || nnz > INT32_MAX || ptr[0] != 0 || ptr[nseg] != nnz)
+        return fail(h, IPM_ERR_SHAPE, "bad compressed-sparse header");
+    for (int i = 0; i < nseg; ++i) {
+        if (ptr[i + 1] < ptr[i]) return fail(h, IPM_ERR_SHAPE, "pointer array not monotone");
+        for (int64_t p = ptr[i]; p < ptr[i + 1]; ++p) {
+            if (idx[p] < 0 || idx[p] >= nother) return fail(h, IPM_ERR_SHAPE, "index out of range");
+            if (p > ptr[i] && idx[p] <= idx[p - 1])
+                return fail(h, IPM_ERR_SHAPE, "indices must be strictly ascending inside a row/column");
         }
     }
     free_problem(h);
     h->dense = false;
     h->nnz = nnz;
     H_TRY(alloc_common(h, m, n));
-    // transpose (CSR of A^T) on the host
-    std::vector<int32_t> tp(n + 1, 0), tc(nnz);
-    std::vector<double> tv(nnz);
-    for (int64_t p = 0; p < nnz; ++p) tp[colind[p] + 1]++;
-    for (int k = 0; k < n; ++k) tp[k + 1] += tp[k];
     {
-        std::vector<int32_t> fill(tp.begin(), tp.end() - 1);
-        for (int i = 0; i < m; ++i)
-            for (int64_t p = rowptr[i]; p < rowptr[i + 1]; ++p) {
-                const int32_t q = fill[colind[p]]++;
-                tc[q] = i;
-                tv[q] = val[p];
-            }
+        int r = acquire_pattern(h->dev, m, n, nnz, h->ldm, from_csc, ptr, idx, h->st, h->pat, h->pat_hit);
+        if (r == IPM_ERR_CUDA) return cuda_fail(h);
+        if (r != IPM_OK) return r;
     }
-    SpgemmPattern pat;
-    spgemm_symbolic(m, n, rowptr, colind, h->ldm, pat);
-    h->nent = (int64_t)pat.out_idx.size();
-    const size_t nz = (size_t)std::max<int64_t>(nnz, 1), np = std::max<size_t>(pat.pa.size(), 1);
-    H_CUDA(cudaMalloc(&h->rowptr, (m + 1) * sizeof(int32_t)));
-    H_CUDA(cudaMalloc(&h->colind, nz * sizeof(int32_t)));
-    H_CUDA(cudaMalloc(&h->val, nz * sizeof(double)));
-    H_CUDA(cudaMalloc(&h->ad, nz * sizeof(double)));
-    H_CUDA(cudaMalloc(&h->t_rowptr, (n + 1) * sizeof(int32_t)));
-    H_CUDA(cudaMalloc(&h->t_colind, nz * sizeof(int32_t)));
-    H_CUDA(cudaMalloc(&h->t_val, nz * sizeof(double)));
-    H_CUDA(cudaMalloc(&h->out_idx, std::max<size_t>(pat.out_idx.size(), 1) * sizeof(int64_t)));
-    H_CUDA(cudaMalloc(&h->prod_ptr, pat.prod_ptr.size() * sizeof(int64_t)));
-    H_CUDA(cudaMalloc(&h->pa, np * sizeof(int32_t)));
-    H_CUDA(cudaMalloc(&h->pb, np * sizeof(int32_t)));
-    H_CUDA(cudaMemcpyAsync(h->rowptr, rowptr, (m + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, h->st));
-    H_CUDA(cudaMemcpyAsync(h->colind, colind, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, h->st));
-    H_CUDA(cudaMemcpyAsync(h->val, val, nnz * sizeof(double), cudaMemcpyHostToDevice, h->st));
-    H_CUDA(cudaMemcpyAsync(h->t_rowptr, tp.data(), (n + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, h->st));
-    H_CUDA(cudaMemcpyAsync(h->t_colind, tc.data(), nnz * sizeof(int32_t), cudaMemcpyHostToDevice, h->st));
-    H_CUDA(cudaMemcpyAsync(h->t_val, tv.data(), nnz * sizeof(double), cudaMemcpyHostToDevice, h->st));
-    H_CUDA(cudaMemcpyAsync(h->out_idx, pat.out_idx.data(), pat.out_idx.size() * sizeof(int64_t),
-                           cudaMemcpyHostToDevice, h->st));
-    H_CUDA(cudaMemcpyAsync(h->prod_ptr, pat.prod_ptr.data(), pat.prod_ptr.size() * sizeof(int64_t),
-                           cudaMemcpyHostToDevice, h->st));
-    H_CUDA(cudaMemcpyAsync(h->pa, pat.pa.data(), pat.pa.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->st));
-    H_CUDA(cudaMemcpyAsync(h->pb, pat.pb.data(), pat.pb.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->st));
+    const DevPattern& P = *h->pat;
+    h->rowptr = P.rowptr; h->colind = P.colind; h->t_rowptr = P.t_rowptr; h->t_colind = P.t_colind;
+    h->out_idx = P.out_idx; h->prod_ptr = P.prod_ptr; h->pa = P.pa; h->pb = P.pb;
+    h->nent = P.nent;
+    const size_t nz = (size_t)round_up(std::max<int64_t>(nnz, 1), 2);
+    H_CUDA(cudaMalloc(&h->vslab, 3 * nz * sizeof(double)));
+    h->val = h->vslab; h->t_val = h->val + nz; h->ad = h->t_val + nz;
+    double* given = from_csc ? h->t_val : h->val;       // A in CSC order = A^T in CSR order
+    double* derived = from_csc ? h->val : h->t_val;
+    H_CUDA(cudaMemcpyAsync(given, val, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    k_ing_gather<<<std::max(1, std::min<int>(ceil_div(nnz, 256), 8 * kNumSMs)), 256, 0, h->st>>>(nnz, given, P.perm,
+                                                                                                 derived);
+    count_launch();
     H_CUDA(cudaMemcpyAsync(h->b, b, m * sizeof(double), cudaMemcpyHostToDevice, h->st));
     H_CUDA(cudaMemcpyAsync(h->c, c, n * sizeof(double), cudaMemcpyHostToDevice, h->st));
-    H_CUDA(cudaStreamSynchronize(h->st));     // host staging vectors go out of scope
-    return finish_load(h);
+    H_TRY(finish_load(h));
+    h->load_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    return IPM_OK;
+}
+
+int ipm_load_csr(ipm_handle* h, int m, int n, int64_t nnz, const int32_t* rowptr, const int32_t* colind,
+                 const double* val, const double* b, const double* c) {
+    if (!h) return IPM_ERR_ARG;
+    return load_sparse(h, m, n, nnz, rowptr, colind, val, b, c, false);
+}
+
+int ipm_load_csc(ipm_handle* h, int m, int n, int64_t nnz, const int32_t* colptr, const int32_t* rowind,
+                 const double* val, const double* b, const double* c) {
+    if (!h) return IPM_ERR_ARG;
+    return load_sparse(h, m, n, nnz, colptr, rowind, val, b, c, true);
+}
+
+int ipm_set_ingest_mode(int host_symbolic, int use_cache) {
+    ingest_mode().store((host_symbolic ? 1 : 0) | (use_cache ? 0 : 2));
+    return IPM_OK;
+}
+
+int ipm_pattern_info(ipm_handle* h, int64_t out[6]) {
+    H_TRY(check_handle(h));
+    if (!out) return fail(h, IPM_ERR_ARG, "null pointer");
+    if (h->dense || !h->pat) return fail(h, IPM_ERR_STATE, "no sparse problem loaded");
+    out[0] = h->pat->nent; out[1] = h->pat->nterms; out[2] = h->pat_hit ? 1 : 0;
+    out[3] = h->pat->device_built ? 1 : 0;
+    out[4] = (int64_t)(h->pat->build_ms * 1e3); out[5] = (int64_t)(h->load_ms * 1e3);
+    return IPM_OK;
+}
+
+int ipm_get_pattern(ipm_handle* h, int32_t* rowptr, int32_t* colind, int32_t* t_rowptr, int32_t* t_colind,
+                    int64_t* out_idx, int64_t* prod_ptr, int32_t* pa, int32_t* pb) {
+    H_TRY(check_handle(h));
+    if (h->dense || !h->pat) return fail(h, IPM_ERR_STATE, "no sparse problem loaded");
+    const DevPattern& P = *h->pat;
+    auto get = [&](void* dst, const void* src, size_t bytes) -> int {
+        if (dst && bytes) IPM_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->st));
+        return IPM_OK;
+    };
+    H_TRY(get(rowptr, P.rowptr, (size_t)(P.m + 1) * sizeof(int32_t)));
+    H_TRY(get(colind, P.colind, (size_t)P.nnz * sizeof(int32_t)));
+    H_TRY(get(t_rowptr, P.t_rowptr, (size_t)(P.n + 1) * sizeof(int32_t)));
+    H_TRY(get(t_colind, P.t_colind, (size_t)P.nnz * sizeof(int32_t)));
+    H_TRY(get(out_idx, P.out_idx, (size_t)P.nent * sizeof(int64_t)));
+    H_TRY(get(prod_ptr, P.prod_ptr, (size_t)(P.nent + 1) * sizeof(int64_t)));
+    H_TRY(get(pa, P.pa, (size_t)P.nterms * sizeof(int32_t)));
+    H_TRY(get(pb, P.pb, (size_t)P.nterms * sizeof(int32_t)));
+    H_CUDA(cudaStreamSynchronize(h->st));
+    return IPM_OK;
+}
+
+int ipm_get_values(ipm_handle* h, double* val_csr, double* val_csc) {
+    H_TRY(check_handle(h));
+    if (h->dense || !h->pat) return fail(h, IPM_ERR_STATE, "no sparse problem loaded");
+    if (val_csr) H_CUDA(cudaMemcpyAsync(val_csr, h->val, (size_t)h->nnz * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    if (val_csc) H_CUDA(cudaMemcpyAsync(val_csc, h->t_val, (size_t)h->nnz * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    H_CUDA(cudaStreamSynchronize(h->st));
+    return IPM_OK;
+}
+
+int ipm_pattern_cache_stats(int64_t out[4]) {
+    if (!out) return IPM_ERR_ARG;
+    PatternCache& C = pattern_cache();
+    std::lock_guard<std::mutex> g(C.mu);
+    size_t bytes = 0;
+    for (auto& p : C.items) bytes += p->bytes;
+    out[0] = (int64_t)C.items.size(); out[1] = C.hits; out[2] = C.misses; out[3] = (int64_t)bytes;
+    return IPM_OK;
+}
+
+int ipm_pattern_cache_clear(void) {
+    pattern_cache_clear();
+    return IPM_OK;
 }
 
 static int load_dense_common(ipm_handle* h, int m, int n) {

@@ -94,17 +94,23 @@ class NewtonStep:
     # ------------------------------------------------------------------ data
     def load(self, A, b, c):
         if _sp is not None and _sp.issparse(A):
-            Ar = _sp.csr_matrix(A, dtype=np.float64)
+            # create_problem_from_mps hands over the csc_matrix loadmat produced (sparse_interior.py:211-216): it goes
+            # to the device as it is (ipm_load_csc); any other sparse format goes row-compressed (ipm_load_csr).
+            # The other orientation and the SpGEMM pattern are built on the GPU and cached per structure.
+            csc = A.format == "csc"
+            Ar = A.astype(np.float64) if csc else _sp.csr_matrix(A, dtype=np.float64)   # both copy
             Ar.sum_duplicates()
             Ar.sort_indices()
             self.m, self.n = Ar.shape
             bb, cc = _f64(b, self.m), _f64(c, self.n)
-            rowptr = np.ascontiguousarray(Ar.indptr, dtype=np.int32)
-            colind = np.ascontiguousarray(Ar.indices, dtype=np.int32)
+            ptr = np.ascontiguousarray(Ar.indptr, dtype=np.int32)
+            idx = np.ascontiguousarray(Ar.indices, dtype=np.int32)
             val = np.ascontiguousarray(Ar.data, dtype=np.float64)
-            self._check(self._lib.ipm_load_csr(self._h, self.m, self.n, int(Ar.nnz), _ptr(rowptr), _ptr(colind),
-                                               _ptr(val), _ptr(bb), _ptr(cc)), "ipm_load_csr")
+            fn = self._lib.ipm_load_csc if csc else self._lib.ipm_load_csr
+            self._check(fn(self._h, self.m, self.n, int(Ar.nnz), _ptr(ptr), _ptr(idx), _ptr(val), _ptr(bb), _ptr(cc)),
+                        "ipm_load_csc" if csc else "ipm_load_csr")
             self.sparse = True
+            self.nnz = int(Ar.nnz)
         else:
             Ad = np.ascontiguousarray(np.asarray(A, dtype=np.float64))
             if Ad.ndim != 2:
@@ -114,6 +120,28 @@ class NewtonStep:
             self._check(self._lib.ipm_load_dense(self._h, self.m, self.n, _ptr(Ad), self.n, _ptr(bb), _ptr(cc)),
                         "ipm_load_dense")
             self.sparse = False
+
+    def pattern_info(self):
+        """Ingestion record of the loaded sparse problem (ipm_pattern_info)."""
+        out = np.zeros(6, dtype=np.int64)
+        self._check(self._lib.ipm_pattern_info(self._h, _ptr(out)), "ipm_pattern_info")
+        return dict(entries=int(out[0]), terms=int(out[1]), cache_hit=bool(out[2]), device_built=bool(out[3]),
+                    build_ms=out[4] / 1e3, load_ms=out[5] / 1e3)
+
+    def pattern(self):
+        """Copies of the device-resident structure (ipm_get_pattern, ipm_get_values): parity tests."""
+        info = self.pattern_info()
+        nnz, ne, nt = self.nnz, info["entries"], info["terms"]
+        out = dict(rowptr=np.empty(self.m + 1, np.int32), colind=np.empty(nnz, np.int32),
+                   t_rowptr=np.empty(self.n + 1, np.int32), t_colind=np.empty(nnz, np.int32),
+                   out_idx=np.empty(ne, np.int64), prod_ptr=np.empty(ne + 1, np.int64),
+                   pa=np.empty(nt, np.int32), pb=np.empty(nt, np.int32))
+        self._check(self._lib.ipm_get_pattern(self._h, *[_ptr(out[k]) for k in (
+            "rowptr", "colind", "t_rowptr", "t_colind", "out_idx", "prod_ptr", "pa", "pb")]), "ipm_get_pattern")
+        out["val"] = np.empty(nnz)
+        out["t_val"] = np.empty(nnz)
+        self._check(self._lib.ipm_get_values(self._h, _ptr(out["val"]), _ptr(out["t_val"])), "ipm_get_values")
+        return out
 
     def set_pivot_threshold(self, tau: float):
         self._check(self._lib.ipm_set_pivot_threshold(self._h, float(tau)), "ipm_set_pivot_threshold")
