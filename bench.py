@@ -109,51 +109,62 @@ def run_reference_arm(args):
 
 # ----------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons of this rank's GPU DURING the timed region, sampled in-process through NVML
+    (pynvml) every 250 ms by a thread.  An `nvidia-smi -lms` child was used before: on the 8-GPU box its polling
+    serialised against the kernel launches of all eight ranks (weak-scaling step 1.9 s instead of 0.37 s,
+    profiles/r1_bench_n8_weak_nvidia_smi_sampler.json); NVML calls on one open handle do not."""
+    PERIOD_S = 0.25
 
     def __init__(self, gpu_index):
-        self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
-        self.proc = None
+        import threading
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
-                 "-lms", "200"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            h = None
+            try:
+                uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self._nv, self._h = pynvml, h
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
         except Exception:
-            self.proc = None
-        self.t_start = time.time()
+            self._thread = None
+
+    def _run(self):
+        nv, h = self._nv, self._h
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                for bit, nm in names.items():
+                    if mask & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(self.PERIOD_S)
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0, "source": "nvml"}
+        if self._thread is None:
             return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        try:
-            for ln in open(self.path):
-                f = [t.strip() for t in ln.split(",")]
-                if len(f) < 9:
-                    continue
-                try:
-                    sm.append(float(f[1])); mx.append(float(f[2]))
-                except ValueError:
-                    continue
-                for nm, val in zip(names, f[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(nm)
-            os.unlink(self.path)
-        except Exception:
-            pass
+        self._stop.set()
+        self._thread.join(timeout=2)
+        sm = list(self.samples)
         if sm:
             hi = sorted(sm)[len(sm) // 2:]          # the upper half = samples under load
             out.update(sm_mhz=float(np.median(sm)), sm_mhz_under_load=float(np.median(hi)),
-                       sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+                       reasons=sorted(self.reasons), samples=len(sm))
         return out
 
 
@@ -317,8 +328,13 @@ def main():
         barrier()
         wall = time.perf_counter() - w0
         t = torch.tensor([e0.elapsed_time(e1) * 1e-3, wall], dtype=torch.float64, device=dev)
+        per_rank = [float(t[0])]
         if world > 1:
+            every = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(every, t)
+            per_rank = [float(v[0]) for v in every]
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        timed.per_rank_ms = [v * 1e3 / steps for v in per_rank]
         return float(t[0]), float(t[1]), out
 
     # ---- device-resident arm
@@ -329,6 +345,7 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = lib.ipm_launch_count()
     t_dev, wall_dev, out = timed(step_device, args.steps)
+    per_rank_dev = list(timed.per_rank_ms)
     launches = lib.ipm_launch_count() - launches0
     clocks = sampler.stop() if sampler else None
     ms = (ctypes.c_double * 4)()
@@ -417,6 +434,7 @@ def main():
                    "newton_iterations_per_step": int(it_all.sum()), "lockstep_iterations": int(it_all.max())},
         "newton_it_per_s": float(it_all.sum()) * args.steps / t_dev,
         "wall_ms_per_step": wall_dev / args.steps * 1e3,
+        "per_rank_ms_per_step": [round(v, 2) for v in per_rank_dev],
         "converged": n_conv, "iterations_min_max": [int(it_all.min()), int(it_all.max())],
         "e2e": {"value": B * args.steps / t_e2e, "unit": "LPs/s",
                 "h2d_bytes_per_step": int(B) * (M_LP * N_LP + M_LP + N_LP) * 8,

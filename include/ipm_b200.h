@@ -202,6 +202,14 @@ int64_t ipm_batched_workspace_bytes(int B, int m, int n);
  * three_pass = 0: six passes, every residual from scratch in every iteration, exactly as main.py:725-751 orders it.
  * Process-wide; for A/B measurements and parity tests. */
 int ipm_batched_set_variant(int three_pass, int refresh_every);
+/* Straggler restart of the four-pass iteration.  The four-pass and the literal iteration round differently, and in
+ * the ill-conditioned last iterations that can decide whether an LP converges or is trapped at the boundary with
+ * step lengths near zero (benchmark LP 16893: 3527 iterations four-pass, 17 six-pass, 18 in the CPU port of the
+ * reference), and one trapped LP keeps the whole lockstep loop alive.  Once half of the batch has finished (lockstep
+ * iteration h), an LP gets max(slack, h/2) more iterations; what is still running then restarts from the starting
+ * point (main.py:287-302) under the literal six-pass iteration, and its iteration count is that of the restarted
+ * run.  slack = 0 switches the restart off; default 8.  Process-wide. */
+int ipm_batched_set_straggler_restart(int slack);
 
 /* Phase timing of the batched solver (bench.py roofline): CUDA events on the solve stream around the four
  * phases of every lockstep iteration.  ms/calls index: 0 residual pass, 1 SYRK (dmma_nt_kernel, one launch

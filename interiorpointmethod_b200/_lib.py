@@ -61,6 +61,7 @@ SYMBOLS = {
     "ipm_release_cached": (c_int, []),
     "ipm_batched_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
     "ipm_batched_set_variant": (c_int, [c_int, c_int]),
+    "ipm_batched_set_straggler_restart": (c_int, [c_int]),
     "ipm_profile_enable": (c_int, [c_int]),
     "ipm_profile_read": (c_int, [c_void_p, c_void_p, POINTER(c_int64)]),
     "ipm_profile_last": (c_int, [c_void_p, c_void_p, c_int]),

@@ -91,6 +91,7 @@ struct Profiler {
 Profiler g_prof;
 
 int g_fresh_every = 3;         // residuals from scratch every 3rd iteration (see ipm_batched_set_variant)
+int g_restart_slack = 8;       // straggler restart (see ipm_batched_set_straggler_restart); 0 = off
 bool g_allow_fused = true;      // ipm_batched_set_variant(): 0 forces the 6-pass iteration (tests, A/B timing)
 
 // ---------------------------------------------------------------------------------------------
@@ -223,6 +224,30 @@ __global__ void __launch_bounds__(256) kb_init(const BatchArgs a, int flag, int 
         scal[S_NB] = sqrt(nb);
         scal[S_NC] = sqrt(nc);
         a.active[lp] = flag;
+        a.iters[lp] = 0;
+    }
+}
+
+// Straggler restart: every LP that is still iterating after min_iters iterations goes back to the starting point
+// x = s = 1, y = 0 (main.py:287-302) with its iteration count reset; the caller continues with the literal
+// six-pass iteration.  |b|, |c| are kept.
+__global__ void __launch_bounds__(256) kb_restart(const BatchArgs a, int min_iters) {
+    const int lp = blockIdx.x, tid = threadIdx.x;
+    if (a.active[lp] == 0 || a.iters[lp] < min_iters) return;
+    const int m = a.m, n = a.n;
+    for (int i = tid; i < m; i += blockDim.x) a.y[(size_t)lp * m + i] = 0.0;
+    for (int i = tid; i < n; i += blockDim.x) {
+        a.x[(size_t)lp * n + i] = 1.0;
+        a.s[(size_t)lp * n + i] = 1.0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double* scal = a.scal + (size_t)lp * S_COUNT;
+        const double nb = scal[S_NB], nc = scal[S_NC];
+        for (int i = 0; i < S_COUNT; ++i) scal[i] = 0.0;
+        scal[S_NB] = nb;
+        scal[S_NC] = nc;
+        a.active[lp] = 1;
         a.iters[lp] = 0;
     }
 }
@@ -466,7 +491,8 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
     g.C = w.M; g.ldc = w.ldm; g.strideC = (int64_t)m * w.ldm;
     g.rowsP = m; g.rowsQ = m; g.K = n; g.lower_only = 1; g.active = a.active;
     // 3-pass iteration (ipm_batched_fused.cuh) when one CTA can hold a column strip of A_i
-    const bool fused = g_allow_fused && m <= KF_MAX_M && (n % 2 == 0) && ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0);
+    // (not const: a straggler restart switches the rest of the solve to the literal six-pass iteration)
+    bool fused = g_allow_fused && m <= KF_MAX_M && (n % 2 == 0) && ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0);
     static int configured_dev = -1;
     int dev = 0;
     IPM_CUDA_OK(cudaGetDevice(&dev));
@@ -523,6 +549,14 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
     IPM_CUDA_OK(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
     struct EvGuard { cudaEvent_t* e; ~EvGuard() { cudaEventDestroy(e[0]); cudaEventDestroy(e[1]); } } ev_guard{ev};
     int it = 0, bodies = 0;
+    // Straggler restart.  The four-pass iteration and the literal one round differently, and in the ill-conditioned
+    // last iterations of the normal equations that can decide whether an LP converges or gets trapped at the
+    // boundary with step lengths near zero (benchmark LP 16893: 3527 iterations four-pass, 17 six-pass, 18 in the
+    // CPU oracle; all others of 65536 within +-1).  One trapped LP keeps the whole lockstep loop alive at launch
+    // latency.  So: once half of the batch has finished (lockstep iteration it_half) an LP gets
+    // max(slack, it_half/2) more iterations; whatever is still running then is restarted from the starting point
+    // under the literal six-pass iteration (= the reference's own order of operations, main.py:725-751).
+    int it_half = -1, restart_at = -1;
     bool all_joined[2] = {true, true};          // per check slot: had every chunk joined when the check was enqueued?
     bool joined_pending = false;                // a chunk joined after the last check was enqueued
     for (;; ++it) {
@@ -531,6 +565,11 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
             const int before = arr->next;
             IPM_TRY(join_landed(false));
             if (arr->next != before) joined_pending = true;
+        }
+        if (fused && restart_at > 0 && it >= restart_at) {
+            kb_restart<<<B, 256, 0, st>>>(a, it_half);
+            count_launch();
+            fused = false;
         }
         const bool counted_join = joined_pending;       // those LPs pass through this iteration's check first
         joined_pending = false;
@@ -559,6 +598,10 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
             }
             ++bodies;
             if (g_prof.enabled) g_prof.lp_iterations += cnt;
+            if (fused && g_restart_slack > 0 && it_half < 0 && all_joined[slot ^ 1] && 2 * (int64_t)cnt <= B) {
+                it_half = it;
+                restart_at = it_half + std::max(g_restart_slack, it_half / 2);
+            }
         }
         g_prof.segment(st);
         IPM_TRY((dmma_syrk_auto<0>(g, B, st)));
@@ -625,6 +668,12 @@ int ipm_batched_set_variant(int three_pass, int refresh_every) {
     if (refresh_every < 0) return IPM_ERR_ARG;
     g_allow_fused = three_pass != 0;
     g_fresh_every = refresh_every;
+    return IPM_OK;
+}
+
+int ipm_batched_set_straggler_restart(int slack) {
+    if (slack < 0) return IPM_ERR_ARG;
+    g_restart_slack = slack;
     return IPM_OK;
 }
 
