@@ -110,10 +110,10 @@ def run_reference_arm(args):
 # ----------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
     """SM clock / throttle reasons of this rank's GPU DURING the timed region, sampled in-process through NVML
-    (pynvml) every 250 ms by a thread.  An `nvidia-smi -lms` child was used before: on the 8-GPU box its polling
+    (pynvml) every 100 ms by a thread.  An `nvidia-smi -lms` child was used before: on the 8-GPU box its polling
     serialised against the kernel launches of all eight ranks (weak-scaling step 1.9 s instead of 0.37 s,
     profiles/r1_bench_n8_weak_nvidia_smi_sampler.json); NVML calls on one open handle do not."""
-    PERIOD_S = 0.25
+    PERIOD_S = 0.1
 
     def __init__(self, gpu_index):
         import threading
