@@ -556,7 +556,7 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
     // latency.  So: once half of the batch has finished (lockstep iteration it_half) an LP gets
     // max(slack, it_half/2) more iterations; whatever is still running then is restarted from the starting point
     // under the literal six-pass iteration (= the reference's own order of operations, main.py:725-751).
-    int it_half = -1, restart_at = -1;
+    int it_half = -1, restart_at = -1, it_last_join = 0;
     bool all_joined[2] = {true, true};          // per check slot: had every chunk joined when the check was enqueued?
     bool joined_pending = false;                // a chunk joined after the last check was enqueued
     for (;; ++it) {
@@ -564,7 +564,7 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
         if (arr && it > 0) {
             const int before = arr->next;
             IPM_TRY(join_landed(false));
-            if (arr->next != before) joined_pending = true;
+            if (arr->next != before) { joined_pending = true; it_last_join = it; }
         }
         if (fused && restart_at > 0 && it >= restart_at) {
             kb_restart<<<B, 256, 0, st>>>(a, it_half);
@@ -593,6 +593,7 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
                     // solves): wait for it, let it join, and send it through the next check before any body runs
                     if (arr->next < arr->nchunks) IPM_TRY(join_landed(true));
                     joined_pending = true;
+                    it_last_join = it;
                     continue;
                 }
             }
@@ -600,7 +601,10 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
             if (g_prof.enabled) g_prof.lp_iterations += cnt;
             if (fused && g_restart_slack > 0 && it_half < 0 && all_joined[slot ^ 1] && 2 * (int64_t)cnt <= B) {
                 it_half = it;
-                restart_at = it_half + std::max(g_restart_slack, it_half / 2);
+                // LPs of a chunk that joined at lockstep iteration j are only due around j + (their own count):
+                // it_half (an over-estimate of that count when the joins were staggered) + slack after the last join
+                restart_at = std::max(it_half + std::max(g_restart_slack, it_half / 2),
+                                      it_last_join + it_half + g_restart_slack);
             }
         }
         g_prof.segment(st);
