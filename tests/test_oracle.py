@@ -160,3 +160,28 @@ def test_mehrotra_start_oracle_reaches_netlib_optima():
     r = orc.solve(A, b, c, cTlb=cTlb, tol=1e-8, start="mehrotra", max_iter=200)
     assert r["status"] == 0 and r["k"] <= 40
     assert abs(r["obj"] - 5.5018458883e03) <= 1e-8 * 5.5018458883e03
+
+
+@pytest.mark.parametrize("seed", [0, 7466, 16893])
+def test_fourpass_identities_against_literal_iteration(seed):
+    """The two identities behind the batched solver's four-pass iteration (tests/fourpass_emulation.py), checked
+    on the CPU against the literal iteration: LP 0, LP 7466 (the one that needed the periodic refresh on the GPU)
+    and LP 16893 (the straggler of the weak-scaling workload)."""
+    from oracle import ipm_oracle as orc
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("fourpass_emulation", os.path.join(os.path.dirname(__file__), "fourpass_emulation.py"))
+    emu = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(emu)
+    solve_fourpass = emu.solve_fourpass
+    A, b, c = orc.synthetic_dense_lp(256, 512, seed)
+    lit = orc.solve(A, b, c, tol=1e-8, max_iter=50000, y0_is_one=False, linear="normal")
+    k, x, y, s, hist = solve_fourpass(A, b, c, tol=1e-8, refresh_every=3)
+    assert lit["status"] == 0 and abs(k - lit["k"]) <= 1
+    obj = float((c.reshape(1, -1) @ x)[0, 0])
+    assert abs(obj - lit["obj"]) <= 1e-8 * abs(lit["obj"])
+    floor = 1e-8 * (1 + np.linalg.norm(b))
+    for (_, rb_rec, rb_true, rc_rec, rc_true, lin_err) in hist:
+        assert abs(rb_rec - rb_true) <= 1e-3 * max(rb_true, floor)      # the recurrences track the true residuals
+        assert abs(rc_rec - rc_true) <= 1e-3 * max(rc_true, floor)
+        assert lin_err <= 1e-9                                          # linearity of main.py:150-152 in r4
