@@ -401,6 +401,92 @@ __global__ void __launch_bounds__(KB_NT) kb_dir(const BatchArgs a, int kind) {
     }
 }
 
+// Iterative refinement of the corrector (restarted LPs only, see run_batched).  With dy from the factored normal
+// equations the primal equation A dx = -rb of the Newton system (third block row of main.py:13-21) holds only as
+// well as the Cholesky factor of M = A D A^T allows; in the last iterations (d_max/d_min > 1e19) that is not well
+// enough for |rb| to keep falling, and an LP that has not met check_optimality by then can stay trapped.  One
+// refinement step:  dx = d (A^T dy) + w,  delta = -rb - A dx  (this kernel, two sweeps over A_i: column sums, then
+// row dots), M ddy = delta (the batched triangular solves on the same factor), dy += ddy (kb_add_refinement); the
+// corrector kernel kb_dir then forms dx, ds from the refined dy as before (both are linear in dy).
+template <int NPL>
+__global__ void __launch_bounds__(KB_NT) kb_refine_rhs(const BatchArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    double* colred = smem;                               // [KB_NW][n]
+    const int lp = blockIdx.x;
+    if (a.active[lp] == 0) return;
+    const int m = a.m, n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* dxs = smem + (size_t)KB_NW * n;              // [n]
+    const double* A = a.A + (size_t)lp * m * n;
+    const size_t on = (size_t)lp * n, om = (size_t)lp * m;
+    const double* dy = a.rhs + om;                       // the triangular solve worked in place
+    const int n2 = n >> 1;
+    double2 ca[NPL];
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) ca[j] = make_double2(0.0, 0.0);
+    for (int r = warp; r < m; r += KB_NW) {
+        const double2* row = reinterpret_cast<const double2*>(A + (size_t)r * n);
+        const double yr = dy[r];
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+            const int c2 = j * 32 + lane;
+            if (c2 < n2) {
+                const double2 v = row[c2];
+                ca[j].x += v.x * yr;
+                ca[j].y += v.y * yr;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+        const int c2 = j * 32 + lane;
+        if (c2 < n2) reinterpret_cast<double2*>(colred + (size_t)warp * n)[c2] = ca[j];
+    }
+    __syncthreads();
+    for (int k = tid; k < n; k += KB_NT) {
+        double u = 0.0;
+#pragma unroll
+        for (int w = 0; w < KB_NW; ++w) u += colred[(size_t)w * n + k];
+        dxs[k] = a.d[on + k] * u + a.w[on + k];
+    }
+    __syncthreads();
+    double2 wr[NPL];
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+        const int c2 = j * 32 + lane;
+        wr[j] = (c2 < n2) ? reinterpret_cast<const double2*>(dxs)[c2] : make_double2(0.0, 0.0);
+    }
+    for (int r = warp; r < m; r += KB_NW) {
+        const double2* row = reinterpret_cast<const double2*>(A + (size_t)r * n);
+        double dot0 = 0.0, dot1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+            const int c2 = j * 32 + lane;
+            if (c2 < n2) {
+                const double2 v = row[c2];
+                dot0 += v.x * wr[j].x;
+                dot1 += v.y * wr[j].y;
+            }
+        }
+        const double dot = warp_sum(dot0 + dot1);
+        if (lane == 0) a.dy[om + r] = -a.rb[om + r] - dot;
+    }
+}
+
+__global__ void __launch_bounds__(256) kb_add_refinement(const BatchArgs a) {
+    const int lp = blockIdx.x;
+    if (a.active[lp] == 0) return;
+    const size_t om = (size_t)lp * a.m;
+    for (int i = threadIdx.x; i < a.m; i += blockDim.x) a.rhs[om + i] = a.rhs[om + i] + a.dy[om + i];
+}
+
+// Last resort: an LP that is still running a full allowance after its restart is stopped with status max_iter
+// (S_CONT stays 1), so that the lockstep loop is bounded whatever one LP does.
+__global__ void kb_stop_stragglers(const BatchArgs a, int B, int min_iters) {
+    const int lp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lp >= B) return;
+    if (a.active[lp] != 0 && a.iters[lp] >= min_iters) a.active[lp] = 0;
+}
+
 __global__ void kb_finalize(const BatchArgs a, int B, double* obj, int* iters, int* status) {
     const int lp = blockIdx.x * blockDim.x + threadIdx.x;
     if (lp >= B) return;
@@ -500,6 +586,7 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
         IPM_CUDA_OK(cudaFuncSetAttribute(kb_residual<NPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + 8192));
         IPM_CUDA_OK(cudaFuncSetAttribute(kb_residual<NPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + 8192));
         IPM_CUDA_OK(cudaFuncSetAttribute(kb_dir<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
+        IPM_CUDA_OK(cudaFuncSetAttribute(kb_refine_rhs<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + 8192));
         IPM_CUDA_OK(cudaFuncSetAttribute(kbf_dir<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kf_smem_bytes(256, 1024)));
         IPM_CUDA_OK(cudaFuncSetAttribute(kbf_dir<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kf_smem_bytes(256, 1024)));
         IPM_CUDA_OK(cudaFuncSetAttribute(kbf_dir<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kf_smem_bytes(128, 1024)));
@@ -556,7 +643,8 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
     // latency.  So: once half of the batch has finished (lockstep iteration it_half) an LP gets
     // max(slack, it_half/2) more iterations; whatever is still running then is restarted from the starting point
     // under the literal six-pass iteration (= the reference's own order of operations, main.py:725-751).
-    int it_half = -1, restart_at = -1, it_last_join = 0;
+    int it_half = -1, restart_at = -1, it_last_join = 0, stop_at = -1, allowance = 0;
+    bool refine = false;                        // restarted LPs: corrector with one step of iterative refinement
     bool all_joined[2] = {true, true};          // per check slot: had every chunk joined when the check was enqueued?
     bool joined_pending = false;                // a chunk joined after the last check was enqueued
     for (;; ++it) {
@@ -570,6 +658,13 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
             kb_restart<<<B, 256, 0, st>>>(a, it_half);
             count_launch();
             fused = false;
+            refine = true;
+            allowance = 2 * it_half + g_restart_slack;       // iterations a restarted LP may take
+            stop_at = it + allowance;
+        } else if (stop_at > 0 && it >= stop_at) {
+            kb_stop_stragglers<<<ceil_div(B, 256), 256, 0, st>>>(a, B, allowance - 2);
+            count_launch();
+            stop_at = -1;
         }
         const bool counted_join = joined_pending;       // those LPs pass through this iteration's check first
         joined_pending = false;
@@ -624,6 +719,15 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
             if (!fused || kind == 0) kb_rhs<NPL><<<B, KB_NT, smem_w, st>>>(a, kind);
             if (m <= 32 * TRSVI_MAX_BLK) k_trsv_batched_inv<<<B, TRSVB_NT, trsv_batched_inv_smem(m), st>>>(t);
             else k_trsv_batched<<<B, TRSVB_NT, trsv_batched_smem(m), st>>>(t);
+            if (!fused && refine && kind == 1) {
+                kb_refine_rhs<NPL><<<B, KB_NT, smem_res, st>>>(a);                 // a.dy = -rb - A dx
+                TrsvBatchedArgs t2 = t;
+                t2.v = a.dy; t2.out = nullptr;
+                if (m <= 32 * TRSVI_MAX_BLK) k_trsv_batched_inv<<<B, TRSVB_NT, trsv_batched_inv_smem(m), st>>>(t2);
+                else k_trsv_batched<<<B, TRSVB_NT, trsv_batched_smem(m), st>>>(t2);
+                kb_add_refinement<<<B, 256, 0, st>>>(a);                           // a.rhs (= dy) += ddy
+                count_launch(3);
+            }
             if (!fused) kb_dir<NPL><<<B, KB_NT, smem_col, st>>>(a, kind);
             else launch_kbf_dir(kind, a, B, m, st);
             count_launch((fused && kind == 1) ? 2 : 3);

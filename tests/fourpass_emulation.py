@@ -66,3 +66,31 @@ def solve_fourpass(A, b, c, tol=1e-8, refresh_every=3, max_iter=200):
         if fresh:
             rb, rc = rbt, rct
     return k, x, y, s, hist
+
+
+def solve_refined(A, b, c, tol=1e-8, max_iter=150):
+    """Literal iteration on the normal equations with ONE step of iterative refinement of the corrector - what the
+    batched solver runs for an LP after a straggler restart (kb_refine_rhs):
+        delta = -rb - A dx;  M ddy = delta;  dy += ddy;  dx += d (A^T ddy);  ds = -s dx / x - r4 / x.
+    Returns (k, objective)."""
+    m, n = A.shape
+    b = b.reshape(-1, 1)
+    c = c.reshape(-1, 1)
+    x, y, s = O.initial_point(m, n, y0_is_one=False)
+    k = 0
+    while O.continue_flag(A, b, c, x, y, s, tol, tol, tol) and k < max_iter:
+        rb, rc = O.residuals(A, b, c, x, y, s)
+        r3 = x * s
+        L, _ = O.cholesky_safeguarded(O.normal_matrix(A, x, s))
+        dxa, dya, dsa = O.direction_normal(A, L, x, s, rb, rc, r3)
+        _, mu, sigma = O.sigma_mu(x, s, dxa, dsa)
+        r4 = r3 + dxa * dsa - sigma * mu
+        dx, dy, ds = O.direction_normal(A, L, x, s, rb, rc, r4)
+        ddy = O.solve_with_factor(L, -rb - A @ dx)
+        dy = dy + ddy
+        dx = dx + (x / s) * (A.T @ ddy)
+        ds = (-s * dx / x) - (r4 / x)
+        ap, ad = O.full_stepsize(x, s, dx, ds)
+        x, y, s = x + ap * dx, y + ad * dy, s + ad * ds
+        k += 1
+    return k, float((c.T @ x)[0, 0])

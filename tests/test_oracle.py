@@ -185,3 +185,23 @@ def test_fourpass_identities_against_literal_iteration(seed):
         assert abs(rb_rec - rb_true) <= 1e-3 * max(rb_true, floor)      # the recurrences track the true residuals
         assert abs(rc_rec - rc_true) <= 1e-3 * max(rc_true, floor)
         assert lin_err <= 1e-9                                          # linearity of main.py:150-152 in r4
+
+
+@pytest.mark.parametrize("seed", [16893, 31186])
+def test_refined_corrector_converges_where_the_normal_equations_stall(seed):
+    """LP 31186 of the generator: the reference as written (dense KKT + dgesv) needs 18 iterations, the literal
+    iteration on the normal equations stalls in this container (|rb| stuck near 1e-5 once d_max/d_min passes 1e19;
+    150+ iterations, also from Mehrotra's start) - one refinement step of the corrector, which is what the batched
+    solver applies to restarted LPs, brings it back to 19.  LP 16893 is the GPU straggler of DESIGN.md section 4."""
+    import importlib.util
+    import os
+    from oracle import ipm_oracle as orc
+    spec = importlib.util.spec_from_file_location("fourpass_emulation", os.path.join(os.path.dirname(__file__), "fourpass_emulation.py"))
+    emu = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(emu)
+    A, b, c = orc.synthetic_dense_lp(256, 512, seed)
+    kkt = orc.solve(A, b, c, tol=1e-8, max_iter=200, y0_is_one=False, linear="kkt")
+    assert kkt["status"] == 0 and 15 <= kkt["k"] <= 20
+    k, obj = emu.solve_refined(A, b, c, tol=1e-8, max_iter=60)
+    assert abs(k - kkt["k"]) <= 2
+    assert abs(obj - kkt["obj"]) <= 1e-8 * abs(kkt["obj"])
