@@ -151,7 +151,9 @@ def test_straggler_restart_lp_16893(ipm):
         lib.ipm_batched_set_variant(1, 3)
         obj, it, st = solve_batched_host(A, b, c, tol=1e-8)
         assert (st == 0).all() and (st6 == 0).all()
-        assert np.abs(it.astype(int) - it6.astype(int)).max() <= 1, (it, it6)
+        keep = np.arange(B) != at
+        assert np.abs(it.astype(int) - it6.astype(int))[keep].max() <= 1, (it, it6)
+        assert abs(int(it[at]) - int(it6[at])) <= 2        # literal + refined corrector vs literal
         assert np.abs((obj - obj6) / obj6).max() <= 1e-8
         # (the restarted LP ran the literal iteration plus one refinement step of the corrector from the start)
         o = orc.solve(A[at], b[at], c[at], tol=1e-8, max_iter=50000, y0_is_one=False, linear="normal")
@@ -160,7 +162,6 @@ def test_straggler_restart_lp_16893(ipm):
         lib.ipm_batched_set_straggler_restart(0)
         _, it0, st0 = solve_batched_host(A, b, c, tol=1e-8, max_iter=120)
         assert int(it0[at]) == 120 and int(st0[at]) == 1
-        keep = np.arange(B) != at
         assert np.array_equal(it0[keep], it[keep])
     finally:
         lib.ipm_batched_set_variant(1, 3)
