@@ -208,13 +208,14 @@ int ipm_batched_set_variant(int three_pass, int refresh_every);
  * reference), and one trapped LP keeps the whole lockstep loop alive.  Once half of the batch has finished (lockstep
  * iteration h), an LP gets max(slack, h/2) more iterations; what is still running then restarts from the starting
  * point (main.py:287-302) under the literal six-pass iteration, and its iteration count is that of the restarted
- * run.  Restarted LPs get one step of iterative refinement of the corrector in every iteration
- * (delta = -rb - A dx, M ddy = delta on the same factor, dy += ddy): the normal equations lose the primal equation
- * of the Newton system once max(x/s)/min(x/s) passes 1e19, which is what traps an LP that has not met
- * check_optimality by then (generator LP 31186 stalls in the CPU port of the normal-equations iteration at
- * |rb| = 1e-5 for hundreds of iterations, the reference's own dense KKT solve needs 18, the refined iteration 19).
- * A restarted LP that is still running after 2h + slack further iterations is stopped with status max_iter, so the
- * lockstep loop is bounded whatever one LP does.  slack = 0 switches all of this off; default 8.  Process-wide. */
+ * run.  An LP the literal iteration cannot finish within h + max(slack, h/2) iterations either restarts a second
+ * time, now with one step of iterative refinement of the corrector in every iteration (delta = -rb - A dx,
+ * M ddy = delta on the same factor, dy += ddy): the normal equations lose the primal equation of the Newton system
+ * once max(x/s)/min(x/s) passes 1e19, which is what traps an LP that has not met check_optimality by then
+ * (generator LP 31186 stalls in the CPU port of the normal-equations iteration at |rb| = 1e-5 for hundreds of
+ * iterations, the reference's own dense KKT solve needs 18, the refined iteration 19).  An LP still running
+ * 2h + slack iterations after that is stopped with status max_iter, so the lockstep loop is bounded whatever one LP
+ * does.  slack = 0 switches all of this off; default 8.  Process-wide. */
 int ipm_batched_set_straggler_restart(int slack);
 
 /* Phase timing of the batched solver (bench.py roofline): CUDA events on the solve stream around the four

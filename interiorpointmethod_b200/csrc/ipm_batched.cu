@@ -642,8 +642,11 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
     // CPU oracle; all others of 65536 within +-1).  One trapped LP keeps the whole lockstep loop alive at launch
     // latency.  So: once half of the batch has finished (lockstep iteration it_half) an LP gets
     // max(slack, it_half/2) more iterations; whatever is still running then is restarted from the starting point
-    // under the literal six-pass iteration (= the reference's own order of operations, main.py:725-751).
-    int it_half = -1, restart_at = -1, it_last_join = 0, stop_at = -1, allowance = 0;
+    // under the literal six-pass iteration (= the reference's own order of operations, main.py:725-751).  An LP the
+    // literal iteration cannot finish within it_half + max(slack, it_half/2) iterations either (the CPU port of it
+    // stalls on LP 31186, whatever the start) is restarted a second time with a refined corrector, and stopped with
+    // status max_iter if 2 it_half + slack iterations of that do not finish it: the loop is bounded.
+    int it_half = -1, restart_at = -1, it_last_join = 0, stop_at = -1, allowance = 0, stage = 0;
     bool refine = false;                        // restarted LPs: corrector with one step of iterative refinement
     bool all_joined[2] = {true, true};          // per check slot: had every chunk joined when the check was enqueued?
     bool joined_pending = false;                // a chunk joined after the last check was enqueued
@@ -654,17 +657,27 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
             IPM_TRY(join_landed(false));
             if (arr->next != before) { joined_pending = true; it_last_join = it; }
         }
-        if (fused && restart_at > 0 && it >= restart_at) {
+        if (stage == 0 && fused && restart_at > 0 && it >= restart_at) {
+            // stage 1: back to the starting point, literal six-pass iteration from here on
             kb_restart<<<B, 256, 0, st>>>(a, it_half);
             count_launch();
             fused = false;
-            refine = true;
-            allowance = 2 * it_half + g_restart_slack;       // iterations a restarted LP may take
+            stage = 1;
+            allowance = it_half + std::max(g_restart_slack, it_half / 2);      // iterations a restarted LP may take
             stop_at = it + allowance;
-        } else if (stop_at > 0 && it >= stop_at) {
+        } else if (stage == 1 && it >= stop_at) {
+            // stage 2: what the literal iteration could not finish either restarts once more, now with one step of
+            // iterative refinement of the corrector per iteration (kb_refine_rhs)
+            kb_restart<<<B, 256, 0, st>>>(a, allowance - 2);
+            count_launch();
+            refine = true;
+            stage = 2;
+            allowance = 2 * it_half + g_restart_slack;
+            stop_at = it + allowance;
+        } else if (stage == 2 && it >= stop_at) {
             kb_stop_stragglers<<<ceil_div(B, 256), 256, 0, st>>>(a, B, allowance - 2);
             count_launch();
-            stop_at = -1;
+            stage = 3;
         }
         const bool counted_join = joined_pending;       // those LPs pass through this iteration's check first
         joined_pending = false;
