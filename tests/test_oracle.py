@@ -205,3 +205,15 @@ def test_refined_corrector_converges_where_the_normal_equations_stall(seed):
     k, obj = emu.solve_refined(A, b, c, tol=1e-8, max_iter=60)
     assert abs(k - kkt["k"]) <= 2
     assert abs(obj - kkt["obj"]) <= 1e-8 * abs(kkt["obj"])
+
+
+@pytest.mark.parametrize("seed", [16893, 31186])
+def test_oracle_kkt_matches_reference_on_the_straggler_lps(seed, dense_results):
+    """The as-written port against the unmodified reference's `interior` on the two generator LPs behind the batched
+    solver's straggler handling (frozen by oracle/make_golden_stragglers.py)."""
+    from oracle import ipm_oracle as orc
+    g = dense_results["synthetic_256x512_seed%d" % seed]
+    A, b, c = orc.synthetic_dense_lp(256, 512, seed)
+    r = orc.solve(A, b, c, tol=1e-8, max_iter=50000, y0_is_one=False, linear="kkt")
+    assert r["status"] == 0 and r["k"] == g["k"]
+    assert abs(r["obj"] - g["obj"]) <= 1e-10 * abs(g["obj"])

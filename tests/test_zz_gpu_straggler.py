@@ -12,7 +12,7 @@ def ipm(built_library):
     return pkg
 
 
-def test_straggler_restart_lp_16893(ipm):
+def test_straggler_restart_lp_16893(ipm, dense_results):
     """LP 16893 of the benchmark generator (second GPU's share of the weak-scaling workload): the four-pass
     iteration traps it at the boundary (3527 iterations), the literal six-pass iteration and the CPU port of the
     reference need 17-18.  The restart (ipm_batched_set_straggler_restart, default on) must hand it to the literal
@@ -34,6 +34,8 @@ def test_straggler_restart_lp_16893(ipm):
         assert np.abs((obj - obj6) / obj6)[keep].max() <= 1e-8
         assert abs(obj[at] - obj6[at]) <= 1e-8 * abs(obj6[at])
         assert int(it[at]) == int(it6[at])            # the restarted LP ran the literal iteration from the start
+        g = dense_results["synthetic_256x512_seed16893"]       # the unmodified reference's `interior`: k = 18
+        assert abs(int(it[at]) - g["k"]) <= 1 and abs(obj[at] - g["obj"]) <= 1e-8 * abs(g["obj"])
         o = orc.solve(A[at], b[at], c[at], tol=1e-8, max_iter=50000, y0_is_one=False, linear="normal")
         assert abs(int(it[at]) - o["k"]) <= 1 and abs(obj[at] - o["obj"]) <= 1e-7 * abs(o["obj"])
         # without the restart the trap is there (documents why the restart exists; capped to keep the test short)
