@@ -1,10 +1,10 @@
 """CPU scan of the benchmark generator's LPs (256 x 512, seed = LP index) for stragglers - TEST INFRASTRUCTURE
 (uses the oracle; not collected by pytest).  Results of the round-1 run: profiles/r1_cpu_straggler_scan.txt.
 
-    python tests/scan_generator_stragglers.py FIRST LAST literal|refined|always [workers]
+    python tests/scan_generator_stragglers.py FIRST LAST literal|refined[:THRESH]|always [workers]
 
 literal: the oracle's normal-equations iteration (what the GPU's six-pass iteration restates)
-refined: the same with one refinement step of the corrector when |(-rb - A dx)| > 0.1 |rb|
+refined: the same with one refinement step of the corrector when |(-rb - A dx)| > THRESH |rb| (default 0.1)
 always : the same with the refinement step in every iteration (what restarted LPs run on the GPU)
 """
 import os
@@ -51,7 +51,9 @@ def work(seed):
     A, b, c = O.synthetic_dense_lp(256, 512, seed)
     if MODE == "literal":
         return seed, O.solve(A, b, c, tol=1e-8, max_iter=CAP, y0_is_one=False, linear="normal")["k"]
-    return seed, _refined(O, A, b, c, 0.1 if MODE == "refined" else 0.0)
+    if MODE.startswith("refined"):
+        return seed, _refined(O, A, b, c, float(MODE.split(":")[1]) if ":" in MODE else 0.1)
+    return seed, _refined(O, A, b, c, 0.0)
 
 
 if __name__ == "__main__":
