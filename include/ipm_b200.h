@@ -202,21 +202,23 @@ int64_t ipm_batched_workspace_bytes(int B, int m, int n);
  * three_pass = 0: six passes, every residual from scratch in every iteration, exactly as main.py:725-751 orders it.
  * Process-wide; for A/B measurements and parity tests. */
 int ipm_batched_set_variant(int three_pass, int refresh_every);
-/* Straggler restart of the four-pass iteration.  The four-pass and the literal iteration round differently, and in
- * the ill-conditioned last iterations that can decide whether an LP converges or is trapped at the boundary with
- * step lengths near zero (benchmark LP 16893: 3527 iterations four-pass, 17 six-pass, 18 in the CPU port of the
- * reference), and one trapped LP keeps the whole lockstep loop alive.  Once half of the batch has finished (lockstep
- * iteration h), an LP gets max(slack, h/2) more iterations; what is still running then restarts from the starting
- * point (main.py:287-302) under the literal six-pass iteration, and its iteration count is that of the restarted
- * run.  An LP the literal iteration cannot finish within h + max(slack, h/2) iterations either restarts a second
- * time, now with one step of iterative refinement of the corrector in every iteration (delta = -rb - A dx,
- * M ddy = delta on the same factor, dy += ddy): the normal equations lose the primal equation of the Newton system
- * once max(x/s)/min(x/s) passes 1e19, which is what traps an LP that has not met check_optimality by then
- * (generator LP 31186 stalls in the CPU port of the normal-equations iteration at |rb| = 1e-5 for hundreds of
- * iterations, the reference's own dense KKT solve needs 18, the refined iteration 19).  An LP still running
- * 2h + slack iterations after that is stopped with status max_iter, so the lockstep loop is bounded whatever one LP
- * does.  slack = 0 switches all of this off; default 8.  Process-wide. */
-int ipm_batched_set_straggler_restart(int slack);
+/* Further process-wide options of the batched solver (read at the start of every solve).
+ * IPM_BOPT_REFINE (default 1): conditional refinement of the corrector.  The reference solves the unreduced
+ *   Newton system (main.py:13-21), whose second block row is A dx = -rb; the normal equations (main.py:221-229)
+ *   satisfy it only as well as the factor of M = A D A^T allows, and once max(x/s)/min(x/s) passes 1e19 that is
+ *   not well enough for |rb| to keep falling: an LP that has not met check_optimality (main.py:169-173) by then
+ *   stays trapped at the boundary for thousands of iterations (generator LPs 16893 and 31186; the reference needs
+ *   18 iterations on both), and one trapped LP keeps the whole lockstep loop alive.  The corrector pass forms
+ *   delta = -rb - A dx anyway (A dx carries the residual recurrence); when |delta| > |rb| - the step would not
+ *   reduce the primal residual at all - the LP takes ONE step of iterative refinement on the same factor
+ *   (M ddy = delta, dy += ddy, dx and ds re-formed) before it is updated.  Fires about 0.02 times per LP on the
+ *   benchmark generator and leaves all 65536 of its LPs within +-1 iteration of the reference
+ *   (tests/golden/batch_256x512_*.{npz,json}).  0 switches it off (A/B, and to document the trap).
+ * IPM_BOPT_STRIP_TMA (default 1): the four-pass direction kernels read the column strips of A straight from the
+ *   caller's row-major array through a 3-D tensor map (cp.async.bulk.tensor); 0 = from a strip-major copy of A
+ *   made once per solve (costs a second copy of A in the workspace: set it BEFORE ipm_batched_workspace_bytes). */
+enum { IPM_BOPT_REFINE = 1, IPM_BOPT_STRIP_TMA = 2 };
+int ipm_batched_set_option(int option, int value);
 
 /* Phase timing of the batched solver (bench.py roofline): CUDA events on the solve stream around the four
  * phases of every lockstep iteration.  ms/calls index: 0 residual pass, 1 SYRK (dmma_nt_kernel, one launch

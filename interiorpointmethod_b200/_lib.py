@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_PKG, "libipm_b200.so")
 IPM_OK = 0
 ERRORS = {-1: "IPM_ERR_CUDA", -2: "IPM_ERR_ARG", -3: "IPM_ERR_SHAPE", -4: "IPM_ERR_STATE", -5: "IPM_ERR_NOMEM"}
 STATUS = {0: "converged", 1: "max_iter", 2: "nan"}
+BOPT_REFINE, BOPT_STRIP_TMA = 1, 2      # ipm_batched_set_option
 
 # every symbol include/ipm_b200.h declares: name -> (restype, argtypes)
 _dp = POINTER(c_double)
@@ -61,7 +62,7 @@ SYMBOLS = {
     "ipm_release_cached": (c_int, []),
     "ipm_batched_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
     "ipm_batched_set_variant": (c_int, [c_int, c_int]),
-    "ipm_batched_set_straggler_restart": (c_int, [c_int]),
+    "ipm_batched_set_option": (c_int, [c_int, c_int]),
     "ipm_profile_enable": (c_int, [c_int]),
     "ipm_profile_read": (c_int, [c_void_p, c_void_p, POINTER(c_int64)]),
     "ipm_profile_last": (c_int, [c_void_p, c_void_p, c_int]),

@@ -249,7 +249,8 @@ template <int NB, int ROWS>
 constexpr size_t chol_trsm_smem() { return (size_t)(NB * (NB + 2) + NB * ROWS) * sizeof(double); }
 
 // ------------------------------------------------------------------------------------------------
-// side stream of the look-ahead (one per device, created on first use)
+// side stream of the look-ahead (one per device AND host thread, created on first use: two threads factoring on
+// one device through distinct handles never share the stream or re-record each other's events)
 struct CholSide {
     cudaStream_t st = nullptr;
     cudaEvent_t strip_done = nullptr, rest_done = nullptr;
@@ -261,7 +262,7 @@ struct CholSide {
         return IPM_OK;
     }
 };
-static CholSide g_chol_side[16];
+static thread_local CholSide g_chol_side[16];
 static bool g_chol_lookahead = true;
 
 // ------------------------------------------------------------------------------------------------
@@ -269,17 +270,15 @@ static bool g_chol_lookahead = true;
 template <int NB, int NT_DIAG, int ROWS>
 inline int potrf_blocked(double* M, int64_t ldm, int64_t strideM, int m, int batch, double* scal,
                          int64_t strideScal, double tau, const int* active, cudaStream_t st) {
-    static int configured_dev = -1;
-    int dev = 0;
-    IPM_CUDA_OK(cudaGetDevice(&dev));
     auto kd = k_chol_diag<NB, NT_DIAG>;
     auto kt = k_chol_trsm<NB, ROWS>;
-    if (configured_dev != dev) {
+    static DevOnce once;
+    IPM_TRY(once_per_device(once, [&]() -> int {
         IPM_CUDA_OK(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_diag_smem<NB>()));
         IPM_CUDA_OK(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)chol_trsm_smem<NB, ROWS>()));
-        configured_dev = dev;
-    }
+        return IPM_OK;
+    }));
     k_maxdiag<<<dim3(1, 1, batch), 256, 0, st>>>(M, ldm, strideM, m, scal, strideScal, active);
     count_launch();
     CholArgs a;
@@ -296,7 +295,10 @@ inline int potrf_blocked(double* M, int64_t ldm, int64_t strideM, int m, int bat
     const bool lookahead = (batch == 1) && (NB == WS_BM) && (m >= 8 * NB) && ws_eligible(probe) && g_chol_lookahead;
     CholSide* side = nullptr;
     if (lookahead) {
-        side = &g_chol_side[dev < 16 ? dev : 0];
+        int dev = 0;
+        IPM_CUDA_OK(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 16) return IPM_ERR_ARG;
+        side = &g_chol_side[dev];
         IPM_TRY(side->ensure());
     }
     bool rest_pending = false;
@@ -484,14 +486,12 @@ static __global__ void __launch_bounds__(TRSV128_NT, 1) k_trsv_bwd128(const Trsv
 
 // rhs (destroyed) -> sol.  L is the factor produced by potrf_blocked.
 inline int potrs_single_blocks(const double* L, int64_t ldm, int m, double* rhs, double* tmp, double* sol, cudaStream_t st) {
-    static int configured_dev = -1;
-    int dev = 0;
-    IPM_CUDA_OK(cudaGetDevice(&dev));
-    if (configured_dev != dev) {
+    static DevOnce once;
+    IPM_TRY(once_per_device(once, []() -> int {
         IPM_CUDA_OK(cudaFuncSetAttribute(k_trsv_fwd128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsv128_smem()));
         IPM_CUDA_OK(cudaFuncSetAttribute(k_trsv_bwd128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsv128_smem()));
-        configured_dev = dev;
-    }
+        return IPM_OK;
+    }));
     TrsvArgs a;
     a.L = L; a.ldm = ldm; a.m = m;
     a.v = rhs; a.out = tmp;
@@ -526,7 +526,14 @@ struct TrsvBatchedArgs {
     int m;
     const int* active;
     double* out = nullptr;           // optional separate destination (same stride)
+    int only_flag = 0;               // != 0: only LPs whose active flag equals it (corrector refinement: 3)
+    int accumulate = 0;              // != 0: destination += solution
 };
+__device__ __forceinline__ bool trsv_batched_skip(const TrsvBatchedArgs& a, int bz) {
+    if (!a.active) return false;
+    const int f = a.active[bz];
+    return a.only_flag ? (f != a.only_flag) : (f == 0);
+}
 constexpr int TRSVB_NT = 256;
 constexpr int TRSVB_NW = TRSVB_NT / 32;
 
@@ -535,7 +542,7 @@ static __global__ void __launch_bounds__(TRSVB_NT, 3) k_trsv_batched(const TrsvB
     double* Ls0 = smem_tb;                  // [2][32][33] diagonal blocks, double buffered
     double* vec = smem_tb + 2 * 32 * 33;    // [m]
     const int bz = blockIdx.x;
-    if (a.active && a.active[bz] == 0) return;
+    if (trsv_batched_skip(a, bz)) return;
     const double* L = a.L + (size_t)bz * a.strideM;
     double* v = a.v + (size_t)bz * a.strideV;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, m = a.m;
@@ -639,7 +646,11 @@ static __global__ void __launch_bounds__(TRSVB_NT, 3) k_trsv_batched(const TrsvB
         __syncthreads();
     }
     double* dst = a.out ? a.out + (size_t)bz * a.strideV : v;
-    for (int i = tid; i < m; i += TRSVB_NT) dst[i] = vec[i];
+    if (a.accumulate) {
+        for (int i = tid; i < m; i += TRSVB_NT) dst[i] = dst[i] + vec[i];
+    } else {
+        for (int i = tid; i < m; i += TRSVB_NT) dst[i] = vec[i];
+    }
 }
 // ---- variant for m <= 256 (at most 8 diagonal blocks): the 32-step substitution chains of the diagonal blocks
 // were the critical path (every other warp waited on warp 0), so each warp first INVERTS one 32x32 diagonal block
@@ -654,7 +665,7 @@ static __global__ void __launch_bounds__(TRSVB_NT, 3) k_trsv_batched_inv(const T
     double* vec = smem_ti + TRSVI_MAX_BLK * 32 * 33;     // [m]
     double* dinv = vec + a.m;                            // [8 warps][32]
     const int bz = blockIdx.x;
-    if (a.active && a.active[bz] == 0) return;
+    if (trsv_batched_skip(a, bz)) return;
     const double* L = a.L + (size_t)bz * a.strideM;
     double* v = a.v + (size_t)bz * a.strideV;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, m = a.m;
@@ -755,7 +766,11 @@ static __global__ void __launch_bounds__(TRSVB_NT, 3) k_trsv_batched_inv(const T
         __syncthreads();
     }
     double* dst = a.out ? a.out + (size_t)bz * a.strideV : v;
-    for (int i = tid; i < m; i += TRSVB_NT) dst[i] = vec[i];
+    if (a.accumulate) {
+        for (int i = tid; i < m; i += TRSVB_NT) dst[i] = dst[i] + vec[i];
+    } else {
+        for (int i = tid; i < m; i += TRSVB_NT) dst[i] = vec[i];
+    }
 }
 
 inline size_t trsv_batched_smem(int m) { return (size_t)(2 * 32 * 33 + m) * sizeof(double); }
@@ -768,14 +783,12 @@ inline int potrs_single(const double* L, int64_t ldm, int m, double* rhs, double
         TrsvBatchedArgs t;
         t.L = L; t.ldm = ldm; t.strideM = 0; t.v = rhs; t.strideV = 0; t.m = m; t.active = nullptr; t.out = sol;
         if (m <= 32 * TRSVI_MAX_BLK) {
-            static int configured_dev = -1;
-            int dev = 0;
-            IPM_CUDA_OK(cudaGetDevice(&dev));
-            if (configured_dev != dev) {
+            static DevOnce once;
+            IPM_TRY(once_per_device(once, []() -> int {
                 IPM_CUDA_OK(cudaFuncSetAttribute(k_trsv_batched_inv, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  (int)trsv_batched_inv_smem(32 * TRSVI_MAX_BLK)));
-                configured_dev = dev;
-            }
+                return IPM_OK;
+            }));
             k_trsv_batched_inv<<<1, TRSVB_NT, trsv_batched_inv_smem(m), st>>>(t);
         } else
         k_trsv_batched<<<1, TRSVB_NT, trsv_batched_smem(m), st>>>(t);

@@ -134,6 +134,13 @@ static __global__ void __launch_bounds__(KBC_NT, KBC_NT == 256 ? 2 : 1) kb_chol(
     double* Mb = a.M + (size_t)lp * a.strideM;
     const int64_t ldm = a.ldm;
 
+    // The lower triangle of M_i goes to L2 now (one bulk prefetch per row): M was written by the SYRK of ALL LPs and
+    // has left L2 long ago, so without this every first touch of a panel column (accumulator initialisation of the
+    // early update) is an exposed DRAM round trip in the middle of the factorisation.
+    for (int r = tid; r < m; r += KBC_NT) {
+        const uint32_t bytes = (uint32_t)(((r + 1) * 8 + 15) & ~15);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(Mb + (size_t)r * ldm), "r"(bytes) : "memory");
+    }
     // max_i M_ii (threshold of the safeguard) and the raw first panel: rows 0..m-1, columns 0..31
     {
         double v = red_identity<RED_MAX>();
@@ -366,14 +373,12 @@ static __global__ void __launch_bounds__(KBC_NT, KBC_NT == 256 ? 2 : 1) kb_chol(
 template <int NT>
 inline int potrf_batched_fused_nt(double* M, int64_t ldm, int64_t strideM, int m, int batch, double* scal,
                                   int64_t strideScal, double tau, const int* active, cudaStream_t st) {
-    static int configured_dev = -1;
-    int dev = 0;
-    IPM_CUDA_OK(cudaGetDevice(&dev));
-    if (configured_dev != dev) {
+    static DevOnce once;
+    IPM_TRY(once_per_device(once, []() -> int {
         IPM_CUDA_OK(cudaFuncSetAttribute(kb_chol<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kbc_smem_bytes(kbc_max_m(NT))));
-        configured_dev = dev;
-    }
+        return IPM_OK;
+    }));
     CholBatchedArgs a;
     a.M = M; a.ldm = ldm; a.strideM = strideM; a.scal = scal; a.strideScal = strideScal; a.tau = tau; a.m = m;
     a.active = active;

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <atomic>
+#include <mutex>
 #include <string>
 
 #include "../../include/ipm_b200.h"
@@ -41,6 +42,26 @@ inline int launch_check() {
     return IPM_OK;
 }
 
+// One-time per-device configuration of a kernel (cudaFuncSetAttribute for > 48 KB of dynamic shared memory): a
+// `static DevOnce` next to the launch, thread-safe, one flag per device ordinal (function attributes are per
+// device, so a process that drives several GPUs from several threads configures each of them exactly once).
+struct DevOnce {
+    std::mutex mu;
+    bool done[64] = {};
+};
+template <class F>
+inline int once_per_device(DevOnce& o, F&& configure) {
+    int dev = 0;
+    IPM_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return IPM_ERR_ARG;
+    std::lock_guard<std::mutex> lk(o.mu);
+    if (!o.done[dev]) {
+        IPM_TRY(configure());
+        o.done[dev] = true;
+    }
+    return IPM_OK;
+}
+
 static inline int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
@@ -70,6 +91,7 @@ enum Scal {
     S_NFIXED,       // pivots replaced in the last factorisation
     S_RAW_P,        // min({-x/dx : dx<0} U {1}) of the last direction
     S_RAW_D,        // min({-s/ds : ds<0} U {1}) of the last direction
+    S_NREFINE,      // batched solver: corrector refinements taken so far
     S_COUNT = 24
 };
 

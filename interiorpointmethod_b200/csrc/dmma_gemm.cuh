@@ -194,13 +194,13 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) dmma_nt_kernel(const DmmaArgs
 // Host launcher.  grid = (tiles over rowsQ, tiles over rowsP, batch).
 template <int BM, int BN, int WM, int WN, int EPI>
 inline int dmma_nt_launch(const DmmaArgs& a, int batch, cudaStream_t st) {
-    static bool configured = false;
     constexpr size_t smem = dmma_smem_bytes<BM, BN, WM, WN>();
     auto kern = dmma_nt_kernel<BM, BN, WM, WN, EPI>;
-    if (!configured) {
+    static DevOnce once;
+    IPM_TRY(once_per_device(once, [&]() -> int {
         IPM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+        return IPM_OK;
+    }));
     if (a.rowsP <= 0 || a.rowsQ <= 0 || batch <= 0) return IPM_OK;
     dim3 grid(ceil_div(a.rowsQ, BN), ceil_div(a.rowsP, BM), batch);
     kern<<<grid, WM * WN * 32, smem, st>>>(a);

@@ -17,6 +17,8 @@
 //   trsv, kbf_dir<1>            corrector direction, update, residuals of the new point by recurrence
 //   kb_residual<.,true>         from-scratch check_optimality, only for LPs the recurrences declare finished
 #include <cmath>
+#include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "chol.cuh"
@@ -90,9 +92,15 @@ struct Profiler {
 };
 Profiler g_prof;
 
-int g_fresh_every = 3;         // residuals from scratch every 3rd iteration (see ipm_batched_set_variant)
-int g_restart_slack = 8;       // straggler restart (see ipm_batched_set_straggler_restart); 0 = off
-bool g_allow_fused = true;      // ipm_batched_set_variant(): 0 forces the 6-pass iteration (tests, A/B timing)
+// Process-wide options of the batched solver (ipm_batched_set_variant / ipm_batched_set_option): read once at the
+// start of every solve, atomics so that setting them from another thread is not a data race.
+struct BatchedOptions {
+    std::atomic<int> fused{1};          // 0 forces the literal six-pass iteration (tests, A/B timing)
+    std::atomic<int> fresh_every{3};    // four-pass path: residuals from scratch every 3rd iteration
+    std::atomic<int> refine{1};         // conditional refinement of the corrector (kbf_dir / kb_dir)
+    std::atomic<int> strip_tma{1};      // four-pass path: strips of A through a tensor map (1) or a strip-major copy (0)
+};
+BatchedOptions g_opt;
 
 // ---------------------------------------------------------------------------------------------
 // One pass over A_i: Ax (warp per row) and A^T y (column partial sums per warp, combined in warp order).
@@ -228,30 +236,6 @@ __global__ void __launch_bounds__(256) kb_init(const BatchArgs a, int flag, int 
     }
 }
 
-// Straggler restart: every LP that is still iterating after min_iters iterations goes back to the starting point
-// x = s = 1, y = 0 (main.py:287-302) with its iteration count reset; the caller continues with the literal
-// six-pass iteration.  |b|, |c| are kept.
-__global__ void __launch_bounds__(256) kb_restart(const BatchArgs a, int min_iters) {
-    const int lp = blockIdx.x, tid = threadIdx.x;
-    if (a.active[lp] == 0 || a.iters[lp] < min_iters) return;
-    const int m = a.m, n = a.n;
-    for (int i = tid; i < m; i += blockDim.x) a.y[(size_t)lp * m + i] = 0.0;
-    for (int i = tid; i < n; i += blockDim.x) {
-        a.x[(size_t)lp * n + i] = 1.0;
-        a.s[(size_t)lp * n + i] = 1.0;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        double* scal = a.scal + (size_t)lp * S_COUNT;
-        const double nb = scal[S_NB], nc = scal[S_NC];
-        for (int i = 0; i < S_COUNT; ++i) scal[i] = 0.0;
-        scal[S_NB] = nb;
-        scal[S_NC] = nc;
-        a.active[lp] = 1;
-        a.iters[lp] = 0;
-    }
-}
-
 // rcx = rcomp/x, w = d (rc - rcx), rhs = -rb - A w      (main.py:72, 150-152, 225)
 template <int NPL>
 __global__ void __launch_bounds__(KB_NT) kb_rhs(const BatchArgs a, int kind) {
@@ -302,14 +286,21 @@ __global__ void __launch_bounds__(KB_NT) kb_rhs(const BatchArgs a, int kind) {
 //   kind 0: mu_aff, mu, sigma (main.py:582-600), predictor direction stored for the corrector rhs
 //   kind 1: alpha = min(1, eta*min) (main.py:616-623), x += ap dx, y += ad dy, s += ad ds (main.py:694-696)
 // dy is read from a.rhs (the batched triangular solve works in place).
+// Conditional refinement of the corrector (kind 1, a.refine; the rule and its reason are stated at kbf_dir,
+// ipm_batched_fused.cuh): a second sweep over A_i (from L2) forms delta = -rb - A dx; when |delta| > |rb| the LP
+// is not updated, delta goes to a.dy and the LP is flagged FLAG_REFINE; the host's next two launches solve
+// a.rhs += M^-1 delta and run this kernel again with pass = 1 for the flagged LPs.
 template <int NPL>
-__global__ void __launch_bounds__(KB_NT) kb_dir(const BatchArgs a, int kind) {
+__global__ void __launch_bounds__(KB_NT) kb_dir(const BatchArgs a, int kind, int pass) {
     extern __shared__ __align__(16) double smem[];
     double* colred = smem;     // [KB_NW][n]
     __shared__ double sh[32];
-    __shared__ double s_alpha[2];
+    __shared__ double s_alpha[4];
     const int lp = blockIdx.x;
-    if (a.active[lp] == 0) return;
+    {
+        const int flag = a.active[lp];
+        if (pass == 0 ? (flag == 0) : (flag != FLAG_REFINE)) return;
+    }
     const int m = a.m, n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double* A = a.A + (size_t)lp * m * n;
     const size_t on = (size_t)lp * n, om = (size_t)lp * m;
@@ -383,6 +374,55 @@ __global__ void __launch_bounds__(KB_NT) kb_dir(const BatchArgs a, int kind) {
             scal[S_SIGMA] = sigma; scal[S_SIGMA_MU] = sigma * mu;
         }
     } else {
+        if (a.refine && pass == 0) {
+            // every thread is past the barriers above, so the column partials are dead: dx takes their place
+            double* dxs = colred;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int k = tid + q * KB_NT;
+                if (k < n) dxs[k] = dxv[q];
+            }
+            __syncthreads();
+            double2 wr[NPL];
+#pragma unroll
+            for (int j = 0; j < NPL; ++j) {
+                const int c2 = j * 32 + lane;
+                wr[j] = (c2 < n2) ? reinterpret_cast<const double2*>(dxs)[c2] : make_double2(0.0, 0.0);
+            }
+            double nd2 = 0.0, nr2 = 0.0;
+            for (int r = warp; r < m; r += KB_NW) {
+                const double2* row = reinterpret_cast<const double2*>(A + (size_t)r * n);
+                double dot0 = 0.0, dot1 = 0.0;
+#pragma unroll
+                for (int j = 0; j < NPL; ++j) {
+                    const int c2 = j * 32 + lane;
+                    if (c2 < n2) {
+                        const double2 v = row[c2];
+                        dot0 += v.x * wr[j].x;
+                        dot1 += v.y * wr[j].y;
+                    }
+                }
+                const double dot = warp_sum(dot0 + dot1);
+                if (lane == 0) {
+                    const double rbr = a.rb[om + r], dl = -rbr - dot;
+                    a.dy[om + r] = dl;
+                    nd2 += dl * dl;
+                    nr2 += rbr * rbr;
+                }
+            }
+            nd2 = block_red<RED_SUM>(nd2, sh);
+            if (tid == 0) s_alpha[2] = nd2;
+            nr2 = block_red<RED_SUM>(nr2, sh);
+            if (tid == 0) s_alpha[3] = (s_alpha[2] > nr2) ? 1.0 : 0.0;        // NaN compares false: no refinement
+            __syncthreads();
+            if (s_alpha[3] != 0.0) {
+                if (tid == 0) {
+                    a.active[lp] = FLAG_REFINE;
+                    scal[S_NREFINE] = scal[S_NREFINE] + 1.0;
+                }
+                return;
+            }
+        }
         ap = fmin(1.0, a.eta * ap);
         ad = fmin(1.0, a.eta * ad);
 #pragma unroll
@@ -397,94 +437,9 @@ __global__ void __launch_bounds__(KB_NT) kb_dir(const BatchArgs a, int kind) {
         if (tid == 0) {
             scal[S_AP] = ap; scal[S_AD] = ad;
             a.iters[lp] += 1;
+            a.active[lp] = 1;
         }
     }
-}
-
-// Iterative refinement of the corrector (restarted LPs only, see run_batched).  With dy from the factored normal
-// equations the primal equation A dx = -rb of the Newton system (third block row of main.py:13-21) holds only as
-// well as the Cholesky factor of M = A D A^T allows; in the last iterations (d_max/d_min > 1e19) that is not well
-// enough for |rb| to keep falling, and an LP that has not met check_optimality by then can stay trapped.  One
-// refinement step:  dx = d (A^T dy) + w,  delta = -rb - A dx  (this kernel, two sweeps over A_i: column sums, then
-// row dots), M ddy = delta (the batched triangular solves on the same factor), dy += ddy (kb_add_refinement); the
-// corrector kernel kb_dir then forms dx, ds from the refined dy as before (both are linear in dy).
-template <int NPL>
-__global__ void __launch_bounds__(KB_NT) kb_refine_rhs(const BatchArgs a) {
-    extern __shared__ __align__(16) double smem[];
-    double* colred = smem;                               // [KB_NW][n]
-    const int lp = blockIdx.x;
-    if (a.active[lp] == 0) return;
-    const int m = a.m, n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double* dxs = smem + (size_t)KB_NW * n;              // [n]
-    const double* A = a.A + (size_t)lp * m * n;
-    const size_t on = (size_t)lp * n, om = (size_t)lp * m;
-    const double* dy = a.rhs + om;                       // the triangular solve worked in place
-    const int n2 = n >> 1;
-    double2 ca[NPL];
-#pragma unroll
-    for (int j = 0; j < NPL; ++j) ca[j] = make_double2(0.0, 0.0);
-    for (int r = warp; r < m; r += KB_NW) {
-        const double2* row = reinterpret_cast<const double2*>(A + (size_t)r * n);
-        const double yr = dy[r];
-#pragma unroll
-        for (int j = 0; j < NPL; ++j) {
-            const int c2 = j * 32 + lane;
-            if (c2 < n2) {
-                const double2 v = row[c2];
-                ca[j].x += v.x * yr;
-                ca[j].y += v.y * yr;
-            }
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < NPL; ++j) {
-        const int c2 = j * 32 + lane;
-        if (c2 < n2) reinterpret_cast<double2*>(colred + (size_t)warp * n)[c2] = ca[j];
-    }
-    __syncthreads();
-    for (int k = tid; k < n; k += KB_NT) {
-        double u = 0.0;
-#pragma unroll
-        for (int w = 0; w < KB_NW; ++w) u += colred[(size_t)w * n + k];
-        dxs[k] = a.d[on + k] * u + a.w[on + k];
-    }
-    __syncthreads();
-    double2 wr[NPL];
-#pragma unroll
-    for (int j = 0; j < NPL; ++j) {
-        const int c2 = j * 32 + lane;
-        wr[j] = (c2 < n2) ? reinterpret_cast<const double2*>(dxs)[c2] : make_double2(0.0, 0.0);
-    }
-    for (int r = warp; r < m; r += KB_NW) {
-        const double2* row = reinterpret_cast<const double2*>(A + (size_t)r * n);
-        double dot0 = 0.0, dot1 = 0.0;
-#pragma unroll
-        for (int j = 0; j < NPL; ++j) {
-            const int c2 = j * 32 + lane;
-            if (c2 < n2) {
-                const double2 v = row[c2];
-                dot0 += v.x * wr[j].x;
-                dot1 += v.y * wr[j].y;
-            }
-        }
-        const double dot = warp_sum(dot0 + dot1);
-        if (lane == 0) a.dy[om + r] = -a.rb[om + r] - dot;
-    }
-}
-
-__global__ void __launch_bounds__(256) kb_add_refinement(const BatchArgs a) {
-    const int lp = blockIdx.x;
-    if (a.active[lp] == 0) return;
-    const size_t om = (size_t)lp * a.m;
-    for (int i = threadIdx.x; i < a.m; i += blockDim.x) a.rhs[om + i] = a.rhs[om + i] + a.dy[om + i];
-}
-
-// Last resort: an LP that is still running a full allowance after its restart is stopped with status max_iter
-// (S_CONT stays 1), so that the lockstep loop is bounded whatever one LP does.
-__global__ void kb_stop_stragglers(const BatchArgs a, int B, int min_iters) {
-    const int lp = blockIdx.x * blockDim.x + threadIdx.x;
-    if (lp >= B) return;
-    if (a.active[lp] != 0 && a.iters[lp] >= min_iters) a.active[lp] = 0;
 }
 
 __global__ void kb_finalize(const BatchArgs a, int B, double* obj, int* iters, int* status) {
@@ -508,14 +463,14 @@ struct Workspace {
     unsigned* h_nact;    // pinned
 };
 
-int64_t at_doubles(int B, int m, int n) {        // strip-major copy of A (3-pass path only)
-    if (m > KF_MAX_M) return 0;
+int64_t at_doubles(int B, int m, int n) {        // strip-major copy of A (3-pass path with IPM_BOPT_STRIP_TMA = 0 only)
+    if (m > KF_MAX_M || g_opt.strip_tma.load() != 0) return 0;
     return (int64_t)B * ceil_div(n, KF_W) * (32 * kf_nrp(m)) * KF_W;
 }
 
 int64_t ws_bytes(int B, int m, int n) {
     const int64_t ldm = round_up(m, 16);
-    int64_t doubles = (int64_t)B * (8 * (int64_t)n + 4 * (int64_t)m + S_COUNT) + (int64_t)B * m * ldm + at_doubles(B, m, n);
+    int64_t doubles = (int64_t)B * (10 * (int64_t)n + 4 * (int64_t)m + S_COUNT) + (int64_t)B * m * ldm + at_doubles(B, m, n);
     int64_t bytes = doubles * 8 + (int64_t)B * 2 * sizeof(int) + 256 + 1024;
     return round_up(bytes, 256);
 }
@@ -528,7 +483,7 @@ void carve(Workspace& w, void* base, int B, int m, int n) {
     w.M = take((int64_t)B * m * w.ldm);
     w.a.At = take(at_doubles(B, m, n));
     w.a.x = take(bn); w.a.s = take(bn); w.a.rc = take(bn); w.a.d = take(bn); w.a.w = take(bn); w.a.rcx = take(bn);
-    w.a.dxa = take(bn); w.a.dsa = take(bn);
+    w.a.dxa = take(bn); w.a.dsa = take(bn); w.a.dxc = take(bn); w.a.dsc = take(bn);
     w.a.y = take(bm); w.a.rb = take(bm); w.a.dy = take(bm); w.a.rhs = take(bm);
     w.a.scal = take((int64_t)B * S_COUNT);
     int* ip = reinterpret_cast<int*>(p);
@@ -540,8 +495,8 @@ void carve(Workspace& w, void* base, int B, int m, int n) {
 }
 
 // Host-buffer entry point: the batch arrives in chunks on a copy stream while the lockstep loop is already
-// running; a chunk's LPs join the loop (kb_init, strip-major copy) at the first iteration after its copy has
-// landed.  Every LP keeps its own iteration counter, so joining late changes nothing for it.
+// running; a chunk's LPs join the loop (kb_init) at the first iteration after its copy has landed.  Every LP keeps
+// its own iteration counter, so joining late changes nothing for it.
 struct Arrival {
     int nchunks = 0;
     const int* first = nullptr;
@@ -550,18 +505,36 @@ struct Arrival {
     int next = 0;                       // first chunk that has not joined yet
 };
 
-void launch_kbf_dir(int kind, const BatchArgs& a, int B, int m, cudaStream_t st) {
+template <int SRC>
+void launch_kbf_dir_src(int kind, int pass, const BatchArgs& a, const CUtensorMap& tm, int B, int m, cudaStream_t st) {
     const size_t sm = kf_smem_bytes(m, a.n);
     switch (kf_nrp(m) * 2 + kind) {
-        case 2: kbf_dir<0, 1><<<B, KF_NTT, sm, st>>>(a); break;
-        case 3: kbf_dir<1, 1><<<B, KF_NTT, sm, st>>>(a); break;
-        case 4: kbf_dir<0, 2><<<B, KF_NTT, sm, st>>>(a); break;
-        case 5: kbf_dir<1, 2><<<B, KF_NTT, sm, st>>>(a); break;
-        case 8: kbf_dir<0, 4><<<B, KF_NTT, sm, st>>>(a); break;
-        case 9: kbf_dir<1, 4><<<B, KF_NTT, sm, st>>>(a); break;
-        case 16: kbf_dir<0, 8><<<B, KF_NTT, sm, st>>>(a); break;
-        default: kbf_dir<1, 8><<<B, KF_NTT, sm, st>>>(a); break;
+        case 2: kbf_dir<0, 1, SRC><<<B, KF_NTT, sm, st>>>(a, pass, tm); break;
+        case 3: kbf_dir<1, 1, SRC><<<B, KF_NTT, sm, st>>>(a, pass, tm); break;
+        case 4: kbf_dir<0, 2, SRC><<<B, KF_NTT, sm, st>>>(a, pass, tm); break;
+        case 5: kbf_dir<1, 2, SRC><<<B, KF_NTT, sm, st>>>(a, pass, tm); break;
+        case 8: kbf_dir<0, 4, SRC><<<B, KF_NTT, sm, st>>>(a, pass, tm); break;
+        case 9: kbf_dir<1, 4, SRC><<<B, KF_NTT, sm, st>>>(a, pass, tm); break;
+        case 16: kbf_dir<0, 8, SRC><<<B, KF_NTT, sm, st>>>(a, pass, tm); break;
+        default: kbf_dir<1, 8, SRC><<<B, KF_NTT, sm, st>>>(a, pass, tm); break;
     }
+}
+void launch_kbf_dir(int kind, int pass, bool tma, const BatchArgs& a, const CUtensorMap& tm, int B, int m, cudaStream_t st) {
+    if (tma) launch_kbf_dir_src<1>(kind, pass, a, tm, B, m, st);
+    else launch_kbf_dir_src<0>(kind, pass, a, tm, B, m, st);
+}
+
+template <int KIND, int NRP, int SRC>
+int kbf_configure() {
+    IPM_CUDA_OK(cudaFuncSetAttribute(kbf_dir<KIND, NRP, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)kf_smem_bytes(32 * NRP, 2 * KB_NT)));
+    return IPM_OK;
+}
+template <int NRP>
+int kbf_configure_nrp() {
+    IPM_TRY((kbf_configure<0, NRP, 0>())); IPM_TRY((kbf_configure<1, NRP, 0>()));
+    IPM_TRY((kbf_configure<0, NRP, 1>())); IPM_TRY((kbf_configure<1, NRP, 1>()));
+    return IPM_OK;
 }
 
 template <int NPL>
@@ -577,31 +550,32 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
     g.C = w.M; g.ldc = w.ldm; g.strideC = (int64_t)m * w.ldm;
     g.rowsP = m; g.rowsQ = m; g.K = n; g.lower_only = 1; g.active = a.active;
     // 3-pass iteration (ipm_batched_fused.cuh) when one CTA can hold a column strip of A_i
-    // (not const: a straggler restart switches the rest of the solve to the literal six-pass iteration)
-    bool fused = g_allow_fused && m <= KF_MAX_M && (n % 2 == 0) && ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0);
-    static int configured_dev = -1;
-    int dev = 0;
-    IPM_CUDA_OK(cudaGetDevice(&dev));
-    if (configured_dev != dev) {
+    const bool fused = g_opt.fused.load() != 0 && m <= KF_MAX_M && (n % 2 == 0) &&
+                       ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0);
+    const bool tma = fused && g_opt.strip_tma.load() != 0;
+    const bool refine = g_opt.refine.load() != 0;
+    a.refine = refine ? 1 : 0;
+    static DevOnce once;
+    IPM_TRY(once_per_device(once, [&]() -> int {
         IPM_CUDA_OK(cudaFuncSetAttribute(kb_residual<NPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + 8192));
         IPM_CUDA_OK(cudaFuncSetAttribute(kb_residual<NPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + 8192));
         IPM_CUDA_OK(cudaFuncSetAttribute(kb_dir<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
-        IPM_CUDA_OK(cudaFuncSetAttribute(kb_refine_rhs<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + 8192));
-        IPM_CUDA_OK(cudaFuncSetAttribute(kbf_dir<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kf_smem_bytes(256, 1024)));
-        IPM_CUDA_OK(cudaFuncSetAttribute(kbf_dir<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kf_smem_bytes(256, 1024)));
-        IPM_CUDA_OK(cudaFuncSetAttribute(kbf_dir<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kf_smem_bytes(128, 1024)));
-        IPM_CUDA_OK(cudaFuncSetAttribute(kbf_dir<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kf_smem_bytes(128, 1024)));
-        IPM_CUDA_OK(cudaFuncSetAttribute(kbf_dir<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kf_smem_bytes(64, 1024)));
-        IPM_CUDA_OK(cudaFuncSetAttribute(kbf_dir<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kf_smem_bytes(64, 1024)));
+        // every NRP instantiation the dispatcher can pick, at the largest n check_shape admits (NRP = 1,
+        // m <= 32, needs more than 48 KB once n >= 466)
+        IPM_TRY(kbf_configure_nrp<1>()); IPM_TRY(kbf_configure_nrp<2>());
+        IPM_TRY(kbf_configure_nrp<4>()); IPM_TRY(kbf_configure_nrp<8>());
         IPM_CUDA_OK(cudaFuncSetAttribute(k_trsv_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
         IPM_CUDA_OK(cudaFuncSetAttribute(k_trsv_batched_inv, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)trsv_batched_inv_smem(32 * TRSVI_MAX_BLK)));
-        configured_dev = dev;
-    }
+        return IPM_OK;
+    }));
+    CUtensorMap tmapA;
+    memset(&tmapA, 0, sizeof(tmapA));
+    if (tma) IPM_TRY(kf_make_strip_tmap(&tmapA, a.A, B, m, n, 32 * kf_nrp(m)));
     auto join = [&](int lp0, int cnt) {             // LPs lp0 .. lp0+cnt-1 enter the loop
         kb_init<<<cnt, 256, 0, st>>>(a, fused ? 2 : 1, lp0);
         count_launch();
-        if (fused) {
+        if (fused && !tma) {
             const int nstrips = ceil_div(n, KF_W);
             kbf_repack<<<dim3(nstrips, cnt), 256, 0, st>>>(a, 32 * kf_nrp(m), nstrips, lp0);
             count_launch();
@@ -626,58 +600,29 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
     } else {
         join(0, B);
     }
-    count_launch();
     // The host reads the "LPs still active" counter of check k only after check k+1 has been enqueued, so the
     // GPU never idles on the host round trip; the price is one empty iteration (every kernel skips inactive LPs)
-    // after the last LP has converged.
+    // after the last LP has converged.  Every LP is bounded by max_iter, so the loop is.
     unsigned* nact_base = a.n_active;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     IPM_CUDA_OK(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
     IPM_CUDA_OK(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
     struct EvGuard { cudaEvent_t* e; ~EvGuard() { cudaEventDestroy(e[0]); cudaEventDestroy(e[1]); } } ev_guard{ev};
     int it = 0, bodies = 0;
-    // Straggler restart.  The four-pass iteration and the literal one round differently, and in the ill-conditioned
-    // last iterations of the normal equations that can decide whether an LP converges or gets trapped at the
-    // boundary with step lengths near zero (benchmark LP 16893: 3527 iterations four-pass, 17 six-pass, 18 in the
-    // CPU oracle; all others of 65536 within +-1).  One trapped LP keeps the whole lockstep loop alive at launch
-    // latency.  So: once half of the batch has finished (lockstep iteration it_half) an LP gets
-    // max(slack, it_half/2) more iterations; whatever is still running then is restarted from the starting point
-    // under the literal six-pass iteration (= the reference's own order of operations, main.py:725-751).  An LP the
-    // literal iteration cannot finish within it_half + max(slack, it_half/2) iterations either (the CPU port of it
-    // stalls on LP 31186, whatever the start) is restarted a second time with a refined corrector, and stopped with
-    // status max_iter if 2 it_half + slack iterations of that do not finish it: the loop is bounded.
-    int it_half = -1, restart_at = -1, it_last_join = 0, stop_at = -1, allowance = 0, stage = 0;
-    bool refine = false;                        // restarted LPs: corrector with one step of iterative refinement
     bool all_joined[2] = {true, true};          // per check slot: had every chunk joined when the check was enqueued?
     bool joined_pending = false;                // a chunk joined after the last check was enqueued
+    const bool small_m = m <= 32 * TRSVI_MAX_BLK;
+    auto launch_trsv = [&](const TrsvBatchedArgs& t) {
+        if (small_m) k_trsv_batched_inv<<<B, TRSVB_NT, trsv_batched_inv_smem(m), st>>>(t);
+        else k_trsv_batched<<<B, TRSVB_NT, trsv_batched_smem(m), st>>>(t);
+        count_launch();
+    };
     for (;; ++it) {
         const int slot = it & 1;
         if (arr && it > 0) {
             const int before = arr->next;
             IPM_TRY(join_landed(false));
-            if (arr->next != before) { joined_pending = true; it_last_join = it; }
-        }
-        if (stage == 0 && fused && restart_at > 0 && it >= restart_at) {
-            // stage 1: back to the starting point, literal six-pass iteration from here on
-            kb_restart<<<B, 256, 0, st>>>(a, it_half);
-            count_launch();
-            fused = false;
-            stage = 1;
-            allowance = it_half + std::max(g_restart_slack, it_half / 2);      // iterations a restarted LP may take
-            stop_at = it + allowance;
-        } else if (stage == 1 && it >= stop_at) {
-            // stage 2: what the literal iteration could not finish either restarts once more, now with one step of
-            // iterative refinement of the corrector per iteration (kb_refine_rhs)
-            kb_restart<<<B, 256, 0, st>>>(a, allowance - 2);
-            count_launch();
-            refine = true;
-            stage = 2;
-            allowance = 2 * it_half + g_restart_slack;
-            stop_at = it + allowance;
-        } else if (stage == 2 && it >= stop_at) {
-            kb_stop_stragglers<<<ceil_div(B, 256), 256, 0, st>>>(a, B, allowance - 2);
-            count_launch();
-            stage = 3;
+            if (arr->next != before) joined_pending = true;
         }
         const bool counted_join = joined_pending;       // those LPs pass through this iteration's check first
         joined_pending = false;
@@ -701,19 +646,11 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
                     // solves): wait for it, let it join, and send it through the next check before any body runs
                     if (arr->next < arr->nchunks) IPM_TRY(join_landed(true));
                     joined_pending = true;
-                    it_last_join = it;
                     continue;
                 }
             }
             ++bodies;
             if (g_prof.enabled) g_prof.lp_iterations += cnt;
-            if (fused && g_restart_slack > 0 && it_half < 0 && all_joined[slot ^ 1] && 2 * (int64_t)cnt <= B) {
-                it_half = it;
-                // LPs of a chunk that joined at lockstep iteration j are only due around j + (their own count):
-                // it_half (an over-estimate of that count when the joins were staggered) + slack after the last join
-                restart_at = std::max(it_half + std::max(g_restart_slack, it_half / 2),
-                                      it_last_join + it_half + g_restart_slack);
-            }
         }
         g_prof.segment(st);
         IPM_TRY((dmma_syrk_auto<0>(g, B, st)));
@@ -729,21 +666,26 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
         t.active = a.active;
         if (fused) t.out = a.dy;           // the right-hand side survives: the corrector's is built on top of it
         for (int kind = 0; kind < 2; ++kind) {
-            if (!fused || kind == 0) kb_rhs<NPL><<<B, KB_NT, smem_w, st>>>(a, kind);
-            if (m <= 32 * TRSVI_MAX_BLK) k_trsv_batched_inv<<<B, TRSVB_NT, trsv_batched_inv_smem(m), st>>>(t);
-            else k_trsv_batched<<<B, TRSVB_NT, trsv_batched_smem(m), st>>>(t);
-            if (!fused && refine && kind == 1) {
-                kb_refine_rhs<NPL><<<B, KB_NT, smem_res, st>>>(a);                 // a.dy = -rb - A dx
-                TrsvBatchedArgs t2 = t;
-                t2.v = a.dy; t2.out = nullptr;
-                if (m <= 32 * TRSVI_MAX_BLK) k_trsv_batched_inv<<<B, TRSVB_NT, trsv_batched_inv_smem(m), st>>>(t2);
-                else k_trsv_batched<<<B, TRSVB_NT, trsv_batched_smem(m), st>>>(t2);
-                kb_add_refinement<<<B, 256, 0, st>>>(a);                           // a.rhs (= dy) += ddy
-                count_launch(3);
+            if (!fused || kind == 0) {
+                kb_rhs<NPL><<<B, KB_NT, smem_w, st>>>(a, kind);
+                count_launch();
             }
-            if (!fused) kb_dir<NPL><<<B, KB_NT, smem_col, st>>>(a, kind);
-            else launch_kbf_dir(kind, a, B, m, st);
-            count_launch((fused && kind == 1) ? 2 : 3);
+            launch_trsv(t);
+            if (!fused) kb_dir<NPL><<<B, KB_NT, smem_col, st>>>(a, kind, 0);
+            else launch_kbf_dir(kind, 0, tma, a, tmapA, B, m, st);
+            count_launch();
+        }
+        if (refine) {
+            // LPs whose corrector asked for a refinement (flag FLAG_REFINE; about one in fifty per solve): delta is in
+            // a.rhs (fused) / a.dy (six-pass); dy += M^-1 delta on the same factor, then the corrector pass again
+            TrsvBatchedArgs t2 = t;
+            t2.only_flag = FLAG_REFINE; t2.accumulate = 1;
+            if (fused) { t2.v = a.rhs; t2.out = a.dy; }
+            else { t2.v = a.dy; t2.out = a.rhs; }
+            launch_trsv(t2);
+            if (!fused) kb_dir<NPL><<<B, KB_NT, smem_col, st>>>(a, 1, 1);
+            else launch_kbf_dir(1, 1, tma, a, tmapA, B, m, st);
+            count_launch();
         }
         g_prof.end_phase(PH_SOLVE, st);
         IPM_TRY(launch_check());
@@ -762,7 +704,7 @@ int solve_on_device(int B, int m, int n, const double* A_d, const double* b_d, c
     w.h_nact = h_nact;
     w.a.A = A_d; w.a.b = b_d; w.a.c = c_d;
     w.a.tol = tol; w.a.eta = 0.91; w.a.max_iter = max_iter;
-    w.a.fresh_every = g_fresh_every;
+    w.a.fresh_every = g_opt.fresh_every.load();
     const double tau = 1e-30;
     if (n <= 512) IPM_TRY(run_batched<8>(w, B, m, n, tau, st, iterations_run, arr));
     else IPM_TRY(run_batched<16>(w, B, m, n, tau, st, iterations_run, arr));
@@ -787,15 +729,17 @@ extern "C" {
 
 int ipm_batched_set_variant(int three_pass, int refresh_every) {
     if (refresh_every < 0) return IPM_ERR_ARG;
-    g_allow_fused = three_pass != 0;
-    g_fresh_every = refresh_every;
+    g_opt.fused.store(three_pass != 0);
+    g_opt.fresh_every.store(refresh_every);
     return IPM_OK;
 }
 
-int ipm_batched_set_straggler_restart(int slack) {
-    if (slack < 0) return IPM_ERR_ARG;
-    g_restart_slack = slack;
-    return IPM_OK;
+int ipm_batched_set_option(int option, int value) {
+    switch (option) {
+        case IPM_BOPT_REFINE: g_opt.refine.store(value != 0); return IPM_OK;
+        case IPM_BOPT_STRIP_TMA: g_opt.strip_tma.store(value != 0); return IPM_OK;
+        default: return IPM_ERR_ARG;
+    }
 }
 
 int ipm_profile_enable(int on) {
@@ -832,7 +776,9 @@ int ipm_syrk_batched_d(int device_ordinal, int B, int m, int n, const double* A_
 int ipm_potrf_batched_d(int device_ordinal, int B, int m, double* M_d, int64_t ldm, int64_t strideM,
                         double pivot_rel_thresh, int* n_fixed_total) {
     if (!M_d) return IPM_ERR_ARG;
-    if (B <= 0 || m <= 0 || ldm < m || (ldm & 1) || strideM < (int64_t)m * ldm) return IPM_ERR_SHAPE;
+    if (B <= 0 || m <= 0 || ldm < m || (ldm & 1) || (strideM & 1) || strideM < (int64_t)m * ldm ||
+        (reinterpret_cast<uintptr_t>(M_d) & 15))
+        return IPM_ERR_SHAPE;          // rows must start on 16-byte boundaries (vector loads, bulk prefetch)
     IPM_CUDA_OK(cudaSetDevice(device_ordinal));
     double* scal = nullptr;
     IPM_CUDA_OK(cudaMalloc(&scal, (size_t)B * S_COUNT * sizeof(double)));
@@ -870,7 +816,11 @@ int64_t ipm_batched_workspace_bytes(int B, int m, int n) {
 int ipm_solve_batched_dense_d(int device_ordinal, int B, int m, int n, const double* A_d, const double* b_d,
                               const double* c_d, double tol, int max_iter, double* obj_d, int* iters_d,
                               int* status_d, double* x_d, void* work_d, int* iterations_run) {
-    if (!A_d || !b_d || !c_d) return IPM_ERR_ARG;
+    if (!A_d || !b_d || !c_d || max_iter < 0) return IPM_ERR_ARG;
+    if (work_d && (reinterpret_cast<uintptr_t>(work_d) & 15)) {
+        g_last_error = "work_d must be 16-byte aligned";
+        return IPM_ERR_ARG;
+    }
     IPM_TRY(check_shape(B, m, n));
     IPM_CUDA_OK(cudaSetDevice(device_ordinal));
     void* own = nullptr;
@@ -937,9 +887,13 @@ int ipm_release_cached(void) {
 int ipm_solve_batched_dense(int device_ordinal, int B, int m, int n, const double* A, const double* b,
                             const double* c, double tol, int max_iter, double* obj, int* iters, int* status,
                             double* x) {
-    if (!A || !b || !c) return IPM_ERR_ARG;
+    if (!A || !b || !c || max_iter < 0) return IPM_ERR_ARG;
     IPM_TRY(check_shape(B, m, n));
     if (device_ordinal < 0 || device_ordinal >= 16) return IPM_ERR_ARG;
+    // one solve at a time per device through this entry point: the staging buffers and streams of a device are
+    // shared by every caller (distinct devices run concurrently from distinct threads)
+    static std::mutex host_ctx_mu[16];
+    std::lock_guard<std::mutex> host_ctx_lock(host_ctx_mu[device_ordinal]);
     IPM_CUDA_OK(cudaSetDevice(device_ordinal));
     // The whole batch gets device buffers; it is copied in chunks on a copy stream (a small first chunk: its copy
     // is the only one nothing can hide) and ONE lockstep loop runs from the moment the first chunk has landed:

@@ -12,8 +12,19 @@
 //     q = A dx and u:   rb += ap q,  rc += ad (u + ds)   (exact identities; check_optimality main.py:169-173 is
 //     re-evaluated from scratch by kb_residual for every LP these recurrences declare converged),
 //     then d = x/s and the predictor operand w = d (rc - (x s)/x) for the next assembly.
+//     Conditional refinement (a.refine): the reference solves the unreduced system, whose second block row IS
+//     A dx = -rb (main.py:13-21); the normal equations satisfy it only as well as the factor of M allows, and once
+//     max d / min d passes 1e19 that is not well enough for |rb| to keep falling - an LP that has not met
+//     check_optimality by then stays trapped at the boundary (generator LPs 16893, 31186).  q = A dx is already
+//     here, so delta = -rb - q is free: when |delta| > |rb| - the step would not reduce the primal residual at
+//     all - the LP is not updated; delta goes to a.rhs, the LP is flagged FLAG_REFINE, the host's next two launches
+//     (triangular solve dy += M^-1 delta, then this kernel again with pass = 1, both for flagged LPs only) redo
+//     the corrector from the refined dy.  On the CPU restatement the rule fires 0.02 times per LP and leaves all
+//     65536 generator LPs at 15-20 iterations (tests/golden/batch_256x512_oracle.npz).
 // With the predictor right-hand side (kb_rhs, one pass) an iteration reads A four times instead of six.
 #pragma once
+#include <cuda.h>      // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, no -lcuda)
+
 #include "common.cuh"
 #include "dmma_ws.cuh"
 
@@ -32,6 +43,8 @@ struct BatchArgs {
     const double* b;   // [B][m]
     const double* c;   // [B][n]
     double *x, *s, *rc, *d, *w, *rcx, *dxa, *dsa;      // [B][n]
+    double *dxc, *dsc;                                 // [B][n] corrector direction (the predictor's stays intact
+                                                       // for a refinement pass)
     double *y, *rb, *dy, *rhs;                         // [B][m]
     double* scal;      // [B][S_COUNT]
     int* active;       // [B]   0 = finished, 1 = iterating, 2 = to be checked from scratch (3-pass path)
@@ -42,7 +55,10 @@ struct BatchArgs {
     int max_iter;
     int fresh_every;   // 3-pass path: residuals are re-evaluated from scratch every fresh_every-th iteration (0 = only
                        // when the recurrences report convergence)
+    int refine;        // 1: conditional refinement of the corrector (see kbf_dir / kb_dir), 0: off
 };
+constexpr int FLAG_REFINE = 3;    // active[] value between the corrector pass that asks for a refinement and the one that
+                                  // applies it
 
 constexpr int KF_NBUF = 5;                  // strip buffers: row sums of s-2, s-1 (pending), column sums of s, loads ahead
 constexpr int KF_AHEAD = KF_NBUF - 2;       // strips in flight: one CTA per SM keeps 3 x 32 KB on the wire
@@ -63,19 +79,29 @@ inline size_t kf_smem_bytes(int m, int n) {
 // NRP = rows per thread is a template parameter (rows are padded to 32 NRP with zeros), which turns every
 // shared-memory offset of the inner loops into an immediate: the first version was issue-bound on index
 // arithmetic (ncu: 300 warp instructions per strip and warp, 75 % of them integer).
-template <int KIND, int NRP>
-__global__ void __launch_bounds__(KF_NTT, 1) kbf_dir(const BatchArgs a) {
+// SRC = 1 (default): the strips come straight from the caller's row-major A[B][m][n] through a 3-D tensor map
+// (box 16 columns x MR rows x 1 LP, cp.async.bulk.tensor -> UTMALDG; rows >= m and columns >= n are zero-filled by
+// the hardware), SRC = 0: from a strip-major copy of A made once per solve by kbf_repack (one untiled bulk copy per
+// strip, UBLKCP) - kept for A/B measurements, it costs a second copy of A in HBM and 4.4 ms per 8192 LPs.
+template <int KIND, int NRP, int SRC>
+__global__ void __launch_bounds__(KF_NTT, 1) kbf_dir(const BatchArgs a, const int pass,
+                                                     const __grid_constant__ CUtensorMap tmapA) {
     constexpr int MR = 32 * NRP;                  // padded rows
     constexpr int SB = MR * KF_W;                 // doubles per strip buffer
-    extern __shared__ __align__(16) double smem[];
+    extern __shared__ __align__(128) double smem_kf[];        // strip buffers first: TMA destinations, 128-byte aligned
     __shared__ double sh[32];
     __shared__ double s_val[4];
     __shared__ __align__(8) uint64_t full[KF_NBUF], pfull[4], efull[4];
     const int lp = blockIdx.x;
-    if (a.active[lp] == 0) return;
+    {
+        const int flag = a.active[lp];
+        if (pass == 0 ? (flag == 0) : (flag != FLAG_REFINE)) return;
+    }
     const int m = a.m, n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int mr = MR;
-    double* strip = smem;                         // [KF_NBUF][MR][16]
+    double* const dxo = (KIND == 0) ? a.dxa : a.dxc;       // where this pass leaves its direction
+    double* const dso = (KIND == 0) ? a.dsa : a.dsc;
+    double* strip = smem_kf;                      // [KF_NBUF][MR][16]
     double* dys = strip + KF_NBUF * SB;           // [MR]   dy
     double* q1s = dys + MR;                       // [MR]   A e1
     double* q2s = q1s + MR;                       // [MR]   A e2 (kind 0)
@@ -91,7 +117,7 @@ __global__ void __launch_bounds__(KF_NTT, 1) kbf_dir(const BatchArgs a) {
 
     // strip s of this LP is one contiguous block of the strip-major copy: a single bulk (TMA) copy per strip,
     // completion signalled on the buffer's mbarrier
-    const double* At = a.At + (size_t)lp * nstrips * SB;
+    const double* At = (SRC == 0) ? a.At + (size_t)lp * nstrips * SB : nullptr;
     if (tid == 0) {
         for (int k = 0; k < KF_NBUF; ++k) mbar_init(full + k, 1);
         for (int k = 0; k < 4; ++k) { mbar_init(pfull + k, KF_NT / 32); mbar_init(efull + k, 1); }
@@ -101,9 +127,16 @@ __global__ void __launch_bounds__(KF_NTT, 1) kbf_dir(const BatchArgs a) {
     auto issue = [&](int sidx, int boff_d, int slot) {     // thread 0 only
         const uint32_t bar = smem_u32(full + slot);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(SB * 8)) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(strip + boff_d)), "l"(At + (size_t)sidx * SB), "r"((uint32_t)(SB * 8)), "r"(bar)
-                     : "memory");
+        if (SRC == 0) {
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(strip + boff_d)), "l"(At + (size_t)sidx * SB), "r"((uint32_t)(SB * 8)), "r"(bar)
+                         : "memory");
+        } else {
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                         ::"r"(smem_u32(strip + boff_d)), "l"(reinterpret_cast<uint64_t>(&tmapA)), "r"(sidx * KF_W), "r"(0),
+                           "r"(lp), "r"(bar)
+                         : "memory");
+        }
     };
     if (tid == 0) {
         for (int k = 0; k < KF_AHEAD && k < nstrips; ++k) issue(k, k * SB, k);
@@ -166,8 +199,8 @@ __global__ void __launch_bounds__(KF_NTT, 1) kbf_dir(const BatchArgs a) {
                 if (KIND == 0) { e1 = g3 * (dxi * dsi); e2 = g3; }
                 else e1 = dxi;
                 if (col < n) {
-                    a.dxa[on + col] = dxi;          // kind 1: the final direction replaces the predictor's
-                    a.dsa[on + col] = dsi;
+                    dxo[on + col] = dxi;
+                    dso[on + col] = dsi;
                     if (KIND == 1) a.w[on + col] = u + dsi;       // A^T dy + ds: change of rc per unit dual step
                 } else {
                     e1 = e2 = 0.0;
@@ -239,7 +272,7 @@ __global__ void __launch_bounds__(KF_NTT, 1) kbf_dir(const BatchArgs a) {
     // ratio test over all columns (main.py:305-322)
     double minp = 1.0, mind = 1.0;
     for (int k = tid; k < n; k += KF_NTT) {
-        const double dxi = a.dxa[on + k], dsi = a.dsa[on + k];
+        const double dxi = dxo[on + k], dsi = dso[on + k];
         if (dxi < 0.0) minp = fmin(minp, -a.x[on + k] / dxi);
         if (dsi < 0.0) mind = fmin(mind, -a.s[on + k] / dsi);
     }
@@ -265,12 +298,34 @@ __global__ void __launch_bounds__(KF_NTT, 1) kbf_dir(const BatchArgs a) {
         const double sm = s_val[2];
         for (int i = tid; i < m; i += KF_NTT) a.rhs[om + i] = a.rhs[om + i] + q1s[i] - sm * q2s[i];
     } else {
+        if (a.refine && pass == 0) {
+            // delta = -rb - A dx against rb (both squared norms in index order: deterministic)
+            double nd2 = 0.0, nr2 = 0.0;
+            for (int i = tid; i < m; i += KF_NTT) {
+                const double r = a.rb[om + i], dl = -r - q1s[i];
+                nd2 += dl * dl;
+                nr2 += r * r;
+            }
+            nd2 = block_red<RED_SUM>(nd2, sh);
+            if (tid == 0) s_val[2] = nd2;
+            nr2 = block_red<RED_SUM>(nr2, sh);
+            if (tid == 0) s_val[3] = (s_val[2] > nr2) ? 1.0 : 0.0;      // NaN compares false: no refinement
+            __syncthreads();
+            if (s_val[3] != 0.0) {
+                for (int i = tid; i < m; i += KF_NTT) a.rhs[om + i] = -a.rb[om + i] - q1s[i];
+                if (tid == 0) {
+                    a.active[lp] = FLAG_REFINE;
+                    scal[S_NREFINE] = scal[S_NREFINE] + 1.0;
+                }
+                return;
+            }
+        }
         ap = fmin(1.0, a.eta * ap);
         ad = fmin(1.0, a.eta * ad);
         double nrc2 = 0.0, xs = 0.0, obj = 0.0, nrb2 = 0.0;
         for (int k = tid; k < n; k += KF_NTT) {
-            const double xn = a.x[on + k] + ap * a.dxa[on + k];
-            const double sn = a.s[on + k] + ad * a.dsa[on + k];
+            const double xn = a.x[on + k] + ap * a.dxc[on + k];
+            const double sn = a.s[on + k] + ad * a.dsc[on + k];
             const double rcn = a.rc[on + k] + ad * a.w[on + k];
             const double dn = xn / sn;
             const double q = (xn * sn) / xn;
@@ -302,7 +357,7 @@ __global__ void __launch_bounds__(KF_NTT, 1) kbf_dir(const BatchArgs a) {
             const int it = a.iters[lp] + 1;
             a.iters[lp] = it;
             // stop candidates (and the iteration cap) are decided by kb_residual on residuals computed from scratch
-            if (!cont || it >= a.max_iter || (a.fresh_every > 0 && it % a.fresh_every == 0)) a.active[lp] = 2;
+            a.active[lp] = (!cont || it >= a.max_iter || (a.fresh_every > 0 && it % a.fresh_every == 0)) ? 2 : 1;
         }
     }
 }
@@ -327,5 +382,35 @@ __global__ void __launch_bounds__(256) kbf_repack(const BatchArgs a, int mr, int
 }
 
 #endif
+
+// 3-D tensor map over the caller's A[B][m][n] (row-major, f64): box = KF_W columns x mr rows x 1 LP.
+inline int kf_make_strip_tmap(CUtensorMap* out, const double* A, int B, int m, int n, int mr) {
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        IPM_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) {
+            g_last_error = "cuTensorMapEncodeTiled is not available from this driver";
+            return IPM_ERR_CUDA;
+        }
+        encode = reinterpret_cast<encode_fn>(fn);
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)n, (cuuint64_t)m, (cuuint64_t)B};
+    const cuuint64_t strides[2] = {(cuuint64_t)n * 8, (cuuint64_t)m * n * 8};       // bytes, dimensions 1 and 2
+    const cuuint32_t box[3] = {(cuuint32_t)KF_W, (cuuint32_t)mr, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(A), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        g_last_error = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")";
+        return IPM_ERR_CUDA;
+    }
+    return IPM_OK;
+}
 
 }  // namespace ipm

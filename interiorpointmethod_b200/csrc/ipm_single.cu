@@ -354,8 +354,9 @@ static int load_sparse(ipm_handle* h, int m, int n, int64_t nnz, const int32_t* 
     const int nseg = from_csc ? n : m, nother = from_csc ? m : n;
     if (m <= 0 || n <= 0 || nnz < 0 || nnz > INT32_MAX || ptr[0] != 0 || ptr[nseg] != nnz)
         return fail(h, IPM_ERR_SHAPE, "bad compressed-sparse header");
+    for (int i = 0; i < nseg; ++i)         // the whole pointer array first: idx is only read inside [0, nnz)
+        if (ptr[i + 1] < ptr[i] || ptr[i + 1] > nnz) return fail(h, IPM_ERR_SHAPE, "pointer array not monotone within [0, nnz]");
     for (int i = 0; i < nseg; ++i) {
-        if (ptr[i + 1] < ptr[i]) return fail(h, IPM_ERR_SHAPE, "pointer array not monotone");
         for (int64_t p = ptr[i]; p < ptr[i + 1]; ++p) {
             if (idx[p] < 0 || idx[p] >= nother) return fail(h, IPM_ERR_SHAPE, "index out of range");
             if (p > ptr[i] && idx[p] <= idx[p - 1])

@@ -250,25 +250,56 @@ def interior_sparse(A, b, c, cTlb, tol: float = 1e-20, device: int = 0, return_r
     return res if return_result else res.objective
 
 
-def interior(A, b, c, tol: float = 1e-20, device: int = 0) -> Result:
+def interior(A, b, c, tol: float = 1e-20, device: int = 0, verbose: bool = True) -> Result:
     """Dense driver (main.py:707-757): A list/ndarray, b and c 1-D, start y=0, cap 50000.
-    The reference prints x, k and the objective and returns None; the Result carries them instead."""
-    return solve(np.asarray(A, dtype=np.float64), b, c, tol=tol, device=device, max_iter=50000, y0_is_one=False)
+    Prints what the reference prints at the end (x, k, objective: main.py:754-757; not its per-iteration lines -
+    the loop runs on the device).  The reference returns None; the Result is returned as well so that callers
+    can use the numbers instead of parsing stdout."""
+    res = solve(np.asarray(A, dtype=np.float64), b, c, tol=tol, device=device, max_iter=50000, y0_is_one=False)
+    if verbose:
+        print("optimal:", res.status == "converged")
+        print("x:\n", res.x)
+        print("k:\n", res.iterations)
+        print("objective function:", res.objective)
+    return res
 
 
 _cache = {}
 
 
+def _fingerprint(A, b, c):
+    """Content check of the cached problem: the values can change in place while the objects stay the same."""
+    import zlib
+    vals = A.data if (_sp is not None and _sp.issparse(A)) else np.asarray(A)
+    h = zlib.crc32(np.ascontiguousarray(vals).view(np.uint8).reshape(-1))
+    h = zlib.crc32(np.ascontiguousarray(np.asarray(b)).view(np.uint8).reshape(-1), h)
+    h = zlib.crc32(np.ascontiguousarray(np.asarray(c)).view(np.uint8).reshape(-1), h)
+    return (np.shape(A), h)
+
+
 def _cached_step(A, b, c, device=0) -> NewtonStep:
-    key = (id(A), id(b), id(c), device)
-    ns = _cache.get("ns") if _cache.get("key") == key else None
-    if ns is None:
-        old = _cache.get("ns")
-        if old is not None:
-            old.close()
-        ns = NewtonStep(A, b, c, device=device)
-        _cache["key"], _cache["ns"] = key, ns
+    """The op-level functions below take (A, b, c) on every call like the reference's do; the problem stays
+    resident on the GPU between calls as long as the caller passes the SAME objects with the SAME contents: the
+    cache entry holds strong references (so ids cannot be recycled by the garbage collector) and is compared by
+    identity and by a CRC of the values (so an in-place edit of b, c or A.data re-uploads)."""
+    ent = _cache.get("entry")
+    fp = _fingerprint(A, b, c)
+    if ent is not None and ent["A"] is A and ent["b"] is b and ent["c"] is c and ent["device"] == device \
+            and ent["fp"] == fp:
+        return ent["ns"]
+    if ent is not None:
+        ent["ns"].close()
+        _cache.pop("entry", None)
+    ns = NewtonStep(A, b, c, device=device)
+    _cache["entry"] = dict(A=A, b=b, c=c, device=device, fp=fp, ns=ns)
     return ns
+
+
+def release_cached_step():
+    """Drop the problem the op-level functions keep resident (and the references to the caller's arrays)."""
+    ent = _cache.pop("entry", None)
+    if ent is not None:
+        ent["ns"].close()
 
 
 def check_optimality(A, b, c, x, y, s, e1, e2, e3, options="sparse", device: int = 0) -> bool:

@@ -158,7 +158,9 @@ def _load_chol_lib():
     so = os.path.join(_HERE, "liboracle_chol.so")
     src = os.path.join(_HERE, "chol_safeguard.c")
     if (not os.path.exists(so)) or os.path.getmtime(so) < os.path.getmtime(src):
-        subprocess.check_call(["gcc", "-O3", "-march=native", "-fopenmp", "-shared", "-fPIC", src, "-o", so, "-lm"])
+        tmp = so + ".tmp%d" % os.getpid()
+        subprocess.check_call(["gcc", "-O3", "-mavx2", "-mfma", "-shared", "-fPIC", src, "-o", tmp, "-lm"])
+        os.replace(tmp, so)            # atomic: processes that mapped the old file keep their copy
     lib = ctypes.CDLL(so)
     lib.oracle_chol_safeguard.restype = ctypes.c_int
     lib.oracle_chol_safeguard.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_double,
@@ -269,8 +271,15 @@ def objective(x, c):
 
 
 # --------------------------------------------------------------------------- one iteration / whole solve
-def newton_iteration(A, b, c, x, y, s, linear="normal", dense=False, tau=PIVOT_TAU, info=None):
-    """One predictor-corrector iteration (main.py:781-805).  Returns new (x, y, s)."""
+def newton_iteration(A, b, c, x, y, s, linear="normal", dense=False, tau=PIVOT_TAU, info=None, refine_thresh=None):
+    """One predictor-corrector iteration (main.py:781-805).  Returns new (x, y, s).
+
+    refine_thresh (normal equations only; what the batched GPU solver does with thresh = 1): the corrector's dy
+    comes from the factored M = A D A^T, and in the last iterations (max d / min d > 1e19) that factor no longer
+    reproduces the primal block row A dx = -rb of the Newton system the reference solves directly (main.py:13-21).
+    When delta = -rb - A dx is LARGER than thresh * |rb| - the step would not reduce the primal residual at all -
+    one step of iterative refinement on the same factor is taken: M ddy = delta, dy += ddy, dx and ds re-formed
+    from the refined dy."""
     rb, rc = residuals(A, b, c, x, y, s)
     r3 = x * s
     if linear == "normal":
@@ -284,6 +293,15 @@ def newton_iteration(A, b, c, x, y, s, linear="normal", dense=False, tau=PIVOT_T
     r4 = r3 + dxa * dsa - sigma * mu * np.ones_like(x)   # main.py:150-152
     if linear == "normal":
         dx, dy, ds = direction_normal(A, L, x, s, rb, rc, r4)
+        if refine_thresh is not None:
+            delta = -rb - A @ dx
+            if np.linalg.norm(delta) > refine_thresh * np.linalg.norm(rb):
+                d = x / s
+                dy = dy + solve_with_factor(L, delta)
+                dx = d * (A.T @ dy) + d * (rc - r4 / x)
+                ds = (-s * dx / x) - (r4 / x)
+                if info is not None:
+                    info["refinements"] = info.get("refinements", 0) + 1
     else:
         dx, dy, ds = direction_kkt(A, x, s, rb, rc, r4, dense=dense)
     ap, ad = full_stepsize(x, s, dx, ds)
@@ -294,7 +312,7 @@ def newton_iteration(A, b, c, x, y, s, linear="normal", dense=False, tau=PIVOT_T
 
 
 def solve(A, b, c, cTlb=0.0, tol=1e-8, max_iter=5000, y0_is_one=True, linear="normal", tau=PIVOT_TAU,
-          start="reference"):
+          start="reference", refine_thresh=None):
     """Whole solve with `interior_sparse` semantics (main.py:760-815) when y0_is_one, `interior`
     semantics (main.py:707-757; cap 50000, y0 = 0) otherwise.
 
@@ -320,7 +338,8 @@ def solve(A, b, c, cTlb=0.0, tol=1e-8, max_iter=5000, y0_is_one=True, linear="no
         warnings.simplefilter("ignore")
         with np.errstate(all="ignore"):
             while continue_flag(A, b, c, x, y, s, tol, tol, tol) and k < max_iter:
-                x, y, s = newton_iteration(A, b, c, x, y, s, linear=linear, dense=dense, tau=tau, info=info)
+                x, y, s = newton_iteration(A, b, c, x, y, s, linear=linear, dense=dense, tau=tau, info=info,
+                                           refine_thresh=refine_thresh)
                 k += 1
     obj = objective(x, c) - float(cTlb)
     if not np.isfinite(obj) or not np.all(np.isfinite(x)):
@@ -329,7 +348,8 @@ def solve(A, b, c, cTlb=0.0, tol=1e-8, max_iter=5000, y0_is_one=True, linear="no
         status = 1
     else:
         status = 0
-    return dict(x=x, y=y, s=s, k=k, obj=float(obj), status=status, pivots_fixed=info.get("pivots_fixed", 0))
+    return dict(x=x, y=y, s=s, k=k, obj=float(obj), status=status, pivots_fixed=info.get("pivots_fixed", 0),
+                refinements=info.get("refinements", 0))
 
 
 # --------------------------------------------------------------------------- synthetic workloads

@@ -1,0 +1,89 @@
+"""TEST INFRASTRUCTURE - freezes the golden tables the batched solver (BASELINE.json configs[4]: generator LPs
+256 x 512, LP i = default_rng(i)) is pinned to.  Not product code.
+
+    python oracle/make_golden_batch.py oracle    FIRST LAST [workers]   -> tests/golden/batch_256x512_oracle.npz
+    python oracle/make_golden_batch.py reference FIRST LAST [workers]   -> tests/golden/batch_256x512_reference.json
+                                                                           (build container only: /root/reference)
+
+oracle   : (k, objective, refinement steps) of oracle.ipm_oracle.solve(linear="normal", refine_thresh=1.0) - the
+           elimination and the refinement rule the GPU runs - for every seed of the range.  Ranges are merged into
+           the existing file, so the table can be extended.
+reference: (k, objective) of the UNMODIFIED reference's dense driver `interior` (main.py:707-757: dense (m+2n) KKT
+           + np.linalg.solve twice per iteration), replayed with its own functions by oracle/ref_harness.py, for
+           seeds FIRST..LAST-1 plus the three seeds with a history (7466, 16893, 31186).
+"""
+import json
+import os
+import sys
+import time
+
+os.environ.setdefault("OMP_NUM_THREADS", "1")
+os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, "tests", "golden")
+M, N, TOL, CAP = 256, 512, 1e-8, 150
+
+
+def work_oracle(seed):
+    from oracle import ipm_oracle as O
+    A, b, c = O.synthetic_dense_lp(M, N, seed)
+    r = O.solve(A, b, c, tol=TOL, max_iter=CAP, y0_is_one=False, linear="normal", refine_thresh=1.0)
+    return seed, r["k"], r["obj"], r["refinements"], r["status"]
+
+
+def work_reference(seed):
+    from oracle import ipm_oracle as O
+    from oracle import ref_harness as rh
+    rh.load_reference()
+    A, b, c = O.synthetic_dense_lp(M, N, seed)
+    with rh.quiet():
+        r = rh.replay_interior_dense(A, b, c, tol=TOL)
+    return seed, r["k"], r["obj"]
+
+
+def main():
+    import multiprocessing as mp
+
+    import numpy as np
+    mode, lo, hi = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+    workers = int(sys.argv[4]) if len(sys.argv) > 4 else max(1, (os.cpu_count() or 2) - 1)
+    t0 = time.time()
+    if mode == "oracle":
+        path = os.path.join(GOLD, "batch_256x512_oracle.npz")
+        size = max(hi, 65536)
+        k = np.full(size, -1, np.int16)
+        obj = np.full(size, np.nan)
+        ref = np.zeros(size, np.int8)
+        if os.path.exists(path):
+            old = np.load(path)
+            k[:len(old["k"])] = old["k"]; obj[:len(old["k"])] = old["obj"]; ref[:len(old["k"])] = old["refinements"]
+        with mp.Pool(workers) as pool:
+            for seed, kk, oo, rr, st in pool.imap_unordered(work_oracle, range(lo, hi), chunksize=32):
+                k[seed], obj[seed], ref[seed] = (kk if st == 0 else -2), oo, min(rr, 127)
+                if st != 0 or kk > 21:
+                    print("OUTLIER seed %d k %d status %d" % (seed, kk, st), flush=True)
+        np.savez_compressed(path, k=k, obj=obj, refinements=ref, m=M, n=N, tol=TOL,
+                            how="oracle.ipm_oracle.solve(linear='normal', refine_thresh=1.0, y0_is_one=False)")
+        done = k[k > 0]
+        print("oracle table: %d seeds, k histogram %s, %d s" % (done.size, dict(zip(*np.unique(done, return_counts=True))),
+                                                             time.time() - t0))
+    else:
+        path = os.path.join(GOLD, "batch_256x512_reference.json")
+        d = json.load(open(path)) if os.path.exists(path) else {"meta": {}, "seeds": {}}
+        seeds = [s for s in list(range(lo, hi)) + [7466, 16893, 31186] if str(s) not in d["seeds"]]
+        with mp.Pool(workers) as pool:
+            for seed, kk, oo in pool.imap_unordered(work_reference, seeds, chunksize=4):
+                d["seeds"][str(seed)] = [int(kk), float(oo)]
+        import numpy
+        import scipy
+        d["meta"] = dict(numpy=numpy.__version__, scipy=scipy.__version__, tol=TOL, m=M, n=N,
+                         semantics="UNMODIFIED reference `interior` replayed by oracle/ref_harness.replay_interior_dense "
+                                   "(main.py:718-751); value = [k, objective]")
+        d["seeds"] = dict(sorted(d["seeds"].items(), key=lambda kv: int(kv[0])))
+        json.dump(d, open(path, "w"), indent=0)
+        print("reference table: %d seeds, %d s" % (len(d["seeds"]), time.time() - t0))
+
+
+if __name__ == "__main__":
+    main()

@@ -20,11 +20,21 @@ import os
 import sys
 import types
 
+# The reference tree in the build container; on the GPU box (no /root/reference) the verbatim copy of its two
+# solver modules that `__graft_entry__.build()` places in the git-ignored oracle/_ref/ (it travels like a built .so).
+_HERE = os.path.dirname(os.path.abspath(__file__))
 REFERENCE_ROOT = "/root/reference"
+if not os.path.isfile(os.path.join(REFERENCE_ROOT, "main.py")) and os.path.isfile(os.path.join(_HERE, "_ref", "main.py")):
+    REFERENCE_ROOT = os.path.join(_HERE, "_ref")
 
 
 def reference_available() -> bool:
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "main.py"))
+
+
+def reference_has_benchmarks() -> bool:
+    """The .mat files only exist in the build container's reference tree (the loaders are cwd-relative)."""
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "benchmarks"))
 
 
 _ref = None
@@ -135,6 +145,17 @@ def replay_interior_dense(A, b, c, tol=1e-8, max_iter=50000):
             k += 1
     obj = float(np.sum(x * c))
     return dict(x=x, y=y, s=s, k=k, obj=obj)
+
+
+def call_interior_dense(A, b, c, tol=1e-8):
+    """The reference's dense driver itself (main.py:707-757), output silenced; it returns None (prints x, k,
+    objective), so this is for timing the unmodified code path - values come from replay_interior_dense."""
+    import warnings
+
+    ref_main, _ = load_reference()
+    with quiet(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return ref_main.interior(A, b, c, tol=tol)
 
 
 def call_interior_sparse(A, b, c, cTlb, tol=1e-8):

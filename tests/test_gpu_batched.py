@@ -91,7 +91,8 @@ def test_batched_device_entry_point_large_batch_properties(ipm):
     assert (obj1[::97] <= np.array(xh_obj) + 1e-6).all()
 
 
-@pytest.mark.parametrize("m,n,B", [(256, 512, 64), (48, 100, 40), (130, 70, 9), (200, 1000, 5)])
+@pytest.mark.parametrize("m,n,B", [(256, 512, 64), (48, 100, 40), (130, 70, 9), (200, 1000, 5), (32, 512, 6),
+                                   (16, 1024, 3)])
 def test_three_pass_iteration_matches_six_pass(ipm, m, n, B):
     """The 3-pass iteration (right-hand sides by linearity, residuals by recurrence, from-scratch check before an LP
     is declared finished) against the 6-pass one that evaluates main.py:725-751 literally: same iteration count
@@ -132,3 +133,60 @@ def test_three_pass_refresh_keeps_ill_conditioned_lp_on_track(ipm):
     assert np.abs(k3.astype(int) - k6.astype(int)).max() <= 1
     assert (np.abs(o3 - o6) <= 1e-7 * np.abs(o6)).all()     # rb is at its noise floor here: 1e-8 is not attainable
 
+
+
+@pytest.mark.parametrize("m,n,B", [(256, 512, 48), (100, 300, 7), (16, 1024, 3), (255, 510, 5)])
+def test_tensor_map_strips_equal_strip_major_copy(ipm, m, n, B):
+    """The four-pass direction kernels fed through the 3-D tensor map over the caller's A (UTMALDG; rows >= m and
+    columns >= n zero-filled by the hardware) against the same kernels fed from the strip-major copy: the
+    arithmetic is identical, so the results are bitwise equal."""
+    from interiorpointmethod_b200 import _lib
+    from interiorpointmethod_b200.batch import solve_batched_host
+    lib = _lib.load()
+    A, b, c = ipm.synthetic_dense_batch(3, B, m, n)
+    try:
+        lib.ipm_batched_set_option(_lib.BOPT_STRIP_TMA, 0)
+        o0, k0, s0, x0 = solve_batched_host(A, b, c, tol=1e-8, want_x=True)
+    finally:
+        lib.ipm_batched_set_option(_lib.BOPT_STRIP_TMA, 1)
+    o1, k1, s1, x1 = solve_batched_host(A, b, c, tol=1e-8, want_x=True)
+    assert (s0 == 0).all() and (s1 == 0).all()
+    assert np.array_equal(k0, k1) and np.array_equal(o0, o1) and np.array_equal(x0, x1)
+
+
+def test_whole_benchmark_batch_against_frozen_tables(ipm):
+    """All 8192 LPs of BASELINE.json configs[4] (generator seeds 0..8191) in one batched solve against the frozen
+    tables: every LP converges; iteration count within +-1 and objective within 1e-8 relative of the oracle's
+    normal-equations iteration with the same refinement rule (tests/golden/batch_256x512_oracle.npz, all seeds)
+    and of the UNMODIFIED reference's `interior` (tests/golden/batch_256x512_reference.json, seeds 0..511)."""
+    import json
+    import os
+
+    import torch
+    from interiorpointmethod_b200.batch import DeviceBatch
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    orc = np.load(os.path.join(gold, "batch_256x512_oracle.npz"))
+    ref = {int(k): v for k, v in json.load(open(os.path.join(gold, "batch_256x512_reference.json")))["seeds"].items()}
+    B, m, n = 8192, 256, 512
+    A = torch.empty((B, m, n), dtype=torch.float64, pin_memory=True)
+    b = torch.empty((B, m), dtype=torch.float64)
+    c = torch.empty((B, n), dtype=torch.float64)
+    ipm.synthetic_dense_batch(0, B, m, n, out_A=A.numpy(), out_b=b.numpy(), out_c=c.numpy(), threads=16)
+    dev = torch.device("cuda:0")
+    db = DeviceBatch(A.to(dev), b.to(dev), c.to(dev))
+    nit = db.solve(tol=1e-8)
+    obj, it, st = db.obj.cpu().numpy(), db.iters.cpu().numpy().astype(int), db.status.cpu().numpy()
+    assert (st == 0).all(), np.nonzero(st)[0][:10]
+    assert nit == it.max() <= 21
+    ko, oo = orc["k"][:B].astype(int), orc["obj"][:B]
+    assert (ko > 0).all()
+    bad = np.nonzero(np.abs(it - ko) > 1)[0]
+    assert bad.size == 0, [(int(i), int(it[i]), int(ko[i])) for i in bad[:10]]
+    rel = np.abs(obj - oo) / np.maximum(1.0, np.abs(oo))
+    assert rel.max() <= 1e-8, (int(rel.argmax()), rel.max())
+    seeds = np.array(sorted(s for s in ref if s < B))
+    assert seeds.size >= 512
+    kr = np.array([ref[s][0] for s in seeds])
+    orf = np.array([ref[s][1] for s in seeds])
+    assert np.abs(it[seeds] - kr).max() <= 1
+    assert (np.abs(obj[seeds] - orf) <= 1e-8 * np.maximum(1.0, np.abs(orf))).all()

@@ -217,3 +217,44 @@ def test_oracle_kkt_matches_reference_on_the_straggler_lps(seed, dense_results):
     r = orc.solve(A, b, c, tol=1e-8, max_iter=50000, y0_is_one=False, linear="kkt")
     assert r["status"] == 0 and r["k"] == g["k"]
     assert abs(r["obj"] - g["obj"]) <= 1e-10 * abs(g["obj"])
+
+
+# ------------------------------------------------------------------------------ batch tables (round 2)
+def _batch_tables():
+    import json
+    import os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    ref = {int(k): v for k, v in json.load(open(os.path.join(gold, "batch_256x512_reference.json")))["seeds"].items()}
+    tab = np.load(os.path.join(gold, "batch_256x512_oracle.npz"))
+    return ref, tab["k"].astype(int), tab["obj"], tab["refinements"].astype(int)
+
+
+def test_batch_tables_are_complete_and_agree_with_the_unmodified_reference():
+    """tests/golden/batch_256x512_oracle.npz (oracle, normal equations + the refinement rule, all 65536 generator
+    seeds) against tests/golden/batch_256x512_reference.json (the UNMODIFIED reference's `interior`, seeds 0..511
+    and the three seeds with a history): every LP converges in 15..21 iterations, iteration count within +-1 and
+    objective within 1e-8 relative of the reference on every seed both tables hold."""
+    ref, k, obj, nref = _batch_tables()
+    assert k.shape == (65536,) and (k >= 15).all() and (k <= 21).all() and np.isfinite(obj).all()
+    seeds = np.array(sorted(ref))
+    assert seeds.size >= 515 and {7466, 16893, 31186} <= set(ref)
+    kr = np.array([ref[s][0] for s in seeds])
+    orf = np.array([ref[s][1] for s in seeds])
+    assert np.abs(k[seeds] - kr).max() <= 1
+    assert (np.abs(obj[seeds] - orf) <= 1e-8 * np.maximum(1.0, np.abs(orf))).all()
+    assert 0.005 < (nref > 0).mean() < 0.05          # the rule fires on about one LP in fifty
+
+
+@pytest.mark.parametrize("seed", [0, 5, 7466, 16893, 31186, 40000, 65535])
+def test_oracle_refinement_rule_reproduces_its_table(seed):
+    """The table is what oracle.solve(linear="normal", refine_thresh=1.0) returns (regenerated here for a few seeds),
+    and without the rule LP 31186 is trapped (> 60 iterations) - the reason the rule exists."""
+    from oracle import ipm_oracle as orc
+    _, k, obj, nref = _batch_tables()
+    A, b, c = orc.synthetic_dense_lp(256, 512, seed)
+    r = orc.solve(A, b, c, tol=1e-8, max_iter=150, y0_is_one=False, linear="normal", refine_thresh=1.0)
+    assert r["status"] == 0 and r["k"] == k[seed] and r["refinements"] == nref[seed]
+    assert abs(r["obj"] - obj[seed]) <= 1e-12 * max(1.0, abs(obj[seed]))
+    if seed == 31186:
+        lit = orc.solve(A, b, c, tol=1e-8, max_iter=60, y0_is_one=False, linear="normal")
+        assert lit["k"] == 60 and lit["status"] == 1

@@ -1,0 +1,74 @@
+"""Conditional refinement of the corrector in the batched solver (include/ipm_b200.h IPM_BOPT_REFINE, DESIGN.md
+section 4) on the two generator LPs with a history: seed 16893 (the GPU's four-pass iteration without refinement
+needs 3527 iterations) and seed 31186 (the CPU port of the normal-equations iteration stalls for > 150).  Pinned to
+the UNMODIFIED reference's results (tests/golden/batch_256x512_reference.json: k = 18 on both) and to the oracle's
+table of the same rule (tests/golden/batch_256x512_oracle.npz).  Kept in its own file, last in collection order."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def ipm(built_library):
+    import interiorpointmethod_b200 as pkg
+    return pkg
+
+
+@pytest.fixture(scope="module")
+def tables():
+    ref = {int(k): v for k, v in json.load(open(os.path.join(GOLD, "batch_256x512_reference.json")))["seeds"].items()}
+    orc = np.load(os.path.join(GOLD, "batch_256x512_oracle.npz"))
+    return ref, orc["k"], orc["obj"]
+
+
+@pytest.mark.parametrize("three_pass", [1, 0])
+@pytest.mark.parametrize("seed", [16893, 31186, 7466])
+def test_refinement_keeps_the_trapped_lps_at_the_reference_count(ipm, tables, seed, three_pass):
+    """A block of 64 LPs around the seed, through the four-pass (default) and the literal six-pass iteration: every
+    LP converges within +-1 of the oracle's count, the seed itself within +-1 of the unmodified reference's."""
+    from interiorpointmethod_b200 import _lib
+    from interiorpointmethod_b200.batch import solve_batched_host
+    lib = _lib.load()
+    ref, ok, oobj = tables
+    first = seed - seed % 64
+    A, b, c = ipm.synthetic_dense_batch(first, 64, 256, 512)
+    try:
+        lib.ipm_batched_set_variant(three_pass, 3)
+        obj, it, st, x = solve_batched_host(A, b, c, tol=1e-8, max_iter=400, want_x=True)
+    finally:
+        lib.ipm_batched_set_variant(1, 3)
+    assert (st == 0).all(), (st, it)
+    want_k, want_obj = ok[first:first + 64].astype(int), oobj[first:first + 64]
+    assert np.abs(it.astype(int) - want_k).max() <= 1, (it, want_k)
+    assert (np.abs(obj - want_obj) <= 1e-8 * np.abs(want_obj)).all()
+    k_ref, obj_ref = ref[seed]
+    at = seed - first
+    assert abs(int(it[at]) - k_ref) <= 1 and abs(obj[at] - obj_ref) <= 1e-8 * abs(obj_ref), (it[at], obj[at], ref[seed])
+    rb = np.einsum("bmn,bn->bm", A, x) - b
+    assert (np.linalg.norm(rb, axis=1) <= 1.001e-8 * (1 + np.linalg.norm(b, axis=1))).all()     # main.py:170
+
+
+def test_the_trap_is_there_without_refinement(ipm):
+    """Documents why the rule exists: IPM_BOPT_REFINE = 0, four-pass iteration, LP 16893 runs into the cap while
+    its neighbours are unaffected (bitwise: an LP never sees another LP's data)."""
+    from interiorpointmethod_b200 import _lib
+    from interiorpointmethod_b200.batch import solve_batched_host
+    lib = _lib.load()
+    first, at = 16864, 16893 - 16864
+    A, b, c = ipm.synthetic_dense_batch(first, 64, 256, 512)
+    obj1, it1, st1 = solve_batched_host(A, b, c, tol=1e-8, max_iter=120)
+    try:
+        lib.ipm_batched_set_option(_lib.BOPT_REFINE, 0)
+        obj0, it0, st0 = solve_batched_host(A, b, c, tol=1e-8, max_iter=120)
+    finally:
+        lib.ipm_batched_set_option(_lib.BOPT_REFINE, 1)
+    assert int(st1[at]) == 0 and int(it1[at]) <= 20
+    assert int(it0[at]) == 120 and int(st0[at]) == 1
+    never = np.array([i for i in range(64) if i != at and it0[i] == it1[i]])
+    assert never.size >= 56                       # the rule fires on about one LP in fifty
+    assert np.array_equal(obj0[never], obj1[never])
