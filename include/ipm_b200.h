@@ -216,8 +216,10 @@ int ipm_batched_set_variant(int three_pass, int refresh_every);
  *   (tests/golden/batch_256x512_*.{npz,json}).  0 switches it off (A/B, and to document the trap).
  * IPM_BOPT_STRIP_TMA (default 1): the four-pass direction kernels read the column strips of A straight from the
  *   caller's row-major array through a 3-D tensor map (cp.async.bulk.tensor); 0 = from a strip-major copy of A
- *   made once per solve (costs a second copy of A in the workspace: set it BEFORE ipm_batched_workspace_bytes). */
-enum { IPM_BOPT_REFINE = 1, IPM_BOPT_STRIP_TMA = 2 };
+ *   made once per solve (costs a second copy of A in the workspace: set it BEFORE ipm_batched_workspace_bytes).
+ * IPM_BOPT_OVERLAP_RHS (default 0): the predictor right-hand side pass runs on a second stream beside the Cholesky
+ *   (results are bitwise unchanged: the same kernels on the same data, only their placement in time differs). */
+enum { IPM_BOPT_REFINE = 1, IPM_BOPT_STRIP_TMA = 2, IPM_BOPT_OVERLAP_RHS = 3 };
 int ipm_batched_set_option(int option, int value);
 
 /* Phase timing of the batched solver (bench.py roofline): CUDA events on the solve stream around the four

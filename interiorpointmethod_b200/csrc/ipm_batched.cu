@@ -99,6 +99,7 @@ struct BatchedOptions {
     std::atomic<int> fresh_every{3};    // four-pass path: residuals from scratch every 3rd iteration
     std::atomic<int> refine{1};         // conditional refinement of the corrector (kbf_dir / kb_dir)
     std::atomic<int> strip_tma{1};      // four-pass path: strips of A through a tensor map (1) or a strip-major copy (0)
+    std::atomic<int> overlap_rhs{0};    // predictor right-hand side (HBM-bound) on a second stream beside the Cholesky
 };
 BatchedOptions g_opt;
 
@@ -612,6 +613,23 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
     bool all_joined[2] = {true, true};          // per check slot: had every chunk joined when the check was enqueued?
     bool joined_pending = false;                // a chunk joined after the last check was enqueued
     const bool small_m = m <= 32 * TRSVI_MAX_BLK;
+    // Optional: the predictor right-hand side (one HBM-bound pass over A, independent of the factorisation) runs on a
+    // second, higher-priority stream beside the Cholesky, which leaves HBM idle (10 % of peak) and half of its
+    // register file free whenever one of its two CTAs per SM retires.
+    const bool overlap_rhs = g_opt.overlap_rhs.load() != 0;
+    cudaStream_t st2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    struct SideGuard {
+        cudaStream_t* s; cudaEvent_t *a, *b;
+        ~SideGuard() { if (*s) cudaStreamDestroy(*s); if (*a) cudaEventDestroy(*a); if (*b) cudaEventDestroy(*b); }
+    } side_guard{&st2, &ev_fork, &ev_join};
+    if (overlap_rhs) {
+        int lo = 0, hi = 0;
+        IPM_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        IPM_CUDA_OK(cudaStreamCreateWithPriority(&st2, cudaStreamNonBlocking, hi));
+        IPM_CUDA_OK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        IPM_CUDA_OK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    }
     auto launch_trsv = [&](const TrsvBatchedArgs& t) {
         if (small_m) k_trsv_batched_inv<<<B, TRSVB_NT, trsv_batched_inv_smem(m), st>>>(t);
         else k_trsv_batched<<<B, TRSVB_NT, trsv_batched_smem(m), st>>>(t);
@@ -655,6 +673,13 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
         g_prof.segment(st);
         IPM_TRY((dmma_syrk_auto<0>(g, B, st)));
         g_prof.end_phase(PH_SYRK, st);
+        if (overlap_rhs) {
+            IPM_CUDA_OK(cudaEventRecord(ev_fork, st));             // after the SYRK: its CTAs leave no room beside them
+            IPM_CUDA_OK(cudaStreamWaitEvent(st2, ev_fork, 0));
+            kb_rhs<NPL><<<B, KB_NT, smem_w, st2>>>(a, 0);
+            count_launch();
+            IPM_CUDA_OK(cudaEventRecord(ev_join, st2));
+        }
         if (m <= KBC_MAX_M_BIG)
             IPM_TRY(potrf_batched_fused(w.M, w.ldm, (int64_t)m * w.ldm, m, B, a.scal, S_COUNT, tau, a.active, st));
         else
@@ -666,7 +691,9 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
         t.active = a.active;
         if (fused) t.out = a.dy;           // the right-hand side survives: the corrector's is built on top of it
         for (int kind = 0; kind < 2; ++kind) {
-            if (!fused || kind == 0) {
+            if (kind == 0 && overlap_rhs) {
+                IPM_CUDA_OK(cudaStreamWaitEvent(st, ev_join, 0));
+            } else if (!fused || kind == 0) {
                 kb_rhs<NPL><<<B, KB_NT, smem_w, st>>>(a, kind);
                 count_launch();
             }
@@ -738,6 +765,7 @@ int ipm_batched_set_option(int option, int value) {
     switch (option) {
         case IPM_BOPT_REFINE: g_opt.refine.store(value != 0); return IPM_OK;
         case IPM_BOPT_STRIP_TMA: g_opt.strip_tma.store(value != 0); return IPM_OK;
+        case IPM_BOPT_OVERLAP_RHS: g_opt.overlap_rhs.store(value != 0); return IPM_OK;
         default: return IPM_ERR_ARG;
     }
 }

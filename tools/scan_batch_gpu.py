@@ -60,6 +60,7 @@ for blk in blocks:
         for label, setup in (("default (tensor-map strips, refinement on)", []),
                              ("strip-major copy instead of the tensor map", [(_lib.BOPT_STRIP_TMA, 0)]),
                              ("refinement off", [(_lib.BOPT_REFINE, 0)]),
+                             ("predictor rhs beside the Cholesky (2nd stream)", [(_lib.BOPT_OVERLAP_RHS, 1)]),
                              ("six-pass literal iteration", "six")):
             if setup == "six":
                 lib.ipm_batched_set_variant(0, 3)
@@ -77,6 +78,7 @@ for blk in blocks:
             lib.ipm_batched_set_variant(1, 3)
             lib.ipm_batched_set_option(_lib.BOPT_STRIP_TMA, 1)
             lib.ipm_batched_set_option(_lib.BOPT_REFINE, 1)
+            lib.ipm_batched_set_option(_lib.BOPT_OVERLAP_RHS, 0)
     del db
 print("SCAN %s: %d LPs outside the parity bar over %d blocks" % ("OK" if tot_bad == 0 else "FAILED", tot_bad, len(blocks)))
 sys.exit(0 if tot_bad == 0 else 1)
