@@ -568,6 +568,7 @@ def main():
     t_dev, wall_dev, out = timed(step_device, args.steps)
     per_rank_dev = list(timed.per_rank_ms)
     launches = lib.ipm_launch_count() - launches0
+    handoffs = lib.ipm_batched_last_handoffs()
     clocks = sampler.stop() if sampler else None
     ms = (ctypes.c_double * 4)()
     calls = (ctypes.c_int64 * 4)()
@@ -708,6 +709,7 @@ def main():
                    "max_rel_objective_diff_vs_oracle_table": float(maxs[1].item()) if sums[4].item() == 0 else None,
                    "parity_table": "tests/golden/batch_256x512_oracle.npz (all %d LPs of all ranks, both arms)" % B
                                    if sums[4].item() == 0 else "not covered by the frozen table: convergence gate only",
+                   "handed_to_augmented_system_kernel_rank0": int(handoffs),
                    "strong": strong},
         "parity": "FAILED" if parity_failed else "ok",
         "newton_it_per_s": float(it_all.sum()) * args.steps / t_dev,

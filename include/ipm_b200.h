@@ -104,6 +104,25 @@ int ipm_load_dense_d(ipm_handle *h, int m, int n, const double *A_d, int64_t lda
 /* ---------------------------------------------------------------- iterate */
 /* x = s = 1; y = 1 (initial_vector_sparse, sparse_interior.py:193-200) or y = 0 (initial_vector, main.py:287-302). */
 int ipm_init_state(ipm_handle *h, int y0_is_one);
+/* NOT in the reference (opt-in; iteration parity does not apply, objective parity does): dependent rows of a
+ * rank-deficient A.  The reference's loader hands over A as it is in the file; QAP8/12/15 are 13-20 % rank deficient
+ * (SURVEY App. C.3), and on such a matrix the pivots of the dependent rows of M = A D A^T are round-off - sometimes
+ * below the 1e-30 threshold of the safeguard, sometimes not - so the iteration crawls (QAP8: 196 iterations) or
+ * stalls short of the optimum (QAP15: gap 1e-3 after 500).  This call factors A A^T (d = 1, where M is as well
+ * scaled as it will ever be) with the relative pivot threshold rel_tol (1e-10 is the tested value): a row whose
+ * pivot falls below it is a combination of the rows before it.  The mask stays in the handle until the next load,
+ * and every later factorisation replaces the pivots of the masked rows by 1e128, which removes the row from the
+ * normal equations (dy_i = 0) - the LIPSOL / PCx treatment.  rel_tol <= 0 clears the mask.  Call after a load and
+ * before ipm_solve / ipm_start_mehrotra.  QAP8 then needs 17-19 iterations, QAP15 reaches the Netlib optimum. */
+int ipm_detect_dependent_rows(ipm_handle *h, double rel_tol, int *n_dependent);
+
+/* NOT in the reference (opt-in): conditional refinement of the corrector for ONE LP, the rule the batched solver
+ * applies by default (IPM_BOPT_REFINE above): delta = -rb - A dx; when |delta| > thresh |rb| one step of iterative
+ * refinement on the same factor (M ddy = delta, dy += ddy, dx and ds re-formed).  thresh < 0 switches it off
+ * (default: the 26 LPs the reference converges on are reproduced without it).  thresh = 1 is the batched
+ * solver's rule; smaller values refine more often (0 = always). */
+int ipm_set_refinement(ipm_handle *h, double thresh);
+
 /* NOT in the reference (opt-in): Mehrotra's starting point, x = A^T (A A^T)^-1 b and
  * s = c - A^T y with y = (A A^T)^-1 A c, both shifted into the positive orthant (SIAM J. Optim. 2 (1992) sec. 7),
  * computed on the device with the solver's own SYRK/SpGEMM, Cholesky and triangular-solve kernels.  It changes the
@@ -217,10 +236,27 @@ int ipm_batched_set_variant(int three_pass, int refresh_every);
  * IPM_BOPT_STRIP_TMA (default 1): the four-pass direction kernels read the column strips of A straight from the
  *   caller's row-major array through a 3-D tensor map (cp.async.bulk.tensor); 0 = from a strip-major copy of A
  *   made once per solve (costs a second copy of A in the workspace: set it BEFORE ipm_batched_workspace_bytes).
- * IPM_BOPT_OVERLAP_RHS (default 0): the predictor right-hand side pass runs on a second stream beside the Cholesky
- *   (results are bitwise unchanged: the same kernels on the same data, only their placement in time differs). */
-enum { IPM_BOPT_REFINE = 1, IPM_BOPT_STRIP_TMA = 2, IPM_BOPT_OVERLAP_RHS = 3 };
+ * IPM_BOPT_HANDOFF (default 1, needs IPM_BOPT_REFINE and n + m <= 1600): when the refined corrector STILL has
+ *   |delta| > |rb|, the normal equations have broken down for this LP (the safeguarded Cholesky dropped a row that
+ *   is not dependent: numerically degenerate vertex); the LP leaves the lockstep loop and is finished from its
+ *   current iterate by ipm_solve_dense_kkt's kernel (augmented system, LU with partial pivoting - the reference's
+ *   own dgesv route, main.py:178).  About one generator LP in a thousand; without it such an LP can iterate for
+ *   thousands of iterations at |rb| just above the threshold (LPs 16893, 31186, 54456), the reference needs 17-18.
+ * Value 2 of IPM_BOPT_REFINE / IPM_BOPT_HANDOFF is a test hook: every corrector takes the refinement step / every LP
+ * is handed off after it (tests/test_zz_gpu_refinement.py exercises both paths on whole blocks with them). */
+enum { IPM_BOPT_REFINE = 1, IPM_BOPT_STRIP_TMA = 2, IPM_BOPT_HANDOFF = 3 };
 int ipm_batched_set_option(int option, int value);
+/* LPs the most recent batched solve on this process handed to the augmented-system kernel. */
+int ipm_batched_last_handoffs(void);
+
+/* One dense LP by the reference's dense route (`interior`, main.py:707-757: `create_matrix` main.py:13-21 +
+ * np.linalg.solve main.py:178) on the GPU: predictor-corrector iteration on the augmented system
+ * [[-D^-1, A^T], [A, 0]] (the unreduced KKT matrix with ds eliminated exactly), LU with partial pivoting, one CTA.
+ * Start x = s = 1, y = 0 (main.py:287-302).  Host buffers; A row-major m x n, n + m <= 1600.  A robustness path
+ * (same Newton system and pivoting rule as the reference => same iteration counts), not a throughput path. */
+int ipm_solve_dense_kkt(int device_ordinal, int m, int n, const double *A, const double *b, const double *c,
+                        double tol, int max_iter, double *x, double *y, double *s, double *obj, int *iters,
+                        int *status);
 
 /* Phase timing of the batched solver (bench.py roofline): CUDA events on the solve stream around the four
  * phases of every lockstep iteration.  ms/calls index: 0 residual pass, 1 SYRK (dmma_nt_kernel, one launch

@@ -2,7 +2,8 @@
 payakorn/InteriorPointMethod: hand-written sm_100a CUDA behind a C ABI (include/ipm_b200.h), with a thin
 Python mirror of the reference's call surface."""
 from .solver import (NewtonStep, Result, check_optimality, corrected, direction_corrected_sparse,  # noqa: F401
-                     direction_predicted_sparse, duality_gap, full_stepsize, interior, interior_sparse,
+                     direction_predicted_sparse, duality_gap, full_stepsize, interior, interior_kkt,
+                     interior_sparse,
                      newton_iteration, predicted_stepsize, release_cached_step, solve, solve_linear)
 from . import general_form  # noqa: F401
 from .general_form import (add_bound_into_matrix, create_problem_from_mps_matlab, get_Abc,  # noqa: F401
@@ -10,7 +11,7 @@ from .general_form import (add_bound_into_matrix, create_problem_from_mps_matlab
 from .problems import (create_problem_from_mps, load_golden_problem, synthetic_dense_batch,  # noqa: F401
                        synthetic_dense_lp)
 
-__all__ = ["NewtonStep", "Result", "solve", "interior_sparse", "interior", "direction_predicted_sparse",
+__all__ = ["NewtonStep", "Result", "solve", "interior_sparse", "interior", "interior_kkt", "direction_predicted_sparse",
            "direction_corrected_sparse", "check_optimality", "predicted_stepsize", "full_stepsize", "duality_gap",
            "corrected", "solve_linear", "newton_iteration", "release_cached_step", "create_problem_from_mps",
            "load_golden_problem", "synthetic_dense_lp", "synthetic_dense_batch", "get_Abc", "add_bound_into_matrix",

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_PKG, "libipm_b200.so")
 IPM_OK = 0
 ERRORS = {-1: "IPM_ERR_CUDA", -2: "IPM_ERR_ARG", -3: "IPM_ERR_SHAPE", -4: "IPM_ERR_STATE", -5: "IPM_ERR_NOMEM"}
 STATUS = {0: "converged", 1: "max_iter", 2: "nan"}
-BOPT_REFINE, BOPT_STRIP_TMA, BOPT_OVERLAP_RHS = 1, 2, 3      # ipm_batched_set_option
+BOPT_REFINE, BOPT_STRIP_TMA, BOPT_HANDOFF = 1, 2, 3      # ipm_batched_set_option
 
 # every symbol include/ipm_b200.h declares: name -> (restype, argtypes)
 _dp = POINTER(c_double)
@@ -54,6 +54,8 @@ SYMBOLS = {
                               c_double]),
     "ipm_solve_spd": (c_int, [c_int, c_int, c_void_p, c_void_p, c_double, c_void_p, _ip]),
     "ipm_start_mehrotra": (c_int, [c_void_p]),
+    "ipm_detect_dependent_rows": (c_int, [c_void_p, c_double, _ip]),
+    "ipm_set_refinement": (c_int, [c_void_p, c_double]),
     "ipm_solve": (c_int, [c_void_p, c_double, c_int, c_int, c_void_p, c_void_p, c_void_p, _dp, _ip, _ip, c_void_p]),
     "ipm_solve_batched_dense": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_double, c_int,
                                         c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -63,6 +65,9 @@ SYMBOLS = {
     "ipm_batched_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
     "ipm_batched_set_variant": (c_int, [c_int, c_int]),
     "ipm_batched_set_option": (c_int, [c_int, c_int]),
+    "ipm_batched_last_handoffs": (c_int, []),
+    "ipm_solve_dense_kkt": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_double, c_int, c_void_p, c_void_p,
+                                    c_void_p, _dp, _ip, _ip]),
     "ipm_profile_enable": (c_int, [c_int]),
     "ipm_profile_read": (c_int, [c_void_p, c_void_p, POINTER(c_int64)]),
     "ipm_profile_last": (c_int, [c_void_p, c_void_p, c_int]),

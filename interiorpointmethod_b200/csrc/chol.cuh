@@ -19,6 +19,15 @@ struct CholArgs {
     double tau;                                    // relative pivot threshold
     int m, j0, nb;                                 // matrix order, panel start, panel width (<= NB)
     const int* active;                             // nullable per-LP flag
+    unsigned char* dep = nullptr;                  // nullable, m bytes (one matrix): dependent-row mask
+    int dep_mode = 0;                              // 1: pivots of masked rows are replaced whatever their value
+                                                   // 2: detect - the mask is WRITTEN (1 where the pivot was replaced)
+};
+// Dependent rows of a rank-deficient A (ipm_detect_dependent_rows, include/ipm_b200.h): threaded through the
+// single-matrix drivers below.
+struct DepMask {
+    unsigned char* mask = nullptr;
+    int mode = 0;
 };
 
 #ifdef __CUDACC__
@@ -90,15 +99,18 @@ static __global__ void __launch_bounds__(NT, 1) k_chol_diag(const CholArgs a) {
             for (int c = 0; c < 32; ++c) arow[c] = (ok && c <= lane) ? S[(c0 + lane) * LD + c0 + c] : 0.0;
             int nfix = 0;
             double my_inv = 1.0;
+            const bool masked = a.dep != nullptr && a.dep_mode == 1;
+            const unsigned forced_bits = masked ? __ballot_sync(0xffffffffu, ok && a.dep[a.j0 + c0 + lane] != 0) : 0u;
+            bool my_bad = false;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 if (j < w) {
                     double p = __shfl_sync(0xffffffffu, arow[j], j);
-                    const bool bad = !(p > thresh);
+                    const bool bad = !(p > thresh) || ((forced_bits >> j) & 1u);
                     if (bad) p = kPivotBig;
                     const double l = sqrt(p);
                     const double lij = (lane == j) ? l : arow[j] / l;
-                    if (lane == j) { my_inv = 1.0 / l; nfix += bad ? 1 : 0; }
+                    if (lane == j) { my_inv = 1.0 / l; nfix += bad ? 1 : 0; my_bad = bad; }
                     arow[j] = lij;
                     colb[lane] = lij;
                     __syncwarp();
@@ -112,6 +124,7 @@ static __global__ void __launch_bounds__(NT, 1) k_chol_diag(const CholArgs a) {
                 for (int c = 0; c < 32; ++c)
                     if (c <= lane) S[(c0 + lane) * LD + c0 + c] = arow[c];
                 dinv[lane] = my_inv;
+                if (a.dep != nullptr && a.dep_mode == 2) a.dep[a.j0 + c0 + lane] = my_bad ? 1 : 0;
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) nfix += __shfl_xor_sync(0xffffffffu, nfix, o);
@@ -269,7 +282,7 @@ static bool g_chol_lookahead = true;
 // Host driver: in-place factorisation of `batch` matrices of order m.
 template <int NB, int NT_DIAG, int ROWS>
 inline int potrf_blocked(double* M, int64_t ldm, int64_t strideM, int m, int batch, double* scal,
-                         int64_t strideScal, double tau, const int* active, cudaStream_t st) {
+                         int64_t strideScal, double tau, const int* active, cudaStream_t st, DepMask dm = DepMask()) {
     auto kd = k_chol_diag<NB, NT_DIAG>;
     auto kt = k_chol_trsm<NB, ROWS>;
     static DevOnce once;
@@ -284,6 +297,7 @@ inline int potrf_blocked(double* M, int64_t ldm, int64_t strideM, int m, int bat
     CholArgs a;
     a.M = M; a.ldm = ldm; a.strideM = strideM; a.scal = scal; a.strideScal = strideScal; a.tau = tau;
     a.m = m; a.active = active;
+    a.dep = (batch == 1) ? dm.mask : nullptr; a.dep_mode = (batch == 1) ? dm.mode : 0;
     // Look-ahead (one large matrix, 128-wide panels): the trailing update of panel j is split into the tile column
     // the next panel lives in ("strip", a few microseconds) and the rest, which runs on a side stream on all SMs
     // but one while the main stream already factors the next diagonal block (one CTA, latency-bound, about as
@@ -671,6 +685,14 @@ static __global__ void __launch_bounds__(TRSVB_NT, 3) k_trsv_batched_inv(const T
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, m = a.m;
     const int64_t ldm = a.ldm;
     const int nblk = (m + 31) >> 5;
+    // The forward sweep walks L block row by block row with a dependent chain of global round trips; with the lower
+    // triangle on its way to L2 from the start they are L2 hits (the batched factors of 8192 LPs do not stay there).
+    if ((ldm & 1) == 0 && (reinterpret_cast<uintptr_t>(L) & 15) == 0) {
+        for (int r = tid; r < m; r += TRSVB_NT) {
+            const uint32_t bytes = (uint32_t)(((r + 1) * 8 + 15) & ~15);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(L + (size_t)r * ldm), "r"(bytes) : "memory");
+        }
+    }
     for (int i = tid; i < m; i += TRSVB_NT) vec[i] = v[i];
     // ---- block inverses, one warp per block
     for (int blk = warp; blk < nblk; blk += TRSVB_NW) {

@@ -91,7 +91,9 @@ enum Scal {
     S_NFIXED,       // pivots replaced in the last factorisation
     S_RAW_P,        // min({-x/dx : dx<0} U {1}) of the last direction
     S_RAW_D,        // min({-s/ds : ds<0} U {1}) of the last direction
-    S_NREFINE,      // batched solver: corrector refinements taken so far
+    S_NREFINE,      // corrector refinements taken so far
+    S_REFINE_FLAG,  // single LP: 1.0 = the current corrector takes the refinement step
+    S_HANDOFF,      // batched solver: 1.0 = the LP was handed to the augmented-system kernel (kkt_dense.cuh)
     S_COUNT = 24
 };
 

@@ -27,6 +27,7 @@
 #include "dmma_gemm.cuh"
 #include "dmma_ws.cuh"
 #include "ipm_batched_fused.cuh"
+#include "kkt_dense.cuh"
 
 using namespace ipm;
 
@@ -99,9 +100,24 @@ struct BatchedOptions {
     std::atomic<int> fresh_every{3};    // four-pass path: residuals from scratch every 3rd iteration
     std::atomic<int> refine{1};         // conditional refinement of the corrector (kbf_dir / kb_dir)
     std::atomic<int> strip_tma{1};      // four-pass path: strips of A through a tensor map (1) or a strip-major copy (0)
-    std::atomic<int> overlap_rhs{0};    // predictor right-hand side (HBM-bound) on a second stream beside the Cholesky
+    std::atomic<int> handoff{1};        // LPs the refined corrector cannot fix go to the augmented-system kernel
 };
+std::atomic<int> g_last_handoffs{0};    // LPs handed off in the most recent batched solve (ipm_batched_last_handoffs)
 BatchedOptions g_opt;
+
+// IPM_DEBUG_SYNC=1: synchronise and check after every launch of the batched loop and name the launch that failed
+// (launch errors are otherwise only collected once per lockstep iteration).
+int debug_check(const char* what, cudaStream_t st) {
+    static const bool on = getenv("IPM_DEBUG_SYNC") != nullptr;
+    if (!on) return IPM_OK;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+        return IPM_ERR_CUDA;
+    }
+    return IPM_OK;
+}
 
 // ---------------------------------------------------------------------------------------------
 // One pass over A_i: Ax (warp per row) and A^T y (column partial sums per warp, combined in warp order).
@@ -289,8 +305,10 @@ __global__ void __launch_bounds__(KB_NT) kb_rhs(const BatchArgs a, int kind) {
 // dy is read from a.rhs (the batched triangular solve works in place).
 // Conditional refinement of the corrector (kind 1, a.refine; the rule and its reason are stated at kbf_dir,
 // ipm_batched_fused.cuh): a second sweep over A_i (from L2) forms delta = -rb - A dx; when |delta| > |rb| the LP
-// is not updated, delta goes to a.dy and the LP is flagged FLAG_REFINE; the host's next two launches solve
-// a.rhs += M^-1 delta and run this kernel again with pass = 1 for the flagged LPs.
+// is not updated, dx goes to a.dxc, delta to a.dy and the LP is flagged FLAG_REFINE; the host's next two launches
+// solve ddy = M^-1 delta in place (a.dy) and run this kernel again with pass = 1 for the flagged LPs:
+// dx = dx_old + d (A^T ddy), ds from dx, step in y along dy + ddy; if |delta| > |rb| even then, the LP is parked for
+// the augmented-system kernel (a.handoff_list).
 template <int NPL>
 __global__ void __launch_bounds__(KB_NT) kb_dir(const BatchArgs a, int kind, int pass) {
     extern __shared__ __align__(16) double smem[];
@@ -305,7 +323,7 @@ __global__ void __launch_bounds__(KB_NT) kb_dir(const BatchArgs a, int kind, int
     const int m = a.m, n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double* A = a.A + (size_t)lp * m * n;
     const size_t on = (size_t)lp * n, om = (size_t)lp * m;
-    const double* dy = a.rhs + om;
+    const double* dy = (pass == 0) ? a.rhs + om : a.dy + om;       // pass 1 streams ddy
     double* scal = a.scal + (size_t)lp * S_COUNT;
     const int n2 = n >> 1;
 
@@ -343,7 +361,7 @@ __global__ void __launch_bounds__(KB_NT) kb_dir(const BatchArgs a, int kind, int
 #pragma unroll
             for (int w = 0; w < KB_NW; ++w) u += colred[(size_t)w * n + k];
             const double xi = a.x[on + k], si = a.s[on + k];
-            const double dxi = a.d[on + k] * u + a.w[on + k];
+            const double dxi = a.d[on + k] * u + ((pass == 0) ? a.w[on + k] : a.dxc[on + k]);
             const double dsi = (-si * dxi / xi) - a.rcx[on + k];
             dxv[q] = dxi; dsv[q] = dsi; xv[q] = xi; sv[q] = si;
             if (dxi < 0.0) minp = fmin(minp, -xi / dxi);
@@ -375,7 +393,7 @@ __global__ void __launch_bounds__(KB_NT) kb_dir(const BatchArgs a, int kind, int
             scal[S_SIGMA] = sigma; scal[S_SIGMA_MU] = sigma * mu;
         }
     } else {
-        if (a.refine && pass == 0) {
+        if (a.refine) {
             // every thread is past the barriers above, so the column partials are dead: dx takes their place
             double* dxs = colred;
 #pragma unroll
@@ -390,6 +408,7 @@ __global__ void __launch_bounds__(KB_NT) kb_dir(const BatchArgs a, int kind, int
                 const int c2 = j * 32 + lane;
                 wr[j] = (c2 < n2) ? reinterpret_cast<const double2*>(dxs)[c2] : make_double2(0.0, 0.0);
             }
+            double* dsm = dxs + n;                     // [m] delta (second row of the dead partials)
             double nd2 = 0.0, nr2 = 0.0;
             for (int r = warp; r < m; r += KB_NW) {
                 const double2* row = reinterpret_cast<const double2*>(A + (size_t)r * n);
@@ -406,7 +425,7 @@ __global__ void __launch_bounds__(KB_NT) kb_dir(const BatchArgs a, int kind, int
                 const double dot = warp_sum(dot0 + dot1);
                 if (lane == 0) {
                     const double rbr = a.rb[om + r], dl = -rbr - dot;
-                    a.dy[om + r] = dl;
+                    dsm[r] = dl;
                     nd2 += dl * dl;
                     nr2 += rbr * rbr;
                 }
@@ -414,14 +433,35 @@ __global__ void __launch_bounds__(KB_NT) kb_dir(const BatchArgs a, int kind, int
             nd2 = block_red<RED_SUM>(nd2, sh);
             if (tid == 0) s_alpha[2] = nd2;
             nr2 = block_red<RED_SUM>(nr2, sh);
-            if (tid == 0) s_alpha[3] = (s_alpha[2] > nr2) ? 1.0 : 0.0;        // NaN compares false: no refinement
+            if (tid == 0) {
+                const double fl = 1e-3 * a.tol * (1.0 + scal[S_NB]);            // see kbf_dir
+                s_alpha[3] = (s_alpha[2] > nr2 && s_alpha[2] > fl * fl) ? 1.0 : 0.0;   // NaN compares false
+                if ((pass == 0 && a.refine == 2) || (pass != 0 && a.handoff == 2)) s_alpha[3] = 1.0;    // test hooks
+            }
             __syncthreads();
             if (s_alpha[3] != 0.0) {
-                if (tid == 0) {
-                    a.active[lp] = FLAG_REFINE;
-                    scal[S_NREFINE] = scal[S_NREFINE] + 1.0;
+                if (pass == 0) {
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int k = tid + q * KB_NT;
+                        if (k < n) a.dxc[on + k] = dxv[q];
+                    }
+                    for (int i = tid; i < m; i += KB_NT) a.dy[om + i] = dsm[i];
+                    if (tid == 0) {
+                        a.active[lp] = FLAG_REFINE;
+                        scal[S_NREFINE] = scal[S_NREFINE] + 1.0;
+                    }
+                    return;
                 }
-                return;
+                if (a.handoff) {
+                    if (tid == 0) {
+                        const unsigned slot = atomicAdd(a.n_handoff, 1u);
+                        a.handoff_list[slot] = lp;
+                        scal[S_HANDOFF] = 1.0;
+                        a.active[lp] = 0;
+                    }
+                    return;
+                }
             }
         }
         ap = fmin(1.0, a.eta * ap);
@@ -434,7 +474,10 @@ __global__ void __launch_bounds__(KB_NT) kb_dir(const BatchArgs a, int kind, int
                 a.s[on + k] = sv[q] + ad * dsv[q];
             }
         }
-        for (int i = tid; i < m; i += KB_NT) a.y[om + i] = a.y[om + i] + ad * dy[i];
+        for (int i = tid; i < m; i += KB_NT) {
+            const double dyi = (pass == 0) ? dy[i] : a.rhs[om + i] + dy[i];      // pass 1: dy + ddy
+            a.y[om + i] = a.y[om + i] + ad * dyi;
+        }
         if (tid == 0) {
             scal[S_AP] = ap; scal[S_AD] = ad;
             a.iters[lp] += 1;
@@ -461,7 +504,8 @@ struct Workspace {
     BatchArgs a;
     double* M;
     int64_t ldm;
-    unsigned* h_nact;    // pinned
+    double* ka_work;     // ka_slots * ka_work_doubles
+    unsigned* h_nact;    // pinned (3 words: two check slots + the hand-off count)
 };
 
 int64_t at_doubles(int B, int m, int n) {        // strip-major copy of A (3-pass path with IPM_BOPT_STRIP_TMA = 0 only)
@@ -469,10 +513,14 @@ int64_t at_doubles(int B, int m, int n) {        // strip-major copy of A (3-pas
     return (int64_t)B * ceil_div(n, KF_W) * (32 * kf_nrp(m)) * KF_W;
 }
 
+// slots of the augmented-system kernel (one matrix of order n + m each): LPs handed off beyond that run in rounds
+int ka_slots(int B, int m, int n) { return (m + n > KA_MAX_N) ? 0 : std::min(B, 48); }
+
 int64_t ws_bytes(int B, int m, int n) {
     const int64_t ldm = round_up(m, 16);
-    int64_t doubles = (int64_t)B * (10 * (int64_t)n + 4 * (int64_t)m + S_COUNT) + (int64_t)B * m * ldm + at_doubles(B, m, n);
-    int64_t bytes = doubles * 8 + (int64_t)B * 2 * sizeof(int) + 256 + 1024;
+    int64_t doubles = (int64_t)B * (10 * (int64_t)n + 4 * (int64_t)m + S_COUNT) + (int64_t)B * m * ldm + at_doubles(B, m, n) +
+                      (int64_t)ka_slots(B, m, n) * ka_work_doubles(m, n);
+    int64_t bytes = doubles * 8 + (int64_t)B * 3 * sizeof(int) + 256 + 1024;
     return round_up(bytes, 256);
 }
 
@@ -487,11 +535,14 @@ void carve(Workspace& w, void* base, int B, int m, int n) {
     w.a.dxa = take(bn); w.a.dsa = take(bn); w.a.dxc = take(bn); w.a.dsc = take(bn);
     w.a.y = take(bm); w.a.rb = take(bm); w.a.dy = take(bm); w.a.rhs = take(bm);
     w.a.scal = take((int64_t)B * S_COUNT);
+    w.ka_work = take((int64_t)ka_slots(B, m, n) * ka_work_doubles(m, n));
     int* ip = reinterpret_cast<int*>(p);
     w.a.active = ip; ip += B;
     w.a.iters = ip; ip += B;
+    w.a.handoff_list = ip; ip += B;
     uintptr_t u = (reinterpret_cast<uintptr_t>(ip) + 63) & ~(uintptr_t)63;
-    w.a.n_active = reinterpret_cast<unsigned*>(u);
+    w.a.n_active = reinterpret_cast<unsigned*>(u);          // [0], [16]: the two check slots; [32]: hand-off count
+    w.a.n_handoff = w.a.n_active + 32;
     w.a.m = m; w.a.n = n;
 }
 
@@ -541,7 +592,7 @@ int kbf_configure_nrp() {
 template <int NPL>
 int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, int* iterations_run, Arrival* arr) {
     BatchArgs& a = w.a;
-    const size_t smem_col = (size_t)KB_NW * n * sizeof(double);
+    const size_t smem_col = std::max((size_t)KB_NW * n, (size_t)n + m) * sizeof(double);
     const size_t smem_res = smem_col + (size_t)n * sizeof(double);
     const size_t smem_w = (size_t)n * sizeof(double);
     DmmaArgs g;
@@ -555,7 +606,9 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
                        ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0);
     const bool tma = fused && g_opt.strip_tma.load() != 0;
     const bool refine = g_opt.refine.load() != 0;
-    a.refine = refine ? 1 : 0;
+    a.refine = refine ? g_opt.refine.load() : 0;
+    a.handoff = (refine && g_opt.handoff.load() != 0 && ka_slots(B, m, n) > 0) ? g_opt.handoff.load() : 0;
+    IPM_CUDA_OK(cudaMemsetAsync(a.n_handoff, 0, sizeof(unsigned), st));
     static DevOnce once;
     IPM_TRY(once_per_device(once, [&]() -> int {
         IPM_CUDA_OK(cudaFuncSetAttribute(kb_residual<NPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + 8192));
@@ -573,6 +626,7 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
     CUtensorMap tmapA;
     memset(&tmapA, 0, sizeof(tmapA));
     if (tma) IPM_TRY(kf_make_strip_tmap(&tmapA, a.A, B, m, n, 32 * kf_nrp(m)));
+    IPM_TRY(debug_check("before the first launch (stale error)", st));
     auto join = [&](int lp0, int cnt) {             // LPs lp0 .. lp0+cnt-1 enter the loop
         kb_init<<<cnt, 256, 0, st>>>(a, fused ? 2 : 1, lp0);
         count_launch();
@@ -613,23 +667,6 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
     bool all_joined[2] = {true, true};          // per check slot: had every chunk joined when the check was enqueued?
     bool joined_pending = false;                // a chunk joined after the last check was enqueued
     const bool small_m = m <= 32 * TRSVI_MAX_BLK;
-    // Optional: the predictor right-hand side (one HBM-bound pass over A, independent of the factorisation) runs on a
-    // second, higher-priority stream beside the Cholesky, which leaves HBM idle (10 % of peak) and half of its
-    // register file free whenever one of its two CTAs per SM retires.
-    const bool overlap_rhs = g_opt.overlap_rhs.load() != 0;
-    cudaStream_t st2 = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    struct SideGuard {
-        cudaStream_t* s; cudaEvent_t *a, *b;
-        ~SideGuard() { if (*s) cudaStreamDestroy(*s); if (*a) cudaEventDestroy(*a); if (*b) cudaEventDestroy(*b); }
-    } side_guard{&st2, &ev_fork, &ev_join};
-    if (overlap_rhs) {
-        int lo = 0, hi = 0;
-        IPM_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        IPM_CUDA_OK(cudaStreamCreateWithPriority(&st2, cudaStreamNonBlocking, hi));
-        IPM_CUDA_OK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-        IPM_CUDA_OK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
-    }
     auto launch_trsv = [&](const TrsvBatchedArgs& t) {
         if (small_m) k_trsv_batched_inv<<<B, TRSVB_NT, trsv_batched_inv_smem(m), st>>>(t);
         else k_trsv_batched<<<B, TRSVB_NT, trsv_batched_smem(m), st>>>(t);
@@ -651,6 +688,7 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
         if (fused) kb_residual<NPL, true><<<B, KB_NT, smem_res, st>>>(a);
         else kb_residual<NPL, false><<<B, KB_NT, smem_res, st>>>(a);
         count_launch();
+        IPM_TRY(debug_check("kb_init / kb_residual", st));
         g_prof.end_phase(PH_RESID, st);
         IPM_CUDA_OK(cudaMemcpyAsync(w.h_nact + slot, a.n_active, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
         IPM_CUDA_OK(cudaEventRecord(ev[slot], st));
@@ -672,52 +710,66 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
         }
         g_prof.segment(st);
         IPM_TRY((dmma_syrk_auto<0>(g, B, st)));
+        IPM_TRY(debug_check("syrk", st));
         g_prof.end_phase(PH_SYRK, st);
-        if (overlap_rhs) {
-            IPM_CUDA_OK(cudaEventRecord(ev_fork, st));             // after the SYRK: its CTAs leave no room beside them
-            IPM_CUDA_OK(cudaStreamWaitEvent(st2, ev_fork, 0));
-            kb_rhs<NPL><<<B, KB_NT, smem_w, st2>>>(a, 0);
-            count_launch();
-            IPM_CUDA_OK(cudaEventRecord(ev_join, st2));
-        }
         if (m <= KBC_MAX_M_BIG)
             IPM_TRY(potrf_batched_fused(w.M, w.ldm, (int64_t)m * w.ldm, m, B, a.scal, S_COUNT, tau, a.active, st));
         else
             IPM_TRY((potrf_blocked<64, 256, 128>(w.M, w.ldm, (int64_t)m * w.ldm, m, B, a.scal, S_COUNT, tau,
                                                  a.active, st)));
+        IPM_TRY(debug_check("cholesky", st));
         g_prof.end_phase(PH_CHOL, st);
         TrsvBatchedArgs t;
         t.L = w.M; t.ldm = w.ldm; t.strideM = (int64_t)m * w.ldm; t.v = a.rhs; t.strideV = m; t.m = m;
         t.active = a.active;
         if (fused) t.out = a.dy;           // the right-hand side survives: the corrector's is built on top of it
         for (int kind = 0; kind < 2; ++kind) {
-            if (kind == 0 && overlap_rhs) {
-                IPM_CUDA_OK(cudaStreamWaitEvent(st, ev_join, 0));
-            } else if (!fused || kind == 0) {
+            if (!fused || kind == 0) {
                 kb_rhs<NPL><<<B, KB_NT, smem_w, st>>>(a, kind);
                 count_launch();
             }
+            IPM_TRY(debug_check("kb_rhs", st));
             launch_trsv(t);
+            IPM_TRY(debug_check("trsv", st));
             if (!fused) kb_dir<NPL><<<B, KB_NT, smem_col, st>>>(a, kind, 0);
             else launch_kbf_dir(kind, 0, tma, a, tmapA, B, m, st);
             count_launch();
+            IPM_TRY(debug_check(kind ? "direction (corrector)" : "direction (predictor)", st));
         }
         if (refine) {
-            // LPs whose corrector asked for a refinement (flag FLAG_REFINE; about one in fifty per solve): delta is in
-            // a.rhs (fused) / a.dy (six-pass); dy += M^-1 delta on the same factor, then the corrector pass again
+            // LPs whose corrector asked for a refinement (flag FLAG_REFINE; about one in seventy per solve): delta is in
+            // a.rhs (fused) / a.dy (six-pass); ddy = M^-1 delta in place on the same factor, then the corrector pass
+            // again, which applies the step incrementally
             TrsvBatchedArgs t2 = t;
-            t2.only_flag = FLAG_REFINE; t2.accumulate = 1;
-            if (fused) { t2.v = a.rhs; t2.out = a.dy; }
-            else { t2.v = a.dy; t2.out = a.rhs; }
+            t2.only_flag = FLAG_REFINE; t2.out = nullptr;
+            t2.v = fused ? a.rhs : a.dy;
             launch_trsv(t2);
             if (!fused) kb_dir<NPL><<<B, KB_NT, smem_col, st>>>(a, 1, 1);
             else launch_kbf_dir(1, 1, tma, a, tmapA, B, m, st);
             count_launch();
+            IPM_TRY(debug_check("refinement pass", st));
         }
         g_prof.end_phase(PH_SOLVE, st);
         IPM_TRY(launch_check());
     }
     a.n_active = nact_base;
+    // ---- LPs parked by the corrector pass: the augmented-system kernel continues each from its current iterate
+    int handed = 0;
+    if (a.handoff) {
+        IPM_CUDA_OK(cudaMemcpyAsync(w.h_nact + 2, a.n_handoff, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        IPM_CUDA_OK(cudaStreamSynchronize(st));
+        handed = (int)w.h_nact[2];
+        const int slots = ka_slots(B, m, n);
+        KktArgs k;
+        k.A = a.A; k.b = a.b; k.c = a.c; k.x = a.x; k.s = a.s; k.y = a.y; k.scal = a.scal; k.iters = a.iters;
+        k.work = w.ka_work; k.m = m; k.n = n; k.tol = a.tol; k.eta = a.eta; k.max_iter = a.max_iter;
+        for (int first = 0; first < handed; first += slots) {
+            k.list = a.handoff_list + first;
+            IPM_TRY(ka_launch(k, std::min(slots, handed - first), st));
+            IPM_TRY(debug_check("augmented-system kernel", st));
+        }
+    }
+    g_last_handoffs.store(handed);
     IPM_CUDA_OK(cudaStreamSynchronize(st));
     if (iterations_run) *iterations_run = bodies;
     return IPM_OK;
@@ -763,11 +815,61 @@ int ipm_batched_set_variant(int three_pass, int refresh_every) {
 
 int ipm_batched_set_option(int option, int value) {
     switch (option) {
-        case IPM_BOPT_REFINE: g_opt.refine.store(value != 0); return IPM_OK;
+        case IPM_BOPT_REFINE: g_opt.refine.store(value < 0 ? 0 : (value > 2 ? 2 : value)); return IPM_OK;
         case IPM_BOPT_STRIP_TMA: g_opt.strip_tma.store(value != 0); return IPM_OK;
-        case IPM_BOPT_OVERLAP_RHS: g_opt.overlap_rhs.store(value != 0); return IPM_OK;
+        case IPM_BOPT_HANDOFF: g_opt.handoff.store(value < 0 ? 0 : (value > 2 ? 2 : value)); return IPM_OK;
         default: return IPM_ERR_ARG;
     }
+}
+
+int ipm_batched_last_handoffs(void) { return g_last_handoffs.load(); }
+
+int ipm_solve_dense_kkt(int device_ordinal, int m, int n, const double* A, const double* b, const double* c, double tol,
+                        int max_iter, double* x, double* y, double* s, double* obj, int* iters, int* status) {
+    if (!A || !b || !c || max_iter < 0) return IPM_ERR_ARG;
+    if (m <= 0 || n <= 0) return IPM_ERR_SHAPE;
+    if (m + n > KA_MAX_N) {
+        g_last_error = "ipm_solve_dense_kkt: n + m exceeds " + std::to_string(KA_MAX_N);
+        return IPM_ERR_SHAPE;
+    }
+    IPM_CUDA_OK(cudaSetDevice(device_ordinal));
+    struct Bufs {
+        double *A = nullptr, *vec = nullptr, *work = nullptr, *scal = nullptr;
+        int* ints = nullptr;
+        ~Bufs() { cudaFree(A); cudaFree(vec); cudaFree(work); cudaFree(scal); cudaFree(ints); }
+    } d;
+    const size_t nv = (size_t)2 * m + 3 * n;                 // b, y | c, x, s
+    IPM_CUDA_OK(cudaMalloc(&d.A, (size_t)m * n * sizeof(double)));
+    IPM_CUDA_OK(cudaMalloc(&d.vec, nv * sizeof(double)));
+    IPM_CUDA_OK(cudaMalloc(&d.work, (size_t)ka_work_doubles(m, n) * sizeof(double)));
+    IPM_CUDA_OK(cudaMalloc(&d.scal, S_COUNT * sizeof(double)));
+    IPM_CUDA_OK(cudaMalloc(&d.ints, 4 * sizeof(int)));
+    double *db = d.vec, *dy = db + m, *dc = dy + m, *dx = dc + n, *ds = dx + n;
+    IPM_CUDA_OK(cudaMemcpy(d.A, A, (size_t)m * n * sizeof(double), cudaMemcpyHostToDevice));
+    IPM_CUDA_OK(cudaMemcpy(db, b, (size_t)m * sizeof(double), cudaMemcpyHostToDevice));
+    IPM_CUDA_OK(cudaMemcpy(dc, c, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+    BatchArgs ba;
+    memset(&ba, 0, sizeof(ba));
+    ba.b = db; ba.c = dc; ba.x = dx; ba.s = ds; ba.y = dy; ba.scal = d.scal; ba.active = d.ints; ba.iters = d.ints + 1;
+    ba.m = m; ba.n = n;
+    kb_init<<<1, 256>>>(ba, 1, 0);                           // |b|, |c|; x = s = 1, y = 0 (main.py:287-302)
+    count_launch();
+    KktArgs k;
+    k.A = d.A; k.b = db; k.c = dc; k.x = dx; k.s = ds; k.y = dy; k.scal = d.scal; k.iters = d.ints + 1; k.list = nullptr;
+    k.work = d.work; k.m = m; k.n = n; k.tol = tol; k.eta = 0.91; k.max_iter = max_iter;
+    IPM_TRY(ka_launch(k, 1, 0));
+    double hs[S_COUNT];
+    int hi[4];
+    IPM_CUDA_OK(cudaMemcpy(hs, d.scal, sizeof(hs), cudaMemcpyDeviceToHost));
+    IPM_CUDA_OK(cudaMemcpy(hi, d.ints, sizeof(hi), cudaMemcpyDeviceToHost));
+    if (x) IPM_CUDA_OK(cudaMemcpy(x, dx, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (y) IPM_CUDA_OK(cudaMemcpy(y, dy, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost));
+    if (s) IPM_CUDA_OK(cudaMemcpy(s, ds, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+    const bool finite = std::isfinite(hs[S_NRB]) && std::isfinite(hs[S_NRC]) && std::isfinite(hs[S_XS]) && std::isfinite(hs[S_OBJ]);
+    if (obj) *obj = hs[S_OBJ];
+    if (iters) *iters = hi[1];
+    if (status) *status = !finite ? IPM_STATUS_NAN : (hs[S_CONT] > 0.5 ? IPM_STATUS_MAX_ITER : IPM_STATUS_CONVERGED);
+    return IPM_OK;
 }
 
 int ipm_profile_enable(int on) {
@@ -858,7 +960,7 @@ int ipm_solve_batched_dense_d(int device_ordinal, int B, int m, int n, const dou
     }
     unsigned* h_nact = nullptr;
     int rc = [&]() -> int {
-        IPM_CUDA_OK(cudaMallocHost(&h_nact, 2 * sizeof(unsigned)));
+        IPM_CUDA_OK(cudaMallocHost(&h_nact, 4 * sizeof(unsigned)));
         IPM_TRY(solve_on_device(B, m, n, A_d, b_d, c_d, tol, max_iter, obj_d, iters_d, status_d, x_d, work_d, h_nact,
                                 0, iterations_run));
         IPM_CUDA_OK(cudaStreamSynchronize(0));
@@ -945,7 +1047,7 @@ int ipm_solve_batched_dense(int device_ordinal, int B, int m, int n, const doubl
             C.dev = device_ordinal;
             IPM_CUDA_OK(cudaStreamCreateWithFlags(&C.s_copy, cudaStreamNonBlocking));
             IPM_CUDA_OK(cudaStreamCreateWithFlags(&C.s_comp, cudaStreamNonBlocking));
-            IPM_CUDA_OK(cudaMallocHost(&C.h_nact, 2 * sizeof(unsigned)));
+            IPM_CUDA_OK(cudaMallocHost(&C.h_nact, 4 * sizeof(unsigned)));
         }
         while ((int)C.landed.size() < nchunks) {
             cudaEvent_t e = nullptr;

@@ -17,10 +17,15 @@
 //     max d / min d passes 1e19 that is not well enough for |rb| to keep falling - an LP that has not met
 //     check_optimality by then stays trapped at the boundary (generator LPs 16893, 31186).  q = A dx is already
 //     here, so delta = -rb - q is free: when |delta| > |rb| - the step would not reduce the primal residual at
-//     all - the LP is not updated; delta goes to a.rhs, the LP is flagged FLAG_REFINE, the host's next two launches
-//     (triangular solve dy += M^-1 delta, then this kernel again with pass = 1, both for flagged LPs only) redo
-//     the corrector from the refined dy.  On the CPU restatement the rule fires 0.02 times per LP and leaves all
-//     65536 generator LPs at 15-20 iterations (tests/golden/batch_256x512_oracle.npz).
+//     all - the LP is not updated; delta goes to a.rhs, the LP is flagged FLAG_REFINE, and the host's next two
+//     launches (triangular solve ddy = M^-1 delta in place, then this kernel again with pass = 1, both for flagged
+//     LPs only) apply the step INCREMENTALLY: dx += d (A^T ddy), ds re-formed from dx, dy += ddy.  (Re-forming dx
+//     from the refined dy would bring back the cancellation noise eps d_max |t| of the large-d columns, which is
+//     what the step removes.)  If the refined direction STILL has |delta| > |rb|, the normal equations have broken
+//     down for this LP - a safeguarded pivot on a row that is not dependent: numerically degenerate vertex - and
+//     the LP is parked (a.handoff_list) for the augmented-system kernel (kkt_dense.cuh), which continues it from
+//     its current iterate.  On the CPU restatement the step is taken by 1.4 % of the generator's LPs, 0.1 % are
+//     handed off, and all 65536 finish in the reference's iteration count +-1 (tests/golden/batch_256x512_*).
 // With the predictor right-hand side (kb_rhs, one pass) an iteration reads A four times instead of six.
 #pragma once
 #include <cuda.h>      // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, no -lcuda)
@@ -56,6 +61,9 @@ struct BatchArgs {
     int fresh_every;   // 3-pass path: residuals are re-evaluated from scratch every fresh_every-th iteration (0 = only
                        // when the recurrences report convergence)
     int refine;        // 1: conditional refinement of the corrector (see kbf_dir / kb_dir), 0: off
+    int handoff;       // 1: an LP whose refined corrector still violates A dx = -rb leaves the loop (handoff_list)
+    int* handoff_list; // [B] LP indices parked for the augmented-system kernel (kkt_dense.cuh)
+    unsigned* n_handoff;
 };
 constexpr int FLAG_REFINE = 3;    // active[] value between the corrector pass that asks for a refinement and the one that
                                   // applies it
@@ -141,7 +149,9 @@ __global__ void __launch_bounds__(KF_NTT, 1) kbf_dir(const BatchArgs a, const in
     if (tid == 0) {
         for (int k = 0; k < KF_AHEAD && k < nstrips; ++k) issue(k, k * SB, k);
     }
-    for (int i = tid; i < mr; i += KF_NTT) dys[i] = (i < m) ? a.dy[om + i] : 0.0;
+    // pass 1 streams ddy (the in-place refinement solve left it in a.rhs); dy itself is only needed for y
+    const double* dy_src = (pass == 0) ? a.dy : a.rhs;
+    for (int i = tid; i < mr; i += KF_NTT) dys[i] = (i < m) ? dy_src[om + i] : 0.0;
     const double sigma_mu = (KIND == 1) ? scal[S_SIGMA_MU] : 0.0;
     // Everything of the elementwise formulas that does not depend on u (it holds the divisions), for all columns,
     // by all threads, while the first strips are on their way:
@@ -161,7 +171,7 @@ __global__ void __launch_bounds__(KF_NTT, 1) kbf_dir(const BatchArgs a, const in
             } else {
                 const double rcomp = xi * si + a.dxa[on + k] * a.dsa[on + k] - sigma_mu;
                 g1 = rcomp / xi;
-                v0 = di * (a.rc[on + k] - g1);
+                v0 = (pass == 0) ? di * (a.rc[on + k] - g1) : a.dxc[on + k];      // pass 1: dx = dx_old + d (A^T ddy)
             }
         }
         gsm[k] = di; gsm[npad + k] = v0; gsm[2 * npad + k] = g1; gsm[3 * npad + k] = g2; gsm[4 * npad + k] = g3;
@@ -199,9 +209,10 @@ __global__ void __launch_bounds__(KF_NTT, 1) kbf_dir(const BatchArgs a, const in
                 if (KIND == 0) { e1 = g3 * (dxi * dsi); e2 = g3; }
                 else e1 = dxi;
                 if (col < n) {
+                    // A^T dy + ds (change of rc per unit dual step); pass 1: A^T (dy + ddy) = (w_old - ds_old) + u
+                    if (KIND == 1) a.w[on + col] = (pass == 0) ? (u + dsi) : ((a.w[on + col] - a.dsc[on + col]) + u + dsi);
                     dxo[on + col] = dxi;
                     dso[on + col] = dsi;
-                    if (KIND == 1) a.w[on + col] = u + dsi;       // A^T dy + ds: change of rc per unit dual step
                 } else {
                     e1 = e2 = 0.0;
                 }
@@ -298,7 +309,7 @@ __global__ void __launch_bounds__(KF_NTT, 1) kbf_dir(const BatchArgs a, const in
         const double sm = s_val[2];
         for (int i = tid; i < m; i += KF_NTT) a.rhs[om + i] = a.rhs[om + i] + q1s[i] - sm * q2s[i];
     } else {
-        if (a.refine && pass == 0) {
+        if (a.refine) {
             // delta = -rb - A dx against rb (both squared norms in index order: deterministic)
             double nd2 = 0.0, nr2 = 0.0;
             for (int i = tid; i < m; i += KF_NTT) {
@@ -309,15 +320,34 @@ __global__ void __launch_bounds__(KF_NTT, 1) kbf_dir(const BatchArgs a, const in
             nd2 = block_red<RED_SUM>(nd2, sh);
             if (tid == 0) s_val[2] = nd2;
             nr2 = block_red<RED_SUM>(nr2, sh);
-            if (tid == 0) s_val[3] = (s_val[2] > nr2) ? 1.0 : 0.0;      // NaN compares false: no refinement
+            if (tid == 0) {
+                // NaN compares false: no refinement.  floor: 1e-3 of the stopping threshold of |rb| (main.py:170) -
+                // below it the primal residual is converged whatever delta does
+                const double fl = 1e-3 * a.tol * (1.0 + scal[S_NB]);
+                s_val[3] = (s_val[2] > nr2 && s_val[2] > fl * fl) ? 1.0 : 0.0;
+                // test hooks (ipm_batched_set_option value 2): refine every corrector / hand every LP off
+                if ((pass == 0 && a.refine == 2) || (pass != 0 && a.handoff == 2)) s_val[3] = 1.0;
+            }
             __syncthreads();
             if (s_val[3] != 0.0) {
-                for (int i = tid; i < m; i += KF_NTT) a.rhs[om + i] = -a.rb[om + i] - q1s[i];
-                if (tid == 0) {
-                    a.active[lp] = FLAG_REFINE;
-                    scal[S_NREFINE] = scal[S_NREFINE] + 1.0;
+                if (pass == 0) {
+                    for (int i = tid; i < m; i += KF_NTT) a.rhs[om + i] = -a.rb[om + i] - q1s[i];
+                    if (tid == 0) {
+                        a.active[lp] = FLAG_REFINE;
+                        scal[S_NREFINE] = scal[S_NREFINE] + 1.0;
+                    }
+                    return;
                 }
-                return;
+                if (a.handoff) {
+                    // the refined corrector still does not restore A dx = -rb: park the LP (no update)
+                    if (tid == 0) {
+                        const unsigned slot = atomicAdd(a.n_handoff, 1u);
+                        a.handoff_list[slot] = lp;
+                        scal[S_HANDOFF] = 1.0;
+                        a.active[lp] = 0;
+                    }
+                    return;
+                }
             }
         }
         ap = fmin(1.0, a.eta * ap);
@@ -337,7 +367,12 @@ __global__ void __launch_bounds__(KF_NTT, 1) kbf_dir(const BatchArgs a, const in
             obj += xn * a.c[on + k];
         }
         for (int i = tid; i < m; i += KF_NTT) {
-            a.y[om + i] = a.y[om + i] + ad * dys[i];
+            double dyi = dys[i];
+            if (pass != 0) {                       // dys holds ddy: the step is dy + ddy
+                dyi = a.dy[om + i] + dyi;
+                a.dy[om + i] = dyi;
+            }
+            a.y[om + i] = a.y[om + i] + ad * dyi;
             const double r = a.rb[om + i] + ap * q1s[i];
             a.rb[om + i] = r;
             nrb2 += r * r;

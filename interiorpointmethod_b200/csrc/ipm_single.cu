@@ -57,6 +57,8 @@ struct ipm_handle {
     double* M = nullptr;
     int64_t ldm = 0;
     TrsvPipeWs pipe;              // m > PIPE_MIN_M: inverses of the diagonal blocks + flags of the pipelined solves
+    unsigned char* dep = nullptr; // m bytes: dependent rows of A (ipm_detect_dependent_rows), nullptr = none
+    int n_dep = 0;
     double* scal = nullptr;
     double* partials = nullptr;
     unsigned* counter = nullptr;
@@ -64,9 +66,12 @@ struct ipm_handle {
     double tol = 1e-8;
     double eta = 0.91;            // main.py:607
     double tau = 1e-30;
+    double refine_thresh = -1.0;  // >= 0: conditional refinement of the corrector (ipm_set_refinement); off by default
     // one predictor-corrector iteration captured as a CUDA graph (the small Netlib LPs are launch-bound)
     cudaGraphExec_t gexec = nullptr;
     double g_tol = 0.0, g_tau = 0.0;
+    bool g_dep = false;
+    double g_refine = -1.0;
     bool use_graph = true;
     int64_t launches_per_graph = 0;
     bool have_resid = false, have_M = false, have_factor = false, have_pred = false, have_sigma = false,
@@ -100,7 +105,8 @@ int cuda_fail(ipm_handle* h) {
 void free_problem(ipm_handle* h) {
     cudaSetDevice(h->dev);
     if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
-    void* ptrs[] = {h->vslab, h->A_own, h->gemv_partial, h->slab, h->M, h->pipe.Linv, h->pipe.flags};
+    void* ptrs[] = {h->vslab, h->A_own, h->gemv_partial, h->slab, h->M, h->pipe.Linv, h->pipe.flags, h->dep};
+    h->dep = nullptr; h->n_dep = 0;
     h->pipe = TrsvPipeWs();
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -221,8 +227,10 @@ int assemble_step(ipm_handle* h) {
     return IPM_OK;
 }
 
-int factor_step(ipm_handle* h, double tau) {
-    H_TRY((potrf_single_auto(h->M, h->ldm, h->m, h->scal, tau, h->st)));
+int factor_step(ipm_handle* h, double tau, int dep_mode = 1) {
+    DepMask dm;
+    dm.mask = h->dep; dm.mode = h->dep ? dep_mode : 0;
+    H_TRY((potrf_single_auto(h->M, h->ldm, h->m, h->scal, tau, h->st, dm)));
     if (h->pipe.Linv) H_TRY(trinv_blocks(h->M, h->ldm, h->m, h->pipe, h->st));
     h->have_factor = true;
     h->have_M = false;
@@ -245,6 +253,21 @@ int direction_step(ipm_handle* h, int kind) {
                                                       h->eta, h->scal, h->partials, h->counter);
     count_launch();
     H_TRY(launch_check());
+    if (kind == 1 && h->refine_thresh >= 0.0) {
+        // delta = -rb - A dx -> rhs; M ddy = delta -> tm; dy += ddy when |delta| > thresh |rb|; dx, ds again
+        H_TRY(matvec_A(h, dxo, h->tm));
+        k_refine_delta<<<vec_grid(h->m), VEC_NT, 0, h->st>>>(h->rb, h->tm, h->rhs, h->m, h->refine_thresh, h->scal,
+                                                             h->partials, h->counter);
+        count_launch();
+        H_TRY(solve_factored(h, h->rhs, h->tm));
+        k_add_if<<<vec_grid(h->m), VEC_NT, 0, h->st>>>(dyo, h->tm, h->m, h->scal + S_REFINE_FLAG);
+        count_launch();
+        H_TRY(matvec_AT(h, dyo, h->tn));
+        k_direction<<<vec_grid(h->n), VEC_NT, 0, h->st>>>(kind, h->tn, h->d, h->w, h->rcx, h->x, h->s, dxo, dso, h->n,
+                                                          h->eta, h->scal, h->partials, h->counter);
+        count_launch();
+        H_TRY(launch_check());
+    }
     if (kind == 0) { h->have_pred = true; h->have_sigma = false; h->have_corr = false; }
     else h->have_corr = true;
     return IPM_OK;
@@ -538,6 +561,39 @@ int ipm_start_mehrotra(ipm_handle* h) {
     return IPM_OK;
 }
 
+int ipm_set_refinement(ipm_handle* h, double thresh) {
+    if (!h) return IPM_ERR_ARG;
+    h->refine_thresh = (thresh >= 0.0) ? thresh : -1.0;
+    return IPM_OK;
+}
+
+int ipm_detect_dependent_rows(ipm_handle* h, double rel_tol, int* n_dependent) {
+    H_TRY(check_handle(h));
+    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }      // the captured iteration holds the mask pointer
+    if (h->dep) { H_CUDA(cudaFree(h->dep)); h->dep = nullptr; h->n_dep = 0; }
+    if (n_dependent) *n_dependent = 0;
+    if (!(rel_tol > 0.0)) return IPM_OK;                  // off
+    const int m = h->m, n = h->n;
+    H_CUDA(cudaMalloc(&h->dep, (size_t)m));
+    H_CUDA(cudaMemsetAsync(h->dep, 0, (size_t)m, h->st));
+    // M = A A^T (d = 1): as well scaled as M will ever be, so a pivot at round-off level means "this row is a
+    // combination of the rows before it"
+    k_fill<<<vec_grid(n), VEC_NT, 0, h->st>>>(h->d, n, 1.0);
+    count_launch();
+    H_TRY(assemble_step(h));
+    H_TRY(factor_step(h, rel_tol, 2));
+    std::vector<unsigned char> host((size_t)m);
+    H_CUDA(cudaMemcpyAsync(host.data(), h->dep, (size_t)m, cudaMemcpyDeviceToHost, h->st));
+    H_CUDA(cudaStreamSynchronize(h->st));
+    int cnt = 0;
+    for (unsigned char v : host) cnt += v ? 1 : 0;
+    h->n_dep = cnt;
+    if (cnt == 0) { H_CUDA(cudaFree(h->dep)); h->dep = nullptr; }      // full row rank: nothing to carry around
+    if (n_dependent) *n_dependent = cnt;
+    h->have_resid = h->have_M = h->have_factor = h->have_pred = h->have_sigma = h->have_corr = false;
+    return IPM_OK;
+}
+
 int ipm_set_state(ipm_handle* h, const double* x, const double* y, const double* s) {
     H_TRY(check_handle(h));
     if (!x || !y || !s) return fail(h, IPM_ERR_ARG, "null pointer");
@@ -684,7 +740,8 @@ int ipm_solve(ipm_handle* h, double tol, int max_iter, int y0_is_one, double* x,
         H_CUDA(cudaMemcpyAsync(h->h_scal, h->scal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, h->st));
         return IPM_OK;
     };
-    if (h->gexec && (h->g_tol != tol || h->g_tau != tau)) {
+    if (h->gexec && (h->g_tol != tol || h->g_tau != tau || h->g_dep != (h->dep != nullptr) ||
+                     h->g_refine != h->refine_thresh)) {
         cudaGraphExecDestroy(h->gexec);
         h->gexec = nullptr;
     }
@@ -706,7 +763,7 @@ int ipm_solve(ipm_handle* h, double tol, int max_iter, int y0_is_one, double* x,
                 ce = cudaGraphInstantiate(&h->gexec, graph, 0);
                 cudaGraphDestroy(graph);
                 if (ce != cudaSuccess) return fail(h, IPM_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(ce));
-                h->g_tol = tol; h->g_tau = tau;
+                h->g_tol = tol; h->g_tau = tau; h->g_dep = h->dep != nullptr; h->g_refine = h->refine_thresh;
             } else {
                 count_launch(h->launches_per_graph);
             }

@@ -1,0 +1,410 @@
+// Dense predictor-corrector iteration on the AUGMENTED system, one CTA per LP: the reference's dense path
+// (`create_matrix` main.py:13-21 + `np.linalg.solve` main.py:178 = LAPACK dgesv on the unreduced (m+2n) KKT matrix)
+// with ds eliminated exactly (ds = -s dx/x - rcomp/x), i.e. order n + m:
+//        [ -D^-1  A^T ] [dx]   [ -(rc - rcomp/x) ]
+//        [   A     0  ] [dy] = [       -rb        ]          D = diag(x/s)
+// factored by LU with PARTIAL PIVOTING like dgesv.  It never pivots on the tiny s_j/x_j of the basic variables, so it
+// keeps the primal block row A dx = -rb to working precision where the normal equations M = A D A^T cannot: on a
+// (nearly) degenerate vertex M is numerically singular once max d / min d passes 1e19, the safeguarded Cholesky
+// drops a row that is NOT dependent, and an LP that has not met check_optimality (main.py:169-173) by then never
+// will (generator LPs 16893, 31186, 54456 ...: thousands of iterations, the reference needs 17-18).
+//
+// Used (a) by the batched solver as the hand-off target for exactly those LPs (ipm_batched.cu: the corrector pass
+// detects |(-rb - A dx)| > |rb| after a refinement step and parks the LP; this kernel continues it from its current
+// iterate), about one LP in a thousand, and (b) stand-alone through ipm_solve_dense_kkt (parity tests against the
+// reference's goldens: same Newton system, same pivoting rule => same iteration counts).
+// The tests compare it with a CPU restatement of the same formulas (`direction_augmented` in the test infrastructure).
+//
+// One CTA of 1024 threads does everything for its LP; the matrix K (order N = n + m) lives in global memory (L2
+// resident: 4.7 MB at 256 x 512), panels of 16 columns are factored in shared memory.  It is a robustness path, not a
+// throughput path: (2/3) N^3 flop per iteration on one SM (about 2 ms at 256 x 512).
+#pragma once
+#include "common.cuh"
+
+namespace ipm {
+
+constexpr int KA_NT = 1024;
+constexpr int KA_NW = KA_NT / 32;
+constexpr int KA_PW = 16;                      // panel width
+constexpr int KA_MAX_N = 1600;                 // order n + m the panel buffer admits (200 KB)
+
+struct KktArgs {
+    const double* A;        // [B][m][n]
+    const double* b;        // [B][m]
+    const double* c;        // [B][n]
+    double *x, *s;          // [B][n]   iterate, continued in place
+    double* y;              // [B][m]
+    double* scal;           // [B][S_COUNT]  S_NB, S_NC in; norms, objective, S_CONT out
+    int* iters;             // [B]           continued
+    const int* list;        // [count] LP indices to process (nullptr: LP = blockIdx.x)
+    double* work;           // per CTA: ka_work_doubles(m, n)
+    int m, n;
+    double tol, eta;
+    int max_iter;
+};
+
+#ifdef __CUDACC__
+#define KA_HD __host__ __device__
+#else
+#define KA_HD
+#endif
+KA_HD inline int64_t ka_ldk(int m, int n) { return ((int64_t)m + n + 1) / 2 * 2; }
+KA_HD inline int64_t ka_work_doubles(int m, int n) {
+    const int64_t N = (int64_t)m + n;
+    const int64_t v = N * ka_ldk(m, n) + N /*piv (as ints)*/ + (int64_t)m /*rb*/ + 6 * (int64_t)n;
+    return (v + 15) / 16 * 16;
+}
+inline size_t ka_smem_bytes(int m, int n) {
+    const size_t N = (size_t)m + n;
+    return (N * KA_PW + 32 * 33 + 64) * sizeof(double);
+}
+
+#ifdef __CUDACC__
+// argmax |v| with the lowest index on ties (LAPACK idamax): result valid in ALL threads.
+__device__ __forceinline__ void ka_block_argmax(double v, int idx, double* shv, int* shi, double& vout, int& iout) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    }
+    __syncthreads();
+    if (lane == 0) { shv[w] = v; shi[w] = idx; }
+    __syncthreads();
+    v = shv[lane]; idx = shi[lane];                 // KA_NW == 32 warps
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    }
+    vout = v; iout = idx;
+}
+
+// block sum / min, result in ALL threads
+template <int OP>
+__device__ __forceinline__ double ka_block_all(double v, double* sh, double* bc) {
+    v = block_red<OP>(v, sh);
+    if (threadIdx.x == 0) *bc = v;
+    __syncthreads();
+    v = *bc;
+    __syncthreads();
+    return v;
+}
+
+// In-place LU with partial pivoting of K (N x N, row-major, leading dimension ld), blocked by KA_PW columns.
+// piv[k] = row swapped with row k at step k (LAPACK ipiv, 0-based).
+__device__ void ka_lu_factor(double* K, int N, int64_t ld, int* piv, double* Psm, double* shv, int* shi) {
+    const int tid = threadIdx.x;
+    for (int k0 = 0; k0 < N; k0 += KA_PW) {
+        const int pw = (N - k0 < KA_PW) ? (N - k0) : KA_PW;
+        const int rows = N - k0;
+        // (1) panel -> shared memory
+        for (int idx = tid; idx < rows * KA_PW; idx += KA_NT) {
+            const int r = idx / KA_PW, cc = idx - r * KA_PW;
+            Psm[idx] = (cc < pw) ? K[(size_t)(k0 + r) * ld + k0 + cc] : 0.0;
+        }
+        __syncthreads();
+        // (2) unblocked LU of the panel
+        for (int j = 0; j < pw; ++j) {
+            double best = -1.0;
+            int bi = 0x7fffffff;
+            for (int r = j + tid; r < rows; r += KA_NT) {
+                const double av = fabs(Psm[r * KA_PW + j]);
+                if (av > best) { best = av; bi = r; }       // first maximum, like idamax; NaN never compares greater
+            }
+            double bv; int br;
+            ka_block_argmax(best, bi, shv, shi, bv, br);
+            if (br == 0x7fffffff) br = j;                   // all NaN / empty
+            if (tid == 0) piv[k0 + j] = k0 + br;
+            if (br != j && tid < KA_PW) {
+                const double t0 = Psm[j * KA_PW + tid];
+                Psm[j * KA_PW + tid] = Psm[br * KA_PW + tid];
+                Psm[br * KA_PW + tid] = t0;
+            }
+            __syncthreads();
+            const double p = Psm[j * KA_PW + j];
+            for (int r = j + 1 + tid; r < rows; r += KA_NT) {
+                double* pr = Psm + r * KA_PW;
+                const double l = pr[j] / p;
+                pr[j] = l;
+                for (int cc = j + 1; cc < pw; ++cc) pr[cc] = fma(-l, Psm[j * KA_PW + cc], pr[cc]);
+            }
+            __syncthreads();
+        }
+        // (3) panel back to K
+        for (int idx = tid; idx < rows * KA_PW; idx += KA_NT) {
+            const int r = idx / KA_PW, cc = idx - r * KA_PW;
+            if (cc < pw) K[(size_t)(k0 + r) * ld + k0 + cc] = Psm[idx];
+        }
+        // (4) the panel's row interchanges on the columns outside the panel, in order
+        for (int j = 0; j < pw; ++j) {
+            const int r1 = k0 + j, r2 = piv[k0 + j];        // written by thread 0 before a barrier above
+            if (r1 != r2) {
+                for (int cc = tid; cc < N; cc += KA_NT) {
+                    if (cc >= k0 && cc < k0 + pw) continue;
+                    const double t0 = K[(size_t)r1 * ld + cc];
+                    K[(size_t)r1 * ld + cc] = K[(size_t)r2 * ld + cc];
+                    K[(size_t)r2 * ld + cc] = t0;
+                }
+            }
+            __syncthreads();
+        }
+        // (5) U12 = L11^-1 K12 and the trailing update K22 -= L21 U12: one thread owns a column of both
+        const int c0 = k0 + pw;
+        for (int cc = c0 + tid; cc < N; cc += KA_NT) {
+            double u[KA_PW];
+#pragma unroll
+            for (int r = 0; r < KA_PW; ++r) {
+                double v = 0.0;
+                if (r < pw) {
+                    v = K[(size_t)(k0 + r) * ld + cc];
+                    for (int q = 0; q < r; ++q) v = fma(-Psm[r * KA_PW + q], u[q], v);
+                    K[(size_t)(k0 + r) * ld + cc] = v;
+                }
+                u[r] = v;
+            }
+            for (int i = c0; i < N; ++i) {
+                const double* lr = Psm + (size_t)(i - k0) * KA_PW;
+                double acc = K[(size_t)i * ld + cc];
+#pragma unroll
+                for (int r = 0; r < KA_PW; ++r) acc = fma(-lr[r], u[r], acc);
+                K[(size_t)i * ld + cc] = acc;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Solve with the factors: vec (N, shared memory) <- K^-1 vec.  blk = 32 x 33 staging of one diagonal block.
+__device__ void ka_lu_solve(const double* K, int N, int64_t ld, const int* piv, double* vec, double* blk) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int k = 0; k < N; ++k) {
+            const int p = piv[k];
+            if (p != k) { const double t0 = vec[k]; vec[k] = vec[p]; vec[p] = t0; }
+        }
+    }
+    __syncthreads();
+    const int nblk = (N + 31) >> 5;
+    // forward, unit lower
+    for (int I = 0; I < nblk; ++I) {
+        const int i0 = I << 5;
+        const int i = i0 + warp;                                  // 32 warps <-> 32 rows
+        if (i < N) {
+            const double* row = K + (size_t)i * ld;
+            double acc = 0.0;
+            for (int k = lane; k < i0; k += 32) acc = fma(row[k], vec[k], acc);
+            acc = warp_sum(acc);
+            blk[warp * 33 + lane] = (i0 + lane < i) ? row[i0 + lane] : 0.0;      // strictly lower part of the block
+            if (lane == 0) vec[i] -= acc;
+        } else {
+            blk[warp * 33 + lane] = 0.0;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double v = (i0 + lane < N) ? vec[i0 + lane] : 0.0;
+#pragma unroll 8
+            for (int q = 0; q < 32; ++q) {
+                const double vq = __shfl_sync(0xffffffffu, v, q);
+                if (lane > q) v = fma(-blk[lane * 33 + q], vq, v);
+            }
+            if (i0 + lane < N) vec[i0 + lane] = v;
+        }
+        __syncthreads();
+    }
+    // backward, upper with diagonal
+    for (int I = nblk - 1; I >= 0; --I) {
+        const int i0 = I << 5;
+        const int i = i0 + warp;
+        const int k1 = (i0 + 32 < N) ? i0 + 32 : N;
+        if (i < N) {
+            const double* row = K + (size_t)i * ld;
+            double acc = 0.0;
+            for (int k = k1 + lane; k < N; k += 32) acc = fma(row[k], vec[k], acc);
+            acc = warp_sum(acc);
+            blk[warp * 33 + lane] = (i0 + lane >= i && i0 + lane < N) ? row[i0 + lane] : 0.0;   // upper part incl. diagonal
+            if (lane == 0) vec[i] -= acc;
+        } else {
+            blk[warp * 33 + lane] = (lane == warp) ? 1.0 : 0.0;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double v = (i0 + lane < N) ? vec[i0 + lane] : 0.0;
+            const double dg = blk[lane * 33 + lane];
+#pragma unroll 8
+            for (int q = 31; q >= 0; --q) {
+                const double vq = __shfl_sync(0xffffffffu, v / dg, q);     // lane q's final value
+                if (lane == q) v = vq;
+                else if (lane < q) v = fma(-blk[lane * 33 + q], vq, v);
+            }
+            if (i0 + lane < N) vec[i0 + lane] = v;
+        }
+        __syncthreads();
+    }
+}
+
+static __global__ void __launch_bounds__(KA_NT, 1) ka_solve(const KktArgs a) {
+    extern __shared__ __align__(16) double smem_ka[];
+    double* Psm = smem_ka;                                  // [N][KA_PW] panel; the solves keep their vector here
+    double* blk = smem_ka + (size_t)(a.m + a.n) * KA_PW;    // [32][33]
+    __shared__ double sh[32];
+    __shared__ double shv[32];
+    __shared__ int shi[32];
+    __shared__ double bc;
+    const int lp = a.list ? a.list[blockIdx.x] : blockIdx.x;
+    const int m = a.m, n = a.n, N = m + n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t ld = ka_ldk(m, n);
+    const double* A = a.A + (size_t)lp * m * n;
+    const double* b = a.b + (size_t)lp * m;
+    const double* c = a.c + (size_t)lp * n;
+    double* x = a.x + (size_t)lp * n;
+    double* s = a.s + (size_t)lp * n;
+    double* y = a.y + (size_t)lp * m;
+    double* scal = a.scal + (size_t)lp * S_COUNT;
+    double* W = a.work + (size_t)blockIdx.x * ka_work_doubles(m, n);
+    double* K = W;                          W += (size_t)N * ld;
+    int* piv = reinterpret_cast<int*>(W);   W += N;
+    double* rb = W;                         W += m;
+    double* rc = W;                         W += n;
+    double* dxa = W;                        W += n;
+    double* dsa = W;                        W += n;
+    double* dx = W;                         W += n;
+    double* ds = W;                         W += n;
+    double* tt = W;                         // [n] rcomp / x of the current right-hand side
+    double* vec = Psm;
+    const double nb = scal[S_NB], nc = scal[S_NC];
+    int it = a.iters[lp];
+
+    for (;;) {
+        // ---- residuals of the current iterate, from scratch (main.py:67-70), check_optimality (main.py:169-173)
+        double nrb2 = 0.0;
+        for (int i = warp; i < m; i += KA_NW) {
+            const double* row = A + (size_t)i * n;
+            double acc = 0.0;
+            for (int k = lane; k < n; k += 32) acc = fma(row[k], x[k], acc);
+            acc = warp_sum(acc);
+            if (lane == 0) {
+                const double r = acc - b[i];
+                rb[i] = r;
+                nrb2 += r * r;
+            }
+        }
+        double nrc2 = 0.0, xs = 0.0, obj = 0.0;
+        for (int j = tid; j < n; j += KA_NT) {
+            double acc = 0.0;
+            for (int i = 0; i < m; ++i) acc = fma(A[(size_t)i * n + j], y[i], acc);
+            const double r = acc + s[j] - c[j];
+            rc[j] = r;
+            nrc2 += r * r;
+            xs += x[j] * s[j];
+            obj += x[j] * c[j];
+        }
+        nrb2 = ka_block_all<RED_SUM>(nrb2, sh, &bc);
+        nrc2 = ka_block_all<RED_SUM>(nrc2, sh, &bc);
+        xs = ka_block_all<RED_SUM>(xs, sh, &bc);
+        obj = ka_block_all<RED_SUM>(obj, sh, &bc);
+        const double nrb = sqrt(nrb2), nrc = sqrt(nrc2);
+        const bool cont = (a.tol * (1.0 + nb) < nrb) || (a.tol * (1.0 + nc) < nrc) || (a.tol < xs);
+        if (tid == 0) {
+            scal[S_NRB2] = nrb2; scal[S_NRB] = nrb; scal[S_NRC2] = nrc2; scal[S_NRC] = nrc;
+            scal[S_XS] = xs; scal[S_OBJ] = obj; scal[S_CONT] = cont ? 1.0 : 0.0;
+        }
+        if (!cont || it >= a.max_iter) break;
+
+        // ---- K = [[-D^-1, A^T], [A, 0]]
+        for (int64_t idx = tid; idx < (int64_t)N * ld; idx += KA_NT) K[idx] = 0.0;
+        __syncthreads();
+        for (int j = tid; j < n; j += KA_NT) K[(size_t)j * ld + j] = -(s[j] / x[j]);
+        for (int64_t idx = tid; idx < (int64_t)m * n; idx += KA_NT) {
+            const int i = (int)(idx / n), j = (int)(idx - (int64_t)i * n);
+            const double v = A[idx];
+            K[(size_t)(n + i) * ld + j] = v;
+            K[(size_t)j * ld + n + i] = v;
+        }
+        __syncthreads();
+        ka_lu_factor(K, N, ld, piv, Psm, shv, shi);
+
+        // ---- predictor (main.py:66-76, 101-109): rcomp = x s
+        for (int j = tid; j < n; j += KA_NT) {
+            const double q = (x[j] * s[j]) / x[j];
+            tt[j] = q;
+            vec[j] = -(rc[j] - q);
+        }
+        for (int i = tid; i < m; i += KA_NT) vec[n + i] = -rb[i];
+        __syncthreads();
+        ka_lu_solve(K, N, ld, piv, vec, blk);
+        double minp = 1.0, mind = 1.0;
+        for (int j = tid; j < n; j += KA_NT) {
+            const double dxi = vec[j];
+            const double dsi = (-s[j] * dxi / x[j]) - tt[j];
+            dxa[j] = dxi; dsa[j] = dsi;
+            if (dxi < 0.0) minp = fmin(minp, -x[j] / dxi);
+            if (dsi < 0.0) mind = fmin(mind, -s[j] / dsi);
+        }
+        const double apa = ka_block_all<RED_MIN>(minp, sh, &bc);
+        const double ada = ka_block_all<RED_MIN>(mind, sh, &bc);
+        double part = 0.0;
+        for (int j = tid; j < n; j += KA_NT) part += (x[j] + apa * dxa[j]) * (s[j] + ada * dsa[j]);
+        part = ka_block_all<RED_SUM>(part, sh, &bc);
+        const double mu_aff = part / (double)n, mu = xs / (double)n;
+        const double ratio = mu_aff / mu, sigma = ratio * ratio * ratio;       // main.py:598-600, unclamped
+        const double sigma_mu = sigma * mu;
+
+        // ---- corrector (main.py:142-159): rcomp = x s + dxa dsa - sigma mu
+        for (int j = tid; j < n; j += KA_NT) {
+            const double rcomp = x[j] * s[j] + dxa[j] * dsa[j] - sigma_mu;
+            const double q = rcomp / x[j];
+            tt[j] = q;
+            vec[j] = -(rc[j] - q);
+        }
+        for (int i = tid; i < m; i += KA_NT) vec[n + i] = -rb[i];
+        __syncthreads();
+        ka_lu_solve(K, N, ld, piv, vec, blk);
+        minp = 1.0; mind = 1.0;
+        for (int j = tid; j < n; j += KA_NT) {
+            const double dxi = vec[j];
+            const double dsi = (-s[j] * dxi / x[j]) - tt[j];
+            dx[j] = dxi; ds[j] = dsi;
+            if (dxi < 0.0) minp = fmin(minp, -x[j] / dxi);
+            if (dsi < 0.0) mind = fmin(mind, -s[j] / dsi);
+        }
+        double ap = ka_block_all<RED_MIN>(minp, sh, &bc);
+        double ad = ka_block_all<RED_MIN>(mind, sh, &bc);
+        ap = fmin(1.0, a.eta * ap);                                            // main.py:616-623
+        ad = fmin(1.0, a.eta * ad);
+        for (int j = tid; j < n; j += KA_NT) {
+            x[j] = x[j] + ap * dx[j];
+            s[j] = s[j] + ad * ds[j];
+        }
+        for (int i = tid; i < m; i += KA_NT) y[i] = y[i] + ad * vec[n + i];
+        ++it;
+        if (tid == 0) {
+            scal[S_AP_AFF] = apa; scal[S_AD_AFF] = ada; scal[S_MU_AFF] = mu_aff; scal[S_MU] = mu;
+            scal[S_SIGMA] = sigma; scal[S_SIGMA_MU] = sigma_mu; scal[S_AP] = ap; scal[S_AD] = ad;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) a.iters[lp] = it;
+}
+
+// count LPs (list[0..count), or LPs 0..count-1 when list is null), work_d: count * ka_work_doubles(m, n) doubles
+inline int ka_launch(const KktArgs& a, int count, cudaStream_t st) {
+    if (a.m + a.n > KA_MAX_N) {
+        g_last_error = "augmented-system kernel: n + m exceeds " + std::to_string(KA_MAX_N);
+        return IPM_ERR_SHAPE;
+    }
+    static DevOnce once;
+    IPM_TRY(once_per_device(once, []() -> int {
+        IPM_CUDA_OK(cudaFuncSetAttribute(ka_solve, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)((size_t)(KA_MAX_N * KA_PW + 32 * 33 + 64) * sizeof(double))));
+        return IPM_OK;
+    }));
+    ka_solve<<<count, KA_NT, ka_smem_bytes(a.m, a.n), st>>>(a);
+    count_launch();
+    return launch_check();
+}
+#endif
+
+}  // namespace ipm

@@ -163,6 +163,32 @@ static __global__ void k_update(double* x, double* y, double* s, const double* d
     }
 }
 
+// Conditional refinement of the corrector, single LP (same rule as the batched kbf_dir, ipm_batched_fused.cuh):
+// delta = -rb - A dx; flag = |delta| > thresh |rb| (NaN compares false).  The solve M ddy = delta runs
+// unconditionally (no host round trip inside the captured iteration), k_add_if applies it when the flag is set.
+static __global__ void k_refine_delta(const double* rb, const double* Adx, double* delta, int m, double thresh, double* scal,
+                                      double* partials, unsigned* counter) {
+    __shared__ double sh[32];
+    double acc[2] = {0.0, 0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+        const double r = rb[i], dl = -r - Adx[i];
+        delta[i] = dl;
+        acc[0] += dl * dl;
+        acc[1] += r * r;
+    }
+    double tot[2];
+    if (grid_reduce<2, RED_SUM, RED_SUM>(acc, partials, counter, sh, tot) && threadIdx.x == 0) {
+        const bool go = tot[0] > thresh * thresh * tot[1];
+        scal[S_REFINE_FLAG] = go ? 1.0 : 0.0;
+        if (go) scal[S_NREFINE] = scal[S_NREFINE] + 1.0;
+    }
+}
+static __global__ void k_add_if(double* v, const double* add, int len, const double* flag) {
+    if (!(*flag > 0.5)) return;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x)
+        v[i] = v[i] + add[i];
+}
+
 static __global__ void k_fill(double* v, int64_t len, double val) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x)
         v[i] = val;

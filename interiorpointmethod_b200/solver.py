@@ -205,6 +205,18 @@ class NewtonStep:
         self._check(self._lib.ipm_update(self._h, float(alpha_p), float(alpha_d)), "ipm_update")
 
     # ------------------------------------------------------------------ solve level
+    def detect_dependent_rows(self, rel_tol: float = 1e-10) -> int:
+        """Opt-in treatment of a rank-deficient A that is NOT in the reference (include/ipm_b200.h,
+        ipm_detect_dependent_rows); returns the number of dependent rows found.  rel_tol <= 0 clears the mask."""
+        nd = ctypes.c_int(0)
+        self._check(self._lib.ipm_detect_dependent_rows(self._h, float(rel_tol), ctypes.byref(nd)),
+                    "ipm_detect_dependent_rows")
+        return nd.value
+
+    def set_refinement(self, thresh: float | None):
+        """Opt-in conditional refinement of the corrector (include/ipm_b200.h, ipm_set_refinement); None = off."""
+        self._check(self._lib.ipm_set_refinement(self._h, -1.0 if thresh is None else float(thresh)), "ipm_set_refinement")
+
     def start_mehrotra(self):
         """Opt-in starting point that is NOT in the reference (include/ipm_b200.h, ipm_start_mehrotra)."""
         self._check(self._lib.ipm_start_mehrotra(self._h), "ipm_start_mehrotra")
@@ -229,13 +241,19 @@ class NewtonStep:
 
 # ====================================================================== reference-shaped functions
 def solve(A, b, c, tol: float = 1e-8, cTlb: float = 0.0, device: int = 0, max_iter: int = 5000,
-          y0_is_one: bool | None = None, start: str = "reference") -> Result:
+          y0_is_one: bool | None = None, start: str = "reference", dependent_rows: float | None = None,
+          refine: float | None = None) -> Result:
     """Load `benchmarks/*.mat`-style data, solve min c^T x s.t. Ax=b, x>=0; returns x, objective, iterations.
-    start="mehrotra" selects the opt-in starting point that is not in the reference (NewtonStep.solve)."""
+    start="mehrotra" selects the opt-in starting point that is not in the reference (NewtonStep.solve);
+    dependent_rows=1e-10 the opt-in elimination of linearly dependent rows (NewtonStep.detect_dependent_rows)."""
     is_sparse = _sp is not None and _sp.issparse(A)
     if y0_is_one is None:
         y0_is_one = is_sparse          # sparse driver starts y=1 (sparse_interior.py:193-200), dense y=0 (main.py:287-302)
     with NewtonStep(A, b, c, device=device) as ns:
+        if dependent_rows is not None:
+            ns.detect_dependent_rows(dependent_rows)
+        if refine is not None:
+            ns.set_refinement(refine)
         return ns.solve(tol=tol, max_iter=max_iter, y0_is_one=y0_is_one, cTlb=cTlb, start=start)
 
 
@@ -262,6 +280,25 @@ def interior(A, b, c, tol: float = 1e-20, device: int = 0, verbose: bool = True)
         print("k:\n", res.iterations)
         print("objective function:", res.objective)
     return res
+
+
+def interior_kkt(A, b, c, tol: float = 1e-20, device: int = 0, max_iter: int = 50000) -> Result:
+    """The reference's dense route itself on the GPU (`interior`, main.py:707-757 with `create_matrix` main.py:13-21 and
+    np.linalg.solve main.py:178): predictor-corrector on the augmented system (the unreduced KKT matrix with ds
+    eliminated exactly), LU with partial pivoting in one CTA (ipm_solve_dense_kkt).  Same Newton system and pivoting
+    rule as the reference, hence the same iteration counts; it is the batched solver's hand-off target for LPs whose
+    normal equations break down, and is exposed for parity tests.  n + m <= 1600."""
+    lib = _lib.load()
+    Ad = np.ascontiguousarray(np.asarray(A, dtype=np.float64))
+    m, n = Ad.shape
+    bb, cc = _f64(b, m), _f64(c, n)
+    x, y, s = np.empty(n), np.empty(m), np.empty(n)
+    obj, it, st = ctypes.c_double(0.0), ctypes.c_int(0), ctypes.c_int(0)
+    _lib.check(lib.ipm_solve_dense_kkt(int(device), m, n, _ptr(Ad), _ptr(bb), _ptr(cc), float(tol), int(max_iter), _ptr(x),
+                                       _ptr(y), _ptr(s), ctypes.byref(obj), ctypes.byref(it), ctypes.byref(st)), None,
+               "ipm_solve_dense_kkt")
+    return Result(x=_col(x), y=_col(y), s=_col(s), objective=float(obj.value), iterations=it.value,
+                  status=_lib.STATUS.get(st.value, str(st.value)), residuals={})
 
 
 _cache = {}

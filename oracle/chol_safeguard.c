@@ -14,7 +14,19 @@
 
 #define NB 48
 
+/* forced (nullable, m bytes): rows whose pivot is replaced whatever its value - the dependent rows of a
+ * rank-deficient A found once by ipm_detect_dependent_rows (include/ipm_b200.h); replaced (nullable, m bytes): out,
+ * 1 where the pivot was replaced (by the tiny-pivot rule or because it was forced). */
+int oracle_chol_safeguard_masked(double *M, int m, double tau, double big, const unsigned char *forced,
+                                 unsigned char *replaced, int *nfixed_out);
+
 int oracle_chol_safeguard(double *M, int m, double tau, double big, int *nfixed_out)
+{
+    return oracle_chol_safeguard_masked(M, m, tau, big, NULL, NULL, nfixed_out);
+}
+
+int oracle_chol_safeguard_masked(double *M, int m, double tau, double big, const unsigned char *forced,
+                                 unsigned char *replaced, int *nfixed_out)
 {
     if (!M || m < 0) return -1;
     double maxdiag = -INFINITY;
@@ -48,7 +60,9 @@ int oracle_chol_safeguard(double *M, int m, double tau, double big, int *nfixed_
             double *Lj = M + (size_t)j * m;
             double p = Lj[j];
             for (int k = j0; k < j; ++k) p -= Lj[k] * Lj[k];
-            if (!(p > thresh)) { p = big; ++nfixed; }
+            const int bad = !(p > thresh) || (forced && forced[j]);
+            if (bad) { p = big; ++nfixed; }
+            if (replaced) replaced[j] = (unsigned char)bad;
             const double ljj = sqrt(p);
             Lj[j] = ljj;
             for (int i = j + 1; i < j1; ++i) {

@@ -59,13 +59,13 @@ def initial_point(m, n, y0_is_one=True):
     return x, y, s
 
 
-def mehrotra_start(A, b, c, tau=PIVOT_TAU):
+def mehrotra_start(A, b, c, tau=PIVOT_TAU, forced=None):
     """NOT in the reference: Mehrotra's starting point (SIAM J. Optim. 2 (1992) sec. 7), the oracle of the product's
     opt-in `ipm_start_mehrotra`.  x = A^T (A A^T)^-1 b, y = (A A^T)^-1 A c, s = c - A^T y,
     then dx = max(-1.5 min x, 0), ds likewise, and the second shift 0.5 x^T s / sum(s) resp. / sum(x)."""
     m, n = A.shape
     one = np.ones((n, 1))
-    L, _ = cholesky_safeguarded(normal_matrix(A, one, one), tau)
+    L, _ = cholesky_safeguarded(normal_matrix(A, one, one), tau, forced=forced)
     x = A.T @ solve_with_factor(L, b)
     y = solve_with_factor(L, A @ c)
     s = c - A.T @ y
@@ -137,6 +137,27 @@ def direction_kkt(A, x, s, rb, rc, rcomp, dense=False):
     return sol[0:n], sol[n:n + m], sol[n + m:]
 
 
+def direction_augmented(A, x, s, rb, rc, rcomp):
+    """The same Newton system with only ds eliminated (ds = -s dx/x - rcomp/x, exact):
+        [ -D^-1  A^T ] [dx]   [ -(rc - rcomp/x) ]
+        [   A     0  ] [dy] = [       -rb        ]          D = diag(x/s)
+    solved by LU with partial pivoting (np.linalg.solve = LAPACK dgesv, the routine the reference's dense path calls
+    on its (m+2n) matrix, main.py:178).  Order n + m instead of m + 2n; unlike the normal equations it never pivots
+    on the tiny s_j/x_j of the basic variables, so it keeps the primal block row A dx = -rb to working precision on
+    (nearly) degenerate LPs - the executable spec of the batched solver's fallback kernel (csrc/kkt_dense.cuh)."""
+    A = np.asarray(A.todense()) if sparse.issparse(A) else A
+    m, n = A.shape
+    K = np.zeros((n + m, n + m))
+    K[np.arange(n), np.arange(n)] = -(s / x).ravel()
+    K[0:n, n:] = A.T
+    K[n:, 0:n] = A
+    t = rc - rcomp / x
+    sol = np.linalg.solve(K, np.vstack([-t, -rb]))
+    dx, dy = sol[0:n], sol[n:]
+    ds = (-s * dx / x) - (rcomp / x)
+    return dx, dy, ds
+
+
 # --------------------------------------------------------------------------- normal equations
 def normal_matrix(A, x, s):
     """M = A diag(x/s) A^T  (main.py:223-224); returns a dense ndarray."""
@@ -165,6 +186,9 @@ def _load_chol_lib():
     lib.oracle_chol_safeguard.restype = ctypes.c_int
     lib.oracle_chol_safeguard.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_double,
                                           ctypes.c_void_p]
+    lib.oracle_chol_safeguard_masked.restype = ctypes.c_int
+    lib.oracle_chol_safeguard_masked.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     _chol_lib = lib
     return lib
 
@@ -191,8 +215,10 @@ def cholesky_safeguarded_numpy(M, tau=PIVOT_TAU, big=PIVOT_BIG):
     return np.tril(L), nfixed
 
 
-def cholesky_safeguarded(M, tau=PIVOT_TAU, big=PIVOT_BIG):
+def cholesky_safeguarded(M, tau=PIVOT_TAU, big=PIVOT_BIG, forced=None, replaced_out=None):
     """Same rule, C implementation (left-looking, oracle/chol_safeguard.c).  Returns (L lower, n_fixed).
+    forced: optional uint8 mask of rows whose pivot is replaced unconditionally (dependent rows of A, see
+    detect_dependent_rows); replaced_out: optional uint8 array that receives which pivots were replaced.
 
     Iteration counts on degenerate LPs are sensitive to the rounding of the factorisation (SC50A: 35 with
     this accumulation order, 41 with the right-looking numpy one at tau=1e-30), so the oracle fixes one
@@ -203,10 +229,31 @@ def cholesky_safeguarded(M, tau=PIVOT_TAU, big=PIVOT_BIG):
     lib = _load_chol_lib()
     L = np.array(M, dtype=np.float64, order="C", copy=True)
     nfixed = ctypes.c_int(0)
-    rc = lib.oracle_chol_safeguard(L.ctypes.data, m, tau, big, ctypes.byref(nfixed))
+    if forced is None and replaced_out is None:
+        rc = lib.oracle_chol_safeguard(L.ctypes.data, m, tau, big, ctypes.byref(nfixed))
+    else:
+        f = None if forced is None else np.ascontiguousarray(forced, dtype=np.uint8)
+        rc = lib.oracle_chol_safeguard_masked(L.ctypes.data, m, tau, big, None if f is None else f.ctypes.data,
+                                              None if replaced_out is None else replaced_out.ctypes.data,
+                                              ctypes.byref(nfixed))
     if rc != 0:
         raise RuntimeError("oracle_chol_safeguard failed")
     return L, nfixed.value
+
+
+def detect_dependent_rows(A, rel_tol=1e-10):
+    """NOT in the reference (opt-in, the oracle of the product's `ipm_detect_dependent_rows`): rows of A that are
+    linear combinations of the rows before them, found by the Cholesky factorisation of A A^T (d = 1, where M is as
+    well scaled as it will ever be): pivot <= rel_tol * max diag  =>  dependent.  Their pivots are replaced by
+    PIVOT_BIG in every later factorisation, which removes the row from the normal equations (dy_i = 0) - the
+    LIPSOL / PCx treatment of rank-deficient constraint matrices.  Without it the pivots of such rows are
+    round-off (sometimes above the 1e-30 threshold of the safeguard, sometimes negative) and the iteration
+    crawls: QAP8 needs 196 iterations instead of 27."""
+    m, n = A.shape
+    one = np.ones((n, 1))
+    rep = np.zeros(m, dtype=np.uint8)
+    cholesky_safeguarded(normal_matrix(A, one, one), rel_tol, replaced_out=rep)
+    return rep
 
 
 def solve_with_factor(L, rhs):
@@ -271,7 +318,8 @@ def objective(x, c):
 
 
 # --------------------------------------------------------------------------- one iteration / whole solve
-def newton_iteration(A, b, c, x, y, s, linear="normal", dense=False, tau=PIVOT_TAU, info=None, refine_thresh=None):
+def newton_iteration(A, b, c, x, y, s, linear="normal", dense=False, tau=PIVOT_TAU, info=None, refine_thresh=None,
+                     forced=None, refine_abs=None, refine_rounds=1, handoff_floor=None):
     """One predictor-corrector iteration (main.py:781-805).  Returns new (x, y, s).
 
     refine_thresh (normal equations only; what the batched GPU solver does with thresh = 1): the corrector's dy
@@ -283,25 +331,51 @@ def newton_iteration(A, b, c, x, y, s, linear="normal", dense=False, tau=PIVOT_T
     rb, rc = residuals(A, b, c, x, y, s)
     r3 = x * s
     if linear == "normal":
-        L, nfixed = cholesky_safeguarded(normal_matrix(A, x, s), tau)
+        L, nfixed = cholesky_safeguarded(normal_matrix(A, x, s), tau, forced=forced)
         if info is not None:
             info["pivots_fixed"] = info.get("pivots_fixed", 0) + nfixed
         dxa, dya, dsa = direction_normal(A, L, x, s, rb, rc, r3)
+    elif linear == "augmented":
+        dxa, dya, dsa = direction_augmented(A, x, s, rb, rc, r3)
     else:
         dxa, dya, dsa = direction_kkt(A, x, s, rb, rc, r3, dense=dense)
     mu_aff, mu, sigma = sigma_mu(x, s, dxa, dsa)
     r4 = r3 + dxa * dsa - sigma * mu * np.ones_like(x)   # main.py:150-152
     if linear == "normal":
         dx, dy, ds = direction_normal(A, L, x, s, rb, rc, r4)
-        if refine_thresh is not None:
-            delta = -rb - A @ dx
-            if np.linalg.norm(delta) > refine_thresh * np.linalg.norm(rb):
-                d = x / s
-                dy = dy + solve_with_factor(L, delta)
-                dx = d * (A.T @ dy) + d * (rc - r4 / x)
+        if refine_thresh is not None or refine_abs is not None:
+            if refine_thresh is None:
+                refine_thresh = np.inf
+            d = x / s
+            nrb = np.linalg.norm(rb)
+            for _ in range(refine_rounds):
+                delta = -rb - A @ dx
+                nd = np.linalg.norm(delta)
+                if not ((nd > refine_thresh * nrb or (refine_abs is not None and nd > refine_abs))
+                        and (handoff_floor is None or nd > handoff_floor)):
+                    break
+                # INCREMENTAL: the correction d * (A^T ddy) is added to dx.  Re-forming dx = d (A^T dy + t) from the
+                # refined dy would bring back the cancellation noise eps * d_max * |t| of the large-d columns, which is
+                # exactly what the step is meant to remove (measured: |delta| 24.9 |rb| -> 10.3 |rb| re-formed,
+                # -> 1e-3 |rb| incremental, generator LP 31186).
+                ddy = solve_with_factor(L, delta)
+                dy = dy + ddy
+                dx = dx + d * (A.T @ ddy)
                 ds = (-s * dx / x) - (r4 / x)
                 if info is not None:
                     info["refinements"] = info.get("refinements", 0) + 1
+            else:
+                # every round taken and the primal block row is still not restored: the normal equations have broken
+                # down (safeguarded pivot on a row that is NOT dependent - a numerically degenerate vertex).  Hand
+                # the LP to the augmented system from THIS iterate (what the batched solver's fallback kernel does).
+                if handoff_floor is not None:
+                    nd = np.linalg.norm(-rb - A @ dx)
+                    if nd > nrb and nd > handoff_floor:
+                        if info is not None:
+                            info["handoff"] = True
+                        return newton_iteration(A, b, c, x, y, s, linear="augmented", info=info)
+    elif linear == "augmented":
+        dx, dy, ds = direction_augmented(A, x, s, rb, rc, r4)
     else:
         dx, dy, ds = direction_kkt(A, x, s, rb, rc, r4, dense=dense)
     ap, ad = full_stepsize(x, s, dx, ds)
@@ -312,7 +386,17 @@ def newton_iteration(A, b, c, x, y, s, linear="normal", dense=False, tau=PIVOT_T
 
 
 def solve(A, b, c, cTlb=0.0, tol=1e-8, max_iter=5000, y0_is_one=True, linear="normal", tau=PIVOT_TAU,
-          start="reference", refine_thresh=None):
+          start="reference", refine_thresh=None, dependent_tol=None, refine_abs_kappa=None, refine_rounds=1,
+          handoff=False):
+    """(see below)  handoff=True (with refine_thresh): the batched GPU solver's rule - when the refined corrector
+    still has |delta| > |rb| (and |delta| above 1e-3 of the stopping threshold of the primal residual), this and every
+    later iteration of the LP run on the augmented system (`direction_augmented`)."""
+    return _solve(A, b, c, cTlb, tol, max_iter, y0_is_one, linear, tau, start, refine_thresh, dependent_tol,
+                  refine_abs_kappa, refine_rounds, handoff)
+
+
+def _solve(A, b, c, cTlb, tol, max_iter, y0_is_one, linear, tau, start, refine_thresh, dependent_tol, refine_abs_kappa,
+           refine_rounds, handoff):
     """Whole solve with `interior_sparse` semantics (main.py:760-815) when y0_is_one, `interior`
     semantics (main.py:707-757; cap 50000, y0 = 0) otherwise.
 
@@ -327,19 +411,28 @@ def solve(A, b, c, cTlb=0.0, tol=1e-8, max_iter=5000, y0_is_one=True, linear="no
     c = as_column(c)
     m, n = A.shape
     x, y, s = initial_point(m, n, y0_is_one)
+    forced = None
+    if dependent_tol is not None and linear == "normal":
+        forced = detect_dependent_rows(A, dependent_tol)
     if start == "mehrotra":
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             with np.errstate(all="ignore"):
-                x, y, s = mehrotra_start(A, b, c, tau)
+                x, y, s = mehrotra_start(A, b, c, tau, forced=forced)
     k = 0
     info = {}
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         with np.errstate(all="ignore"):
+            floor = 1e-3 * tol * (1.0 + float(np.linalg.norm(b))) if handoff else None
             while continue_flag(A, b, c, x, y, s, tol, tol, tol) and k < max_iter:
+                if info.get("handoff"):
+                    linear = "augmented"
                 x, y, s = newton_iteration(A, b, c, x, y, s, linear=linear, dense=dense, tau=tau, info=info,
-                                           refine_thresh=refine_thresh)
+                                           handoff_floor=floor,
+                                           refine_thresh=refine_thresh, forced=forced, refine_rounds=refine_rounds,
+                                           refine_abs=None if refine_abs_kappa is None
+                                           else refine_abs_kappa * tol * (1.0 + float(np.linalg.norm(b))))
                 k += 1
     obj = objective(x, c) - float(cTlb)
     if not np.isfinite(obj) or not np.all(np.isfinite(x)):
@@ -349,7 +442,9 @@ def solve(A, b, c, cTlb=0.0, tol=1e-8, max_iter=5000, y0_is_one=True, linear="no
     else:
         status = 0
     return dict(x=x, y=y, s=s, k=k, obj=float(obj), status=status, pivots_fixed=info.get("pivots_fixed", 0),
-                refinements=info.get("refinements", 0))
+                refinements=info.get("refinements", 0),
+                dependent_rows=int(forced.sum()) if forced is not None else 0,
+                handoff=bool(info.get("handoff", False)), handoff_at=info.get("handoff_at"))
 
 
 # --------------------------------------------------------------------------- synthetic workloads

@@ -5,9 +5,10 @@
     python oracle/make_golden_batch.py reference FIRST LAST [workers]   -> tests/golden/batch_256x512_reference.json
                                                                            (build container only: /root/reference)
 
-oracle   : (k, objective, refinement steps) of oracle.ipm_oracle.solve(linear="normal", refine_thresh=1.0) - the
-           elimination and the refinement rule the GPU runs - for every seed of the range.  Ranges are merged into
-           the existing file, so the table can be extended.
+oracle   : (k, objective, refinement steps) of oracle.ipm_oracle.solve(linear="normal", refine_thresh=1.0,
+           handoff=True) - the elimination, the refinement rule and the hand-off to the augmented system that the GPU
+           runs - for every seed of the range (refinements + 64 marks an LP that was handed off).  Ranges are merged
+           into the existing file, so the table can be extended.
 reference: (k, objective) of the UNMODIFIED reference's dense driver `interior` (main.py:707-757: dense (m+2n) KKT
            + np.linalg.solve twice per iteration), replayed with its own functions by oracle/ref_harness.py, for
            seeds FIRST..LAST-1 plus the three seeds with a history (7466, 16893, 31186).
@@ -28,8 +29,8 @@ M, N, TOL, CAP = 256, 512, 1e-8, 150
 def work_oracle(seed):
     from oracle import ipm_oracle as O
     A, b, c = O.synthetic_dense_lp(M, N, seed)
-    r = O.solve(A, b, c, tol=TOL, max_iter=CAP, y0_is_one=False, linear="normal", refine_thresh=1.0)
-    return seed, r["k"], r["obj"], r["refinements"], r["status"]
+    r = O.solve(A, b, c, tol=TOL, max_iter=CAP, y0_is_one=False, linear="normal", refine_thresh=1.0, handoff=True)
+    return seed, r["k"], r["obj"], r["refinements"] + (64 if r["handoff"] else 0), r["status"]
 
 
 def work_reference(seed):
@@ -64,7 +65,8 @@ def main():
                 if st != 0 or kk > 21:
                     print("OUTLIER seed %d k %d status %d" % (seed, kk, st), flush=True)
         np.savez_compressed(path, k=k, obj=obj, refinements=ref, m=M, n=N, tol=TOL,
-                            how="oracle.ipm_oracle.solve(linear='normal', refine_thresh=1.0, y0_is_one=False)")
+                            how="oracle.ipm_oracle.solve(linear='normal', refine_thresh=1.0, handoff=True, y0_is_one=False); "
+                                "refinements >= 64: handed off to the augmented system")
         done = k[k > 0]
         print("oracle table: %d seeds, k histogram %s, %d s" % (done.size, dict(zip(*np.unique(done, return_counts=True))),
                                                              time.time() - t0))

@@ -226,35 +226,67 @@ def _batch_tables():
     gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
     ref = {int(k): v for k, v in json.load(open(os.path.join(gold, "batch_256x512_reference.json")))["seeds"].items()}
     tab = np.load(os.path.join(gold, "batch_256x512_oracle.npz"))
-    return ref, tab["k"].astype(int), tab["obj"], tab["refinements"].astype(int)
+    code = tab["refinements"].astype(int)          # refinement steps, + 64 when the LP was handed off
+    return ref, tab["k"].astype(int), tab["obj"], code % 64, code >= 64
 
 
 def test_batch_tables_are_complete_and_agree_with_the_unmodified_reference():
-    """tests/golden/batch_256x512_oracle.npz (oracle, normal equations + the refinement rule, all 65536 generator
-    seeds) against tests/golden/batch_256x512_reference.json (the UNMODIFIED reference's `interior`, seeds 0..511
-    and the three seeds with a history): every LP converges in 15..21 iterations, iteration count within +-1 and
-    objective within 1e-8 relative of the reference on every seed both tables hold."""
-    ref, k, obj, nref = _batch_tables()
-    assert k.shape == (65536,) and (k >= 15).all() and (k <= 21).all() and np.isfinite(obj).all()
+    """tests/golden/batch_256x512_oracle.npz (oracle: normal equations + refinement rule + hand-off to the augmented
+    system, all 65536 generator seeds) against tests/golden/batch_256x512_reference.json (the UNMODIFIED reference's
+    `interior`, seeds 0..511 and the three seeds with a history): every LP converges in 15..20 iterations; on every
+    seed both tables hold the iteration count is within +-1 (in fact equal) and the objective within 1e-8 relative."""
+    ref, k, obj, nref, handed = _batch_tables()
+    assert k.shape == (65536,) and (k >= 15).all() and (k <= 20).all() and np.isfinite(obj).all()
     seeds = np.array(sorted(ref))
     assert seeds.size >= 515 and {7466, 16893, 31186} <= set(ref)
     kr = np.array([ref[s][0] for s in seeds])
     orf = np.array([ref[s][1] for s in seeds])
     assert np.abs(k[seeds] - kr).max() <= 1
     assert (np.abs(obj[seeds] - orf) <= 1e-8 * np.maximum(1.0, np.abs(orf))).all()
-    assert 0.005 < (nref > 0).mean() < 0.05          # the rule fires on about one LP in fifty
+    assert 0.005 < (nref > 0).mean() < 0.05          # the refinement step: about one LP in seventy
+    assert 0.0002 < handed.mean() < 0.005            # the hand-off: about one LP in a thousand
+    assert handed[[16893, 31186]].all()              # the two LPs with a history are among them
 
 
-@pytest.mark.parametrize("seed", [0, 5, 7466, 16893, 31186, 40000, 65535])
-def test_oracle_refinement_rule_reproduces_its_table(seed):
-    """The table is what oracle.solve(linear="normal", refine_thresh=1.0) returns (regenerated here for a few seeds),
-    and without the rule LP 31186 is trapped (> 60 iterations) - the reason the rule exists."""
+@pytest.mark.parametrize("seed", [0, 5, 7466, 7954, 16893, 31186, 40000, 54456, 65535])
+def test_oracle_rule_reproduces_its_table_and_the_trap_is_real(seed):
+    """The table is what oracle.solve(linear="normal", refine_thresh=1.0, handoff=True) returns (regenerated here for a
+    few seeds); without refinement and hand-off LP 31186 is trapped (> 60 iterations) - the reason both exist."""
     from oracle import ipm_oracle as orc
-    _, k, obj, nref = _batch_tables()
+    _, k, obj, nref, handed = _batch_tables()
     A, b, c = orc.synthetic_dense_lp(256, 512, seed)
-    r = orc.solve(A, b, c, tol=1e-8, max_iter=150, y0_is_one=False, linear="normal", refine_thresh=1.0)
-    assert r["status"] == 0 and r["k"] == k[seed] and r["refinements"] == nref[seed]
+    r = orc.solve(A, b, c, tol=1e-8, max_iter=150, y0_is_one=False, linear="normal", refine_thresh=1.0, handoff=True)
+    assert r["status"] == 0 and r["k"] == k[seed] and r["refinements"] == nref[seed] and r["handoff"] == handed[seed]
     assert abs(r["obj"] - obj[seed]) <= 1e-12 * max(1.0, abs(obj[seed]))
     if seed == 31186:
         lit = orc.solve(A, b, c, tol=1e-8, max_iter=60, y0_is_one=False, linear="normal")
         assert lit["k"] == 60 and lit["status"] == 1
+
+
+@pytest.mark.parametrize("seed", [0, 3, 16893, 31186])
+def test_augmented_system_path_reproduces_the_reference(seed, dense_results):
+    """oracle.solve(linear="augmented") - the executable spec of the GPU's augmented-system kernel - against the
+    unmodified reference's `interior` (dense (m+2n) KKT + dgesv): same iteration count, objective to 1e-10."""
+    from oracle import ipm_oracle as orc
+    g = dense_results["synthetic_256x512_seed%d" % seed]
+    A, b, c = orc.synthetic_dense_lp(256, 512, seed)
+    r = orc.solve(A, b, c, tol=1e-8, max_iter=100, y0_is_one=False, linear="augmented")
+    assert r["status"] == 0 and r["k"] == g["k"]
+    assert abs(r["obj"] - g["obj"]) <= 1e-10 * abs(g["obj"])
+
+
+def test_dependent_row_elimination_on_qap8():
+    """Opt-in, not in the reference: rows of A that depend on the rows before them are found once from the factorisation
+    of A A^T and removed from every later factorisation.  QAP8 (742 of 912 rows independent): 17-19
+    iterations to the Netlib optimum 203.5 (main.py:1417-1516) instead of 196; a full-rank LP is untouched."""
+    from oracle import ipm_oracle as orc
+    import interiorpointmethod_b200.problems as P
+    A, b, c, cTlb = P.load_golden_problem("QAP8")
+    for start in ("reference", "mehrotra"):
+        r = orc.solve(A, b, c, cTlb=cTlb, tol=1e-8, max_iter=100, start=start, dependent_tol=1e-10)
+        assert r["status"] == 0 and r["k"] <= 25 and r["dependent_rows"] == 170
+        assert abs(r["obj"] - 203.5) <= 1e-8 * 203.5
+    A, b, c, cTlb = P.load_golden_problem("AFIRO")
+    r0 = orc.solve(A, b, c, cTlb=cTlb, tol=1e-8)
+    r1 = orc.solve(A, b, c, cTlb=cTlb, tol=1e-8, dependent_tol=1e-10)
+    assert r1["dependent_rows"] == 0 and r1["k"] == r0["k"] and r1["obj"] == r0["obj"]

