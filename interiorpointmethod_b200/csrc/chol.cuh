@@ -285,13 +285,8 @@ inline int potrf_blocked(double* M, int64_t ldm, int64_t strideM, int m, int bat
                          int64_t strideScal, double tau, const int* active, cudaStream_t st, DepMask dm = DepMask()) {
     auto kd = k_chol_diag<NB, NT_DIAG>;
     auto kt = k_chol_trsm<NB, ROWS>;
-    static DevOnce once;
-    IPM_TRY(once_per_device(once, [&]() -> int {
-        IPM_CUDA_OK(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_diag_smem<NB>()));
-        IPM_CUDA_OK(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)chol_trsm_smem<NB, ROWS>()));
-        return IPM_OK;
-    }));
+    IPM_TRY(ensure_dyn_smem(kd, chol_diag_smem<NB>()));
+    IPM_TRY(ensure_dyn_smem(kt, chol_trsm_smem<NB, ROWS>()));
     k_maxdiag<<<dim3(1, 1, batch), 256, 0, st>>>(M, ldm, strideM, m, scal, strideScal, active);
     count_launch();
     CholArgs a;
@@ -500,12 +495,8 @@ static __global__ void __launch_bounds__(TRSV128_NT, 1) k_trsv_bwd128(const Trsv
 
 // rhs (destroyed) -> sol.  L is the factor produced by potrf_blocked.
 inline int potrs_single_blocks(const double* L, int64_t ldm, int m, double* rhs, double* tmp, double* sol, cudaStream_t st) {
-    static DevOnce once;
-    IPM_TRY(once_per_device(once, []() -> int {
-        IPM_CUDA_OK(cudaFuncSetAttribute(k_trsv_fwd128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsv128_smem()));
-        IPM_CUDA_OK(cudaFuncSetAttribute(k_trsv_bwd128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsv128_smem()));
-        return IPM_OK;
-    }));
+    IPM_TRY(ensure_dyn_smem(k_trsv_fwd128, trsv128_smem()));
+    IPM_TRY(ensure_dyn_smem(k_trsv_bwd128, trsv128_smem()));
     TrsvArgs a;
     a.L = L; a.ldm = ldm; a.m = m;
     a.v = rhs; a.out = tmp;
@@ -805,12 +796,7 @@ inline int potrs_single(const double* L, int64_t ldm, int m, double* rhs, double
         TrsvBatchedArgs t;
         t.L = L; t.ldm = ldm; t.strideM = 0; t.v = rhs; t.strideV = 0; t.m = m; t.active = nullptr; t.out = sol;
         if (m <= 32 * TRSVI_MAX_BLK) {
-            static DevOnce once;
-            IPM_TRY(once_per_device(once, []() -> int {
-                IPM_CUDA_OK(cudaFuncSetAttribute(k_trsv_batched_inv, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)trsv_batched_inv_smem(32 * TRSVI_MAX_BLK)));
-                return IPM_OK;
-            }));
+            IPM_TRY(ensure_dyn_smem(k_trsv_batched_inv, trsv_batched_inv_smem(32 * TRSVI_MAX_BLK)));
             k_trsv_batched_inv<<<1, TRSVB_NT, trsv_batched_inv_smem(m), st>>>(t);
         } else
         k_trsv_batched<<<1, TRSVB_NT, trsv_batched_smem(m), st>>>(t);

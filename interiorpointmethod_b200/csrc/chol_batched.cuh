@@ -393,12 +393,7 @@ template <int NT>
 inline int potrf_batched_fused_nt(double* M, int64_t ldm, int64_t strideM, int m, int batch, double* scal,
                                   int64_t strideScal, double tau, const int* active, cudaStream_t st,
                                   unsigned char* dep = nullptr, int dep_mode = 0) {
-    static DevOnce once;
-    IPM_TRY(once_per_device(once, []() -> int {
-        IPM_CUDA_OK(cudaFuncSetAttribute(kb_chol<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kbc_smem_bytes(kbc_max_m(NT))));
-        return IPM_OK;
-    }));
+    IPM_TRY(ensure_dyn_smem(kb_chol<NT>, kbc_smem_bytes(kbc_max_m(NT))));
     CholBatchedArgs a;
     a.M = M; a.ldm = ldm; a.strideM = strideM; a.scal = scal; a.strideScal = strideScal; a.tau = tau; a.m = m;
     a.active = active;

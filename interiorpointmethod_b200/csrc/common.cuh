@@ -4,8 +4,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <atomic>
+#include <map>
 #include <mutex>
 #include <string>
+#include <utility>
 
 #include "../../include/ipm_b200.h"
 
@@ -42,24 +44,28 @@ inline int launch_check() {
     return IPM_OK;
 }
 
-// One-time per-device configuration of a kernel (cudaFuncSetAttribute for > 48 KB of dynamic shared memory): a
-// `static DevOnce` next to the launch, thread-safe, one flag per device ordinal (function attributes are per
-// device, so a process that drives several GPUs from several threads configures each of them exactly once).
-struct DevOnce {
-    std::mutex mu;
-    bool done[64] = {};
-};
-template <class F>
-inline int once_per_device(DevOnce& o, F&& configure) {
+// Dynamic shared memory above 48 KB needs cudaFuncAttributeMaxDynamicSharedMemorySize on the kernel, per device.
+// The registry is keyed on (kernel entry point, device ordinal): the kernels live in headers with internal linkage,
+// so every translation unit of the library has its OWN instance of each - a function-local "configured" flag inside
+// an inline launcher is shared by all of them (one merged variable) and leaves every instance but the first one
+// unconfigured ("invalid argument" at the first launch above 48 KB; found by running the single-LP tests before the
+// batched ones in one process).  Thread-safe; one map lookup per launch.
+inline int ensure_dyn_smem_ptr(const void* kernel, int bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, int> configured;
     int dev = 0;
     IPM_CUDA_OK(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64) return IPM_ERR_ARG;
-    std::lock_guard<std::mutex> lk(o.mu);
-    if (!o.done[dev]) {
-        IPM_TRY(configure());
-        o.done[dev] = true;
-    }
+    std::lock_guard<std::mutex> lk(mu);
+    auto key = std::make_pair(kernel, dev);
+    auto it = configured.find(key);
+    if (it != configured.end() && it->second >= bytes) return IPM_OK;
+    IPM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    configured[key] = bytes;
     return IPM_OK;
+}
+template <class K>
+inline int ensure_dyn_smem(K kernel, size_t bytes) {
+    return ensure_dyn_smem_ptr(reinterpret_cast<const void*>(kernel), (int)bytes);
 }
 
 static inline int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }

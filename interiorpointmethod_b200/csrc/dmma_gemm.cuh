@@ -196,11 +196,7 @@ template <int BM, int BN, int WM, int WN, int EPI>
 inline int dmma_nt_launch(const DmmaArgs& a, int batch, cudaStream_t st) {
     constexpr size_t smem = dmma_smem_bytes<BM, BN, WM, WN>();
     auto kern = dmma_nt_kernel<BM, BN, WM, WN, EPI>;
-    static DevOnce once;
-    IPM_TRY(once_per_device(once, [&]() -> int {
-        IPM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        return IPM_OK;
-    }));
+    IPM_TRY(ensure_dyn_smem(kern, smem));
     if (a.rowsP <= 0 || a.rowsQ <= 0 || batch <= 0) return IPM_OK;
     dim3 grid(ceil_div(a.rowsQ, BN), ceil_div(a.rowsP, BM), batch);
     kern<<<grid, WM * WN * 32, smem, st>>>(a);

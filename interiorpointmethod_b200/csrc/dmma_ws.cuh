@@ -300,11 +300,7 @@ inline bool ws_eligible(const DmmaArgs& a) {
 template <int EPI, bool SCALE>
 inline int dmma_ws_launch(const DmmaArgs& a, int batch, cudaStream_t st) {
     auto kern = dmma_ws_kernel<EPI, SCALE>;
-    static DevOnce once;
-    IPM_TRY(once_per_device(once, [&]() -> int {
-        IPM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_smem_bytes()));
-        return IPM_OK;
-    }));
+    IPM_TRY(ensure_dyn_smem(kern, ws_smem_bytes()));
     if (a.rowsP <= 0 || batch <= 0 || a.K <= 0) return IPM_OK;
     const int T = ceil_div(a.rowsP, WS_BM);
     const int ntri = a.col0_only ? T : T * (T + 1) / 2;      // tiles per matrix

@@ -390,12 +390,8 @@ inline int build_pattern(DevPattern& pat, const int32_t* h_ptr, const int32_t* h
         pat.device_built = false;
     } else {
         // ---- symbolic product on the device
-        static DevOnce sym_once;
-        IPM_TRY(once_per_device(sym_once, []() -> int {
-            IPM_CUDA_OK(cudaFuncSetAttribute(k_sym_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ING_SYM_MAX_SMEM));
-            IPM_CUDA_OK(cudaFuncSetAttribute(k_sym_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ING_SYM_MAX_SMEM));
-            return IPM_OK;
-        }));
+        IPM_TRY(ensure_dyn_smem(k_sym_rows<false>, ING_SYM_MAX_SMEM));
+        IPM_TRY(ensure_dyn_smem(k_sym_rows<true>, ING_SYM_MAX_SMEM));
         const size_t smem = (size_t)round_up((int64_t)m * sizeof(int32_t), 16);
         const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)200 * 1024) / std::max<size_t>(smem, 1)));
         const int grows = std::max(1, std::min(m, per_sm * kNumSMs));

@@ -435,7 +435,9 @@ __global__ void __launch_bounds__(KB_NT) kb_dir(const BatchArgs a, int kind, int
             nr2 = block_red<RED_SUM>(nr2, sh);
             if (tid == 0) {
                 const double fl = 1e-3 * a.tol * (1.0 + scal[S_NB]);            // see kbf_dir
-                s_alpha[3] = (s_alpha[2] > nr2 && s_alpha[2] > fl * fl) ? 1.0 : 0.0;   // NaN compares false
+                // pass 0: refine when |delta| > 0.1 |rb|; pass 1: hand off when the refined step still has |delta| > |rb|
+                const double lim2 = (pass == 0) ? KF_REFINE_THRESH * KF_REFINE_THRESH * nr2 : nr2;
+                s_alpha[3] = (s_alpha[2] > lim2 && s_alpha[2] > fl * fl) ? 1.0 : 0.0;   // NaN compares false
                 if ((pass == 0 && a.refine == 2) || (pass != 0 && a.handoff == 2)) s_alpha[3] = 1.0;    // test hooks
             }
             __syncthreads();
@@ -505,7 +507,7 @@ struct Workspace {
     double* M;
     int64_t ldm;
     double* ka_work;     // ka_slots * ka_work_doubles
-    unsigned* h_nact;    // pinned (3 words: two check slots + the hand-off count)
+    unsigned* h_nact;    // pinned, 8 words: [0,1] active LPs per check slot, [2,3] hand-off count per slot, [4] final
 };
 
 int64_t at_doubles(int B, int m, int n) {        // strip-major copy of A (3-pass path with IPM_BOPT_STRIP_TMA = 0 only)
@@ -578,9 +580,7 @@ void launch_kbf_dir(int kind, int pass, bool tma, const BatchArgs& a, const CUte
 
 template <int KIND, int NRP, int SRC>
 int kbf_configure() {
-    IPM_CUDA_OK(cudaFuncSetAttribute(kbf_dir<KIND, NRP, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)kf_smem_bytes(32 * NRP, 2 * KB_NT)));
-    return IPM_OK;
+    return ensure_dyn_smem(kbf_dir<KIND, NRP, SRC>, kf_smem_bytes(32 * NRP, 2 * KB_NT));
 }
 template <int NRP>
 int kbf_configure_nrp() {
@@ -609,20 +609,17 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
     a.refine = refine ? g_opt.refine.load() : 0;
     a.handoff = (refine && g_opt.handoff.load() != 0 && ka_slots(B, m, n) > 0) ? g_opt.handoff.load() : 0;
     IPM_CUDA_OK(cudaMemsetAsync(a.n_handoff, 0, sizeof(unsigned), st));
-    static DevOnce once;
-    IPM_TRY(once_per_device(once, [&]() -> int {
-        IPM_CUDA_OK(cudaFuncSetAttribute(kb_residual<NPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + 8192));
-        IPM_CUDA_OK(cudaFuncSetAttribute(kb_residual<NPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + 8192));
-        IPM_CUDA_OK(cudaFuncSetAttribute(kb_dir<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
+    {
+        IPM_TRY(ensure_dyn_smem(kb_residual<NPL, false>, 131072 + 8192));
+        IPM_TRY(ensure_dyn_smem(kb_residual<NPL, true>, 131072 + 8192));
+        IPM_TRY(ensure_dyn_smem(kb_dir<NPL>, 131072 + 16384));
         // every NRP instantiation the dispatcher can pick, at the largest n check_shape admits (NRP = 1,
         // m <= 32, needs more than 48 KB once n >= 466)
         IPM_TRY(kbf_configure_nrp<1>()); IPM_TRY(kbf_configure_nrp<2>());
         IPM_TRY(kbf_configure_nrp<4>()); IPM_TRY(kbf_configure_nrp<8>());
-        IPM_CUDA_OK(cudaFuncSetAttribute(k_trsv_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-        IPM_CUDA_OK(cudaFuncSetAttribute(k_trsv_batched_inv, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)trsv_batched_inv_smem(32 * TRSVI_MAX_BLK)));
-        return IPM_OK;
-    }));
+        IPM_TRY(ensure_dyn_smem(k_trsv_batched, 65536));
+        IPM_TRY(ensure_dyn_smem(k_trsv_batched_inv, trsv_batched_inv_smem(32 * TRSVI_MAX_BLK)));
+    }
     CUtensorMap tmapA;
     memset(&tmapA, 0, sizeof(tmapA));
     if (tma) IPM_TRY(kf_make_strip_tmap(&tmapA, a.A, B, m, n, 32 * kf_nrp(m)));
@@ -667,6 +664,30 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
     bool all_joined[2] = {true, true};          // per check slot: had every chunk joined when the check was enqueued?
     bool joined_pending = false;                // a chunk joined after the last check was enqueued
     const bool small_m = m <= 32 * TRSVI_MAX_BLK;
+    // LPs parked by the corrector pass (a.handoff_list) are continued by the augmented-system kernel on a second,
+    // higher-priority stream WHILE the lockstep loop runs on: a parked LP is off the loop's books (active = 0), its
+    // iterate is final, and one CTA per LP for a few milliseconds hides behind the remaining iterations.
+    cudaStream_t st_ka = nullptr;
+    struct KaGuard { cudaStream_t* s; ~KaGuard() { if (*s) cudaStreamDestroy(*s); } } ka_guard{&st_ka};
+    const int slots = ka_slots(B, m, n);
+    int ka_launched = 0;
+    KktArgs kk;
+    kk.A = a.A; kk.b = a.b; kk.c = a.c; kk.x = a.x; kk.s = a.s; kk.y = a.y; kk.scal = a.scal; kk.iters = a.iters;
+    kk.m = m; kk.n = n; kk.tol = a.tol; kk.eta = a.eta; kk.max_iter = a.max_iter;
+    if (a.handoff) {
+        int lo = 0, hi = 0;
+        IPM_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        IPM_CUDA_OK(cudaStreamCreateWithPriority(&st_ka, cudaStreamNonBlocking, hi));
+    }
+    auto launch_parked = [&](int upto) -> int {          // list entries [ka_launched, upto) whose state is final
+        upto = std::min(upto, slots);                    // the workspace has `slots` matrices; the rest waits
+        if (upto <= ka_launched) return IPM_OK;
+        kk.list = a.handoff_list + ka_launched;
+        kk.work = w.ka_work + (size_t)ka_launched * ka_work_doubles(m, n);
+        IPM_TRY(ka_launch(kk, upto - ka_launched, st_ka));
+        ka_launched = upto;
+        return IPM_OK;
+    };
     auto launch_trsv = [&](const TrsvBatchedArgs& t) {
         if (small_m) k_trsv_batched_inv<<<B, TRSVB_NT, trsv_batched_inv_smem(m), st>>>(t);
         else k_trsv_batched<<<B, TRSVB_NT, trsv_batched_smem(m), st>>>(t);
@@ -691,10 +712,14 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
         IPM_TRY(debug_check("kb_init / kb_residual", st));
         g_prof.end_phase(PH_RESID, st);
         IPM_CUDA_OK(cudaMemcpyAsync(w.h_nact + slot, a.n_active, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        if (a.handoff)
+            IPM_CUDA_OK(cudaMemcpyAsync(w.h_nact + 2 + slot, a.n_handoff, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
         IPM_CUDA_OK(cudaEventRecord(ev[slot], st));
         if (it > 0) {
             IPM_CUDA_OK(cudaEventSynchronize(ev[slot ^ 1]));
             const unsigned cnt = w.h_nact[slot ^ 1];
+            // everything the stream did before that check has completed: LPs parked by then can start now
+            if (a.handoff) IPM_TRY(launch_parked((int)w.h_nact[2 + (slot ^ 1)]));
             if (cnt == 0) {
                 if (all_joined[slot ^ 1]) break;
                 if (!counted_join) {
@@ -753,20 +778,20 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
         IPM_TRY(launch_check());
     }
     a.n_active = nact_base;
-    // ---- LPs parked by the corrector pass: the augmented-system kernel continues each from its current iterate
+    // ---- LPs parked late (or beyond the workspace's slots): the same kernel, now with the machine to itself
     int handed = 0;
     if (a.handoff) {
-        IPM_CUDA_OK(cudaMemcpyAsync(w.h_nact + 2, a.n_handoff, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        IPM_CUDA_OK(cudaMemcpyAsync(w.h_nact + 4, a.n_handoff, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
         IPM_CUDA_OK(cudaStreamSynchronize(st));
-        handed = (int)w.h_nact[2];
-        const int slots = ka_slots(B, m, n);
-        KktArgs k;
-        k.A = a.A; k.b = a.b; k.c = a.c; k.x = a.x; k.s = a.s; k.y = a.y; k.scal = a.scal; k.iters = a.iters;
-        k.work = w.ka_work; k.m = m; k.n = n; k.tol = a.tol; k.eta = a.eta; k.max_iter = a.max_iter;
-        for (int first = 0; first < handed; first += slots) {
-            k.list = a.handoff_list + first;
-            IPM_TRY(ka_launch(k, std::min(slots, handed - first), st));
-            IPM_TRY(debug_check("augmented-system kernel", st));
+        handed = (int)w.h_nact[4];
+        IPM_TRY(launch_parked(handed));
+        IPM_CUDA_OK(cudaStreamSynchronize(st_ka));
+        IPM_TRY(debug_check("augmented-system kernel", st_ka));
+        for (int first = ka_launched; first < handed; first += slots) {       // more LPs than slots: in rounds
+            kk.list = a.handoff_list + first;
+            kk.work = w.ka_work;
+            IPM_TRY(ka_launch(kk, std::min(slots, handed - first), st_ka));
+            IPM_CUDA_OK(cudaStreamSynchronize(st_ka));
         }
     }
     g_last_handoffs.store(handed);
@@ -960,7 +985,7 @@ int ipm_solve_batched_dense_d(int device_ordinal, int B, int m, int n, const dou
     }
     unsigned* h_nact = nullptr;
     int rc = [&]() -> int {
-        IPM_CUDA_OK(cudaMallocHost(&h_nact, 4 * sizeof(unsigned)));
+        IPM_CUDA_OK(cudaMallocHost(&h_nact, 8 * sizeof(unsigned)));
         IPM_TRY(solve_on_device(B, m, n, A_d, b_d, c_d, tol, max_iter, obj_d, iters_d, status_d, x_d, work_d, h_nact,
                                 0, iterations_run));
         IPM_CUDA_OK(cudaStreamSynchronize(0));
@@ -1047,7 +1072,7 @@ int ipm_solve_batched_dense(int device_ordinal, int B, int m, int n, const doubl
             C.dev = device_ordinal;
             IPM_CUDA_OK(cudaStreamCreateWithFlags(&C.s_copy, cudaStreamNonBlocking));
             IPM_CUDA_OK(cudaStreamCreateWithFlags(&C.s_comp, cudaStreamNonBlocking));
-            IPM_CUDA_OK(cudaMallocHost(&C.h_nact, 4 * sizeof(unsigned)));
+            IPM_CUDA_OK(cudaMallocHost(&C.h_nact, 8 * sizeof(unsigned)));
         }
         while ((int)C.landed.size() < nchunks) {
             cudaEvent_t e = nullptr;

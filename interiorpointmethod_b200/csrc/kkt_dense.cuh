@@ -395,12 +395,7 @@ inline int ka_launch(const KktArgs& a, int count, cudaStream_t st) {
         g_last_error = "augmented-system kernel: n + m exceeds " + std::to_string(KA_MAX_N);
         return IPM_ERR_SHAPE;
     }
-    static DevOnce once;
-    IPM_TRY(once_per_device(once, []() -> int {
-        IPM_CUDA_OK(cudaFuncSetAttribute(ka_solve, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)((size_t)(KA_MAX_N * KA_PW + 32 * 33 + 64) * sizeof(double))));
-        return IPM_OK;
-    }));
+    IPM_TRY(ensure_dyn_smem(ka_solve, (size_t)(KA_MAX_N * KA_PW + 32 * 33 + 64) * sizeof(double)));
     ka_solve<<<count, KA_NT, ka_smem_bytes(a.m, a.n), st>>>(a);
     count_launch();
     return launch_check();

@@ -252,11 +252,7 @@ static __global__ void __launch_bounds__(TP_NT, 1) k_trsv_pipe_bwd(const TrsvPip
 
 // inverses of all diagonal blocks of the factor (after potrf)
 inline int trinv_blocks(const double* L, int64_t ldm, int m, const TrsvPipeWs& ws, cudaStream_t st) {
-    static DevOnce once;
-    IPM_TRY(once_per_device(once, []() -> int {
-        IPM_CUDA_OK(cudaFuncSetAttribute(k_trinv128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trinv_smem()));
-        return IPM_OK;
-    }));
+    IPM_TRY(ensure_dyn_smem(k_trinv128, trinv_smem()));
     k_trinv128<<<ws.nblk, TP_NB, trinv_smem(), st>>>(L, ldm, m, ws.Linv);
     count_launch();
     return launch_check();
