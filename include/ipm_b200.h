@@ -276,6 +276,9 @@ double ipm_measure_dmma_peak(int device_ordinal);
  * C_lower = A diag(d) A^T for a dense row-major device matrix (the SYRK of main.py:224). */
 int ipm_syrk_d(int device_ordinal, int m, int n, const double *A_d, int64_t lda, const double *d_d,
                double *M_d, int64_t ldm);
+/* Stage width of the SYRK / trailing-update kernel's operand ring: 16 columns x 5 stages (default) or 32 x 3 (half as
+ * many stage boundaries per tile).  Process-wide, for A/B measurements; results are bitwise the same. */
+int ipm_set_syrk_stage_width(int columns);
 /* In-place safeguarded Cholesky of a dense row-major device matrix (lower). */
 int ipm_potrf_d(int device_ordinal, int m, double *M_d, int64_t ldm, double pivot_rel_thresh, int *n_fixed);
 

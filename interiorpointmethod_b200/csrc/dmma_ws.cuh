@@ -16,14 +16,19 @@
 
 namespace ipm {
 
-constexpr int WS_BM = 128, WS_BN = 128, WS_BK = 16, WS_LD = 20, WS_STAGES = 5;
+constexpr int WS_BM = 128, WS_BN = 128;
+// Stage geometry: BK columns per stage, LD = BK + 4 doubles per row (conflict-free 64-bit fragment reads: the row
+// stride is 8 banks mod 32 for both), as many stages as fit 227 KB.  BK = 16 x 5 stages is the round-1 kernel; BK = 32 x 3
+// halves the number of stage boundaries (mbarrier wait + release per consumer warp) per tile.
+template <int BK> struct WsGeom {
+    static constexpr int LD = BK + 4;
+    static constexpr int STAGES = (BK == 16) ? 5 : 3;
+    static constexpr size_t smem = (size_t)STAGES * ((WS_BM + WS_BN) * LD + BK) * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
+};
 constexpr int WS_CONSUMER_WARPS = 8;
 constexpr int WS_PRODUCER_WARPS = 2;    // warp 8 streams P (and d), warp 9 streams Q
 constexpr int WS_THREADS = (WS_CONSUMER_WARPS + WS_PRODUCER_WARPS) * 32;
 
-constexpr size_t ws_smem_bytes() {
-    return (size_t)WS_STAGES * ((WS_BM + WS_BN) * WS_LD + WS_BK) * sizeof(double) + 2 * WS_STAGES * sizeof(uint64_t);
-}
 
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -66,11 +71,11 @@ __device__ __forceinline__ void tri_decode(int t, int& bi, int& bj) {
 // Diagonal tile (bi == bj): only the lower triangle is needed.  The 128 rows are cut into 16 strips of 8 rows;
 // strip s needs the 8x8 sub-tiles 0..s.  Consumer warp W takes strips W and 15-W = (W+1) + (16-W) = 17 sub-tiles
 // for every warp, against 32 in a full tile, so a diagonal tile costs 53 % of an off-diagonal one.
-template <int W, int EPI, bool SCALE>
+template <int W, int EPI, bool SCALE, int WS_BK>
 __device__ __forceinline__ void ws_diag_tile(const DmmaArgs& a, const double* Ps, const double* Qs, const double* Ds,
                                              uint64_t* full, uint64_t* empty, uint32_t& it, int nk, int z, int row0,
                                              int lane) {
-    constexpr int LD = WS_LD, S = WS_STAGES;
+    constexpr int LD = WsGeom<WS_BK>::LD, S = WsGeom<WS_BK>::STAGES;
     constexpr int N0 = W + 1, N1 = 16 - W;
     constexpr int R0 = 8 * W, R1 = 8 * (15 - W);
     const int g = lane >> 2, t = lane & 3;
@@ -130,9 +135,11 @@ __device__ __forceinline__ void ws_diag_tile(const DmmaArgs& a, const double* Ps
     for (int j = 0; j < N1; ++j) store(row0 + R1 + g, row0 + 8 * j + 2 * t, acc1[j][0], acc1[j][1]);
 }
 
-template <int EPI, bool SCALE>
+template <int EPI, bool SCALE, int WS_BK>
 __global__ void __launch_bounds__(WS_THREADS, 1) dmma_ws_kernel(const DmmaArgs a, int ntri, int total_tiles) {
-    constexpr int LD = WS_LD, S = WS_STAGES;
+    constexpr int LD = WsGeom<WS_BK>::LD, S = WsGeom<WS_BK>::STAGES;
+    constexpr int HK = WS_BK / 2;                 // lanes that cover one row of a slab (16 bytes each)
+    constexpr int RPP = 32 / HK;                  // rows per pass of a producer warp
     extern __shared__ __align__(128) unsigned char ws_raw[];
     double* Ps = reinterpret_cast<double*>(ws_raw);            // [S][128][LD]
     double* Qs = Ps + S * WS_BM * LD;                          // [S][128][LD]
@@ -157,8 +164,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dmma_ws_kernel(const DmmaArgs a
     if (warp >= WS_CONSUMER_WARPS) {
         // ------------------------------------------------------------------ producers
         const bool isQ = (warp != WS_CONSUMER_WARPS);
-        const int rsub = lane >> 3;                 // row inside a group of 4
-        const int kq = (lane & 7) * 2;              // this lane's column pair inside the slab
+        const int rsub = lane / HK;                 // row inside a group of RPP
+        const int kq = (lane % HK) * 2;             // this lane's column pair inside the slab
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int z = tile / ntri;
             if (a.active && a.active[z] == 0) continue;
@@ -172,7 +179,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dmma_ws_kernel(const DmmaArgs a
             const double* dv = (SCALE && !isQ) ? a.dvec + (size_t)z * a.strideD : nullptr;
             const bool rows_full = r0 + WS_BM <= nrows;
             const double* src0 = base + (size_t)(r0 + rsub) * ld + kq;
-            const size_t rstep = (size_t)4 * ld;
+            const size_t rstep = (size_t)RPP * ld;
             for (int kt = 0; kt < nk; ++kt, ++it) {
                 const int s = it % S;
                 mbar_wait(empty + s, ((it / S) & 1) ^ 1);
@@ -181,19 +188,19 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dmma_ws_kernel(const DmmaArgs a
                 if (rows_full && k0 + WS_BK <= K) {
                     const double* src = src0 + k0;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) cp_async16_zfill(dst + j * 4 * LD, src + j * rstep, 16u);
-                    if (dv != nullptr && lane < 8) cp_async16_zfill(Ds + s * WS_BK + kq, dv + k0 + kq, 16u);
+                    for (int j = 0; j < WS_BM / RPP; ++j) cp_async16_zfill(dst + j * RPP * LD, src + j * rstep, 16u);
+                    if (dv != nullptr && lane < HK) cp_async16_zfill(Ds + s * WS_BK + kq, dv + k0 + kq, 16u);
                 } else {
                     const int k = k0 + kq;
                     const uint32_t kbytes = (k + 1 < K) ? 16u : ((k < K) ? 8u : 0u);
 #pragma unroll 4
-                    for (int j = 0; j < 32; ++j) {
-                        const int gr = r0 + rsub + 4 * j;
+                    for (int j = 0; j < WS_BM / RPP; ++j) {
+                        const int gr = r0 + rsub + RPP * j;
                         const uint32_t nb = (gr < nrows) ? kbytes : 0u;
                         const double* src = nb ? base + (size_t)gr * ld + k : base;
-                        cp_async16_zfill(dst + j * 4 * LD, src, nb);
+                        cp_async16_zfill(dst + j * RPP * LD, src, nb);
                     }
-                    if (dv != nullptr && lane < 8) cp_async16_zfill(Ds + s * WS_BK + kq, kbytes ? dv + k : dv, kbytes);
+                    if (dv != nullptr && lane < HK) cp_async16_zfill(Ds + s * WS_BK + kq, kbytes ? dv + k : dv, kbytes);
                 }
                 cp_async_mbar_arrive_noinc(full + s);
             }
@@ -212,14 +219,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dmma_ws_kernel(const DmmaArgs a
             if (bi == bj) {
                 const int r0d = bi * WS_BM;
                 switch (warp) {
-                    case 0: ws_diag_tile<0, EPI, SCALE>(a, Ps, Qs, Ds, full, empty, it, nk, z, r0d, lane); break;
-                    case 1: ws_diag_tile<1, EPI, SCALE>(a, Ps, Qs, Ds, full, empty, it, nk, z, r0d, lane); break;
-                    case 2: ws_diag_tile<2, EPI, SCALE>(a, Ps, Qs, Ds, full, empty, it, nk, z, r0d, lane); break;
-                    case 3: ws_diag_tile<3, EPI, SCALE>(a, Ps, Qs, Ds, full, empty, it, nk, z, r0d, lane); break;
-                    case 4: ws_diag_tile<4, EPI, SCALE>(a, Ps, Qs, Ds, full, empty, it, nk, z, r0d, lane); break;
-                    case 5: ws_diag_tile<5, EPI, SCALE>(a, Ps, Qs, Ds, full, empty, it, nk, z, r0d, lane); break;
-                    case 6: ws_diag_tile<6, EPI, SCALE>(a, Ps, Qs, Ds, full, empty, it, nk, z, r0d, lane); break;
-                    default: ws_diag_tile<7, EPI, SCALE>(a, Ps, Qs, Ds, full, empty, it, nk, z, r0d, lane); break;
+                    case 0: ws_diag_tile<0, EPI, SCALE, WS_BK>(a, Ps, Qs, Ds, full, empty, it, nk, z, r0d, lane); break;
+                    case 1: ws_diag_tile<1, EPI, SCALE, WS_BK>(a, Ps, Qs, Ds, full, empty, it, nk, z, r0d, lane); break;
+                    case 2: ws_diag_tile<2, EPI, SCALE, WS_BK>(a, Ps, Qs, Ds, full, empty, it, nk, z, r0d, lane); break;
+                    case 3: ws_diag_tile<3, EPI, SCALE, WS_BK>(a, Ps, Qs, Ds, full, empty, it, nk, z, r0d, lane); break;
+                    case 4: ws_diag_tile<4, EPI, SCALE, WS_BK>(a, Ps, Qs, Ds, full, empty, it, nk, z, r0d, lane); break;
+                    case 5: ws_diag_tile<5, EPI, SCALE, WS_BK>(a, Ps, Qs, Ds, full, empty, it, nk, z, r0d, lane); break;
+                    case 6: ws_diag_tile<6, EPI, SCALE, WS_BK>(a, Ps, Qs, Ds, full, empty, it, nk, z, r0d, lane); break;
+                    default: ws_diag_tile<7, EPI, SCALE, WS_BK>(a, Ps, Qs, Ds, full, empty, it, nk, z, r0d, lane); break;
                 }
                 continue;
             }
@@ -297,10 +304,16 @@ inline bool ws_eligible(const DmmaArgs& a) {
            (!a.dvec || (al16(a.dvec) && a.strideD % 2 == 0)) && a.lower_only && a.rowsP == a.rowsQ;
 }
 
-template <int EPI, bool SCALE>
-inline int dmma_ws_launch(const DmmaArgs& a, int batch, cudaStream_t st) {
-    auto kern = dmma_ws_kernel<EPI, SCALE>;
-    IPM_TRY(ensure_dyn_smem(kern, ws_smem_bytes()));
+inline std::atomic<int>& ws_stage_width() {          // 16 (default) or 32: ipm_set_syrk_stage_width, A/B measurements
+    static std::atomic<int> bk{16};
+    return bk;
+}
+
+template <int EPI, bool SCALE, int BK>
+inline int dmma_ws_launch_bk(const DmmaArgs& a, int batch, cudaStream_t st) {
+    auto kern = dmma_ws_kernel<EPI, SCALE, BK>;
+    constexpr size_t smem = WsGeom<BK>::smem;
+    IPM_TRY(ensure_dyn_smem(kern, smem));
     if (a.rowsP <= 0 || batch <= 0 || a.K <= 0) return IPM_OK;
     const int T = ceil_div(a.rowsP, WS_BM);
     const int ntri = a.col0_only ? T : T * (T + 1) / 2;      // tiles per matrix
@@ -308,9 +321,14 @@ inline int dmma_ws_launch(const DmmaArgs& a, int batch, cudaStream_t st) {
     if (total > 0x7fffffff) return IPM_ERR_SHAPE;
     const int cap = (a.max_ctas > 0 && a.max_ctas < kNumSMs) ? a.max_ctas : kNumSMs;
     const int grid = (int)std::min<int64_t>(total, cap);
-    kern<<<grid, WS_THREADS, ws_smem_bytes(), st>>>(a, ntri, (int)total);
+    kern<<<grid, WS_THREADS, smem, st>>>(a, ntri, (int)total);
     count_launch();
     return launch_check();
+}
+template <int EPI, bool SCALE>
+inline int dmma_ws_launch(const DmmaArgs& a, int batch, cudaStream_t st) {
+    if (ws_stage_width().load() == 32) return dmma_ws_launch_bk<EPI, SCALE, 32>(a, batch, st);
+    return dmma_ws_launch_bk<EPI, SCALE, 16>(a, batch, st);
 }
 
 // SYRK-shaped product with the best available kernel: the warp-specialised one when the alignment allows,

@@ -808,6 +808,12 @@ int ipm_syrk_d(int device_ordinal, int m, int n, const double* A_d, int64_t lda,
     return IPM_OK;
 }
 
+int ipm_set_syrk_stage_width(int columns) {
+    if (columns != 16 && columns != 32) return IPM_ERR_ARG;
+    ws_stage_width().store(columns);
+    return IPM_OK;
+}
+
 int ipm_potrf_d(int device_ordinal, int m, double* M_d, int64_t ldm, double pivot_rel_thresh, int* n_fixed) {
     if (!M_d) return IPM_ERR_ARG;
     if (m <= 0 || ldm < m || (ldm & 1) || (reinterpret_cast<uintptr_t>(M_d) & 15)) return IPM_ERR_SHAPE;

@@ -26,6 +26,7 @@ namespace ipm {
 constexpr int KA_NT = 1024;
 constexpr int KA_NW = KA_NT / 32;
 constexpr int KA_PW = 16;                      // panel width
+constexpr int KA_RB = 8;                       // rows per batch of the trailing update
 constexpr int KA_MAX_N = 1600;                 // order n + m the panel buffer admits (200 KB)
 
 struct KktArgs {
@@ -165,12 +166,28 @@ __device__ void ka_lu_factor(double* K, int N, int64_t ld, int* piv, double* Psm
                 }
                 u[r] = v;
             }
-            for (int i = c0; i < N; ++i) {
-                const double* lr = Psm + (size_t)(i - k0) * KA_PW;
-                double acc = K[(size_t)i * ld + cc];
+            // rows in batches of KA_RB: the loads of a batch are independent and issued together (one L2 round trip
+            // per batch instead of one per row - the first version of this loop ran at 10 ms per factorisation,
+            // latency-bound on K[i][cc]), then 16 FMAs per row against the broadcast row of L21
+            for (int i = c0; i < N; i += KA_RB) {
+                double kv[KA_RB];
 #pragma unroll
-                for (int r = 0; r < KA_PW; ++r) acc = fma(-lr[r], u[r], acc);
-                K[(size_t)i * ld + cc] = acc;
+                for (int q = 0; q < KA_RB; ++q) kv[q] = (i + q < N) ? K[(size_t)(i + q) * ld + cc] : 0.0;
+#pragma unroll
+                for (int q = 0; q < KA_RB; ++q) {
+                    const double2* lr = reinterpret_cast<const double2*>(Psm + (size_t)(i + q - k0) * KA_PW);
+                    if (i + q < N) {
+#pragma unroll
+                        for (int r = 0; r < KA_PW / 2; ++r) {
+                            const double2 l2 = lr[r];
+                            kv[q] = fma(-l2.x, u[2 * r], kv[q]);
+                            kv[q] = fma(-l2.y, u[2 * r + 1], kv[q]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < KA_RB; ++q)
+                    if (i + q < N) K[(size_t)(i + q) * ld + cc] = kv[q];
             }
         }
         __syncthreads();

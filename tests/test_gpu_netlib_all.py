@@ -6,8 +6,8 @@ under tests/golden/problems/ exactly as the reference's loader returns them, and
               tests/test_gpu_parity.py; here only the objective is re-checked through the same sweep
   highs       the reference fails (NaN / diverges / does not finish, App. C.2) but the standard-form data has an optimum
               (scipy HiGHS on the same A, b, c): the GPU path with the opt-in Mehrotra start must reach it
-  infeasible  the file is not a faithful standard form (bounds were dropped when it was made): HiGHS proves the data
-              infeasible, so no solver can converge - the GPU path must not claim it did
+  infeasible  the file is not a faithful standard form (bounds were dropped when it was made; 12 files): HiGHS proves
+              the data infeasible, so no solver can converge - the GPU path must not claim it did
   nonfinite   b / cTlb hold NaN or Inf (8 files): status nan at once, like the reference's NaN at k = 1
 """
 import json
@@ -41,7 +41,7 @@ def test_table_covers_the_whole_directory():
     v = [verdict(e) for e in TABLE.values()]
     assert len(TABLE) == 81
     assert (v.count("reference"), v.count("nonfinite"), v.count("infeasible"), v.count("highs"), v.count("unpinned")) == \
-        (26, 8, 13, 33, 1)
+        (26, 8, 12, 34, 1)
     assert [k for k, e in TABLE.items() if verdict(e) == "unpinned"] == ["QAP15"]
     assert all(os.path.exists(os.path.join(GOLD, "problems", k + ".npz")) for k in TABLE)
 

@@ -111,6 +111,7 @@ def test_the_trap_is_there_without_refinement(ipm):
         lib.ipm_batched_set_option(_lib.BOPT_REFINE, 1)
     assert int(st1[at]) == 0 and int(it1[at]) <= 20
     assert int(it0[at]) == 120 and int(st0[at]) == 1
-    never = np.array([i for i in range(64) if i != at and it0[i] == it1[i]])
-    assert never.size >= 56                       # the rule fires on about one LP in fifty
-    assert np.array_equal(obj0[never], obj1[never])
+    same = np.array([i for i in range(64) if i != at and it0[i] == it1[i]])
+    assert same.size >= 56                        # the step is taken by about one LP in thirty
+    assert np.allclose(obj0[same], obj1[same], rtol=1e-7, atol=0)      # equal up to what a refinement step changes
+    assert (obj0[same] == obj1[same]).sum() >= 50                      # untouched LPs: bitwise (no cross-talk)
