@@ -265,6 +265,21 @@ def extras_netlib(ipm, cpu_pool=None):
                 out[name]["mehrotra_start"] = {"iterations": r.iterations, "status": r.status, "objective": r.objective,
                                                "solve_s": dt, "newton_it_per_s": r.iterations / max(dt, 1e-12),
                                                "netlib_optimum": NETLIB_OPT.get(name)}
+                if name == "QAP15":
+                    # opt-in that is NOT in the reference either (ipm_detect_dependent_rows): QAP15's A is 10 % rank
+                    # deficient; with the dependent rows removed from the normal equations the reference's own
+                    # iteration (start x = s = 1, y = 1) reaches the Netlib optimum
+                    nd = ns.detect_dependent_rows(1e-10)
+                    ns.solve(tol=TOL, max_iter=10, cTlb=cTlb)
+                    t0 = time.perf_counter()
+                    r = ns.solve(tol=TOL, max_iter=300, cTlb=cTlb)
+                    dt = time.perf_counter() - t0
+                    opt = NETLIB_OPT[name]
+                    out[name]["dependent_rows_removed"] = {
+                        "dependent_rows": nd, "iterations": r.iterations, "status": r.status, "objective": r.objective,
+                        "solve_s": dt, "newton_it_per_s": r.iterations / max(dt, 1e-12), "netlib_optimum": opt,
+                        "rel_objective_diff": abs(r.objective - opt) / abs(opt)}
+                    ns.detect_dependent_rows(0.0)
         except Exception as e:  # pragma: no cover
             out.setdefault(name, {})["error"] = str(e)[:200]
     for name, fut in cpu_async.items():

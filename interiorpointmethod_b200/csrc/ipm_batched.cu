@@ -667,8 +667,14 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
     // LPs parked by the corrector pass (a.handoff_list) are continued by the augmented-system kernel on a second,
     // higher-priority stream WHILE the lockstep loop runs on: a parked LP is off the loop's books (active = 0), its
     // iterate is final, and one CTA per LP for a few milliseconds hides behind the remaining iterations.
-    cudaStream_t st_ka = nullptr;
-    struct KaGuard { cudaStream_t* s; ~KaGuard() { if (*s) cudaStreamDestroy(*s); } } ka_guard{&st_ka};
+    // (several streams: LPs are parked in different iterations, and launches on one stream would run one after the other)
+    constexpr int KA_STREAMS = 6;
+    cudaStream_t st_kas[KA_STREAMS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    struct KaGuard {
+        cudaStream_t* s;
+        ~KaGuard() { for (int i = 0; i < KA_STREAMS; ++i) if (s[i]) cudaStreamDestroy(s[i]); }
+    } ka_guard{st_kas};
+    int ka_next_stream = 0;
     const int slots = ka_slots(B, m, n);
     int ka_launched = 0;
     KktArgs kk;
@@ -677,14 +683,20 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
     if (a.handoff) {
         int lo = 0, hi = 0;
         IPM_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        IPM_CUDA_OK(cudaStreamCreateWithPriority(&st_ka, cudaStreamNonBlocking, hi));
+        for (int i = 0; i < KA_STREAMS; ++i)
+            IPM_CUDA_OK(cudaStreamCreateWithPriority(&st_kas[i], cudaStreamNonBlocking, hi));
     }
+    auto ka_sync_all = [&]() -> int {
+        for (int i = 0; i < KA_STREAMS; ++i) IPM_CUDA_OK(cudaStreamSynchronize(st_kas[i]));
+        return IPM_OK;
+    };
     auto launch_parked = [&](int upto) -> int {          // list entries [ka_launched, upto) whose state is final
         upto = std::min(upto, slots);                    // the workspace has `slots` matrices; the rest waits
         if (upto <= ka_launched) return IPM_OK;
         kk.list = a.handoff_list + ka_launched;
         kk.work = w.ka_work + (size_t)ka_launched * ka_work_doubles(m, n);
-        IPM_TRY(ka_launch(kk, upto - ka_launched, st_ka));
+        IPM_TRY(ka_launch(kk, upto - ka_launched, st_kas[ka_next_stream]));
+        ka_next_stream = (ka_next_stream + 1) % KA_STREAMS;
         ka_launched = upto;
         return IPM_OK;
     };
@@ -785,13 +797,13 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
         IPM_CUDA_OK(cudaStreamSynchronize(st));
         handed = (int)w.h_nact[4];
         IPM_TRY(launch_parked(handed));
-        IPM_CUDA_OK(cudaStreamSynchronize(st_ka));
-        IPM_TRY(debug_check("augmented-system kernel", st_ka));
+        IPM_TRY(ka_sync_all());
+        IPM_TRY(debug_check("augmented-system kernel", st_kas[0]));
         for (int first = ka_launched; first < handed; first += slots) {       // more LPs than slots: in rounds
             kk.list = a.handoff_list + first;
             kk.work = w.ka_work;
-            IPM_TRY(ka_launch(kk, std::min(slots, handed - first), st_ka));
-            IPM_CUDA_OK(cudaStreamSynchronize(st_ka));
+            IPM_TRY(ka_launch(kk, std::min(slots, handed - first), st_kas[0]));
+            IPM_CUDA_OK(cudaStreamSynchronize(st_kas[0]));
         }
     }
     g_last_handoffs.store(handed);

@@ -25,7 +25,12 @@ thread_local std::string g_last_error;
 
 using namespace ipm;
 
-constexpr int PIPE_MIN_M = 256;      // above this order the triangular solves run as pipelined persistent kernels
+// above this order the triangular solves run as pipelined persistent kernels (one CTA per 128-block, k_trinv128 once
+// per factorisation); at or below it one CTA does both sweeps (k_trsv_batched).  IPM_PIPE_MIN_M overrides it for A/B runs.
+static int pipe_min_m() {
+    static const int v = [] { const char* e = getenv("IPM_PIPE_MIN_M"); return e ? atoi(e) : 256; }();
+    return v;
+}
 
 struct ipm_handle {
     int dev = 0;
@@ -56,7 +61,7 @@ struct ipm_handle {
     double *b, *c, *x, *y, *s, *rb, *rc, *d, *w, *rcx, *dxa, *dya, *dsa, *dx, *dy, *ds, *tm, *tn, *rhs, *tmp_m;
     double* M = nullptr;
     int64_t ldm = 0;
-    TrsvPipeWs pipe;              // m > PIPE_MIN_M: inverses of the diagonal blocks + flags of the pipelined solves
+    TrsvPipeWs pipe;              // m > pipe_min_m(): inverses of the diagonal blocks + flags of the pipelined solves
     unsigned char* dep = nullptr; // m bytes: dependent rows of A (ipm_detect_dependent_rows), nullptr = none
     int n_dep = 0;
     double* scal = nullptr;
@@ -135,7 +140,7 @@ int alloc_common(ipm_handle* h, int m, int n) {
     h->rcx = take(pn); h->dxa = take(pn); h->dsa = take(pn); h->dx = take(pn); h->ds = take(pn); h->tn = take(pn);
     h->ldm = pm;
     H_CUDA(cudaMalloc(&h->M, (size_t)m * h->ldm * sizeof(double)));
-    if (m > PIPE_MIN_M) {
+    if (m > pipe_min_m() && m > 256) {
         h->pipe.nblk = ceil_div(m, TP_NB);
         H_CUDA(cudaMalloc(&h->pipe.Linv, (size_t)h->pipe.nblk * TP_NB * TP_NB * sizeof(double)));
         H_CUDA(cudaMalloc(&h->pipe.flags, (size_t)2 * h->pipe.nblk * sizeof(int)));
