@@ -675,6 +675,7 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
         ~KaGuard() { for (int i = 0; i < KA_STREAMS; ++i) if (s[i]) cudaStreamDestroy(s[i]); }
     } ka_guard{st_kas};
     int ka_next_stream = 0;
+    int ka_pending[KA_STREAMS] = {0, 0, 0, 0, 0, 0};      // CTAs launched on each stream and not known to have finished
     const int slots = ka_slots(B, m, n);
     int ka_launched = 0;
     KktArgs kk;
@@ -696,6 +697,7 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
         kk.list = a.handoff_list + ka_launched;
         kk.work = w.ka_work + (size_t)ka_launched * ka_work_doubles(m, n);
         IPM_TRY(ka_launch(kk, upto - ka_launched, st_kas[ka_next_stream]));
+        ka_pending[ka_next_stream] += upto - ka_launched;
         ka_next_stream = (ka_next_stream + 1) % KA_STREAMS;
         ka_launched = upto;
         return IPM_OK;
@@ -746,6 +748,18 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
             if (g_prof.enabled) g_prof.lp_iterations += cnt;
         }
         g_prof.segment(st);
+        if (a.handoff) {
+            // The SYRK is persistent with one CTA per SM and a static tile schedule: an SM held by an augmented-system
+            // CTA would make one SYRK CTA wait for another to finish (twice the launch time).  Leave those SMs out.
+            int busy = 0;
+            for (int i = 0; i < KA_STREAMS; ++i) {
+                if (ka_pending[i] == 0) continue;
+                if (cudaStreamQuery(st_kas[i]) == cudaSuccess) ka_pending[i] = 0;
+                else (void)cudaGetLastError();            // cudaErrorNotReady is not an error
+                busy += ka_pending[i];
+            }
+            g.max_ctas = (busy > 0 && busy < kNumSMs / 2) ? kNumSMs - busy : 0;
+        }
         IPM_TRY((dmma_syrk_auto<0>(g, B, st)));
         IPM_TRY(debug_check("syrk", st));
         g_prof.end_phase(PH_SYRK, st);

@@ -26,9 +26,11 @@ thread_local std::string g_last_error;
 using namespace ipm;
 
 // above this order the triangular solves run as pipelined persistent kernels (one CTA per 128-block, k_trinv128 once
-// per factorisation); at or below it one CTA does both sweeps (k_trsv_batched).  IPM_PIPE_MIN_M overrides it for A/B runs.
+// per factorisation); at or below it one CTA does both sweeps (k_trsv_batched).  Measured crossover between m = 444
+// and m = 821 (round 2: SCSD8 m = 397 +7 %, BANDM m = 305 +17 % with one CTA; 25FV47 m = 821 -12 %, TRUSS m = 1000
+// -18 %).  IPM_PIPE_MIN_M overrides it for A/B runs.
 static int pipe_min_m() {
-    static const int v = [] { const char* e = getenv("IPM_PIPE_MIN_M"); return e ? atoi(e) : 256; }();
+    static const int v = [] { const char* e = getenv("IPM_PIPE_MIN_M"); return e ? atoi(e) : 512; }();
     return v;
 }
 
