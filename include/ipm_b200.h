@@ -258,6 +258,9 @@ int ipm_batched_last_handoffs(void);
 int ipm_solve_dense_kkt(int device_ordinal, int m, int n, const double *A, const double *b, const double *c,
                         double tol, int max_iter, double *x, double *y, double *s, double *obj, int *iters,
                         int *status);
+/* CTAs (= SMs) per LP of that kernel: a thread-block cluster of 1, 2, 4 (default) or 8 CTAs shares the row swaps and the
+ * trailing update of every panel; results are bitwise the same for every cluster size.  Process-wide. */
+int ipm_set_kkt_cluster(int ctas);
 
 /* Phase timing of the batched solver (bench.py roofline): CUDA events on the solve stream around the four
  * phases of every lockstep iteration.  ms/calls index: 0 residual pass, 1 SYRK (dmma_nt_kernel, one launch

@@ -756,7 +756,7 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
                 if (ka_pending[i] == 0) continue;
                 if (cudaStreamQuery(st_kas[i]) == cudaSuccess) ka_pending[i] = 0;
                 else (void)cudaGetLastError();            // cudaErrorNotReady is not an error
-                busy += ka_pending[i];
+                busy += ka_pending[i] * ka_cluster_ctas().load();
             }
             g.max_ctas = (busy > 0 && busy < kNumSMs / 2) ? kNumSMs - busy : 0;
         }
@@ -874,6 +874,12 @@ int ipm_batched_set_option(int option, int value) {
 }
 
 int ipm_batched_last_handoffs(void) { return g_last_handoffs.load(); }
+
+int ipm_set_kkt_cluster(int ctas) {
+    if (ctas != 1 && ctas != 2 && ctas != 4 && ctas != 8) return IPM_ERR_ARG;
+    ka_cluster_ctas().store(ctas);
+    return IPM_OK;
+}
 
 int ipm_solve_dense_kkt(int device_ordinal, int m, int n, const double* A, const double* b, const double* c, double tol,
                         int max_iter, double* x, double* y, double* s, double* obj, int* iters, int* status) {

@@ -15,10 +15,18 @@
 // reference's goldens: same Newton system, same pivoting rule => same iteration counts).
 // The tests compare it with a CPU restatement of the same formulas (`direction_augmented` in the test infrastructure).
 //
-// One CTA of 1024 threads does everything for its LP; the matrix K (order N = n + m) lives in global memory (L2
-// resident: 4.7 MB at 256 x 512), panels of 16 columns are factored in shared memory.  It is a robustness path, not a
-// throughput path: (2/3) N^3 flop per iteration on one SM (about 2 ms at 256 x 512).
+// One thread-block CLUSTER of KA_CL CTAs (1024 threads each) per LP; the matrix K (order N = n + m) lives in global
+// memory (L2 resident: 4.7 MB at 256 x 512), panels of 16 columns are factored in shared memory.  Every CTA of the
+// cluster runs the WHOLE iteration redundantly - residuals, panel factorisations, triangular solves, ratio tests are
+// cheap and their results bitwise identical, so no data has to be exchanged for them - and only the work that scales
+// with N^2 per panel is divided: rows swaps, the U12 solve and the trailing update are split by 32-column chunks
+// over the CTAs (round-robin), with one cluster barrier per panel.  CTA 0 alone writes the LP's state.  It is a
+// robustness path, not a throughput path: (2/3) N^3 flop per iteration on KA_CL SMs (5 ms per iteration at 256 x 512 on
+// one SM - measured, round 2 - which is what the cluster is for: an LP parked in the last iterations of a solve
+// finishes after everybody else).
 #pragma once
+#include <cstring>
+
 #include "common.cuh"
 
 namespace ipm {
@@ -27,6 +35,7 @@ constexpr int KA_NT = 1024;
 constexpr int KA_NW = KA_NT / 32;
 constexpr int KA_PW = 16;                      // panel width
 constexpr int KA_RB = 8;                       // rows per batch of the trailing update
+constexpr int KA_CL_MAX = 8;                   // largest cluster (portable limit)
 constexpr int KA_MAX_N = 1600;                 // order n + m the panel buffer admits (200 KB)
 
 struct KktArgs {
@@ -52,7 +61,8 @@ struct KktArgs {
 KA_HD inline int64_t ka_ldk(int m, int n) { return ((int64_t)m + n + 1) / 2 * 2; }
 KA_HD inline int64_t ka_work_doubles(int m, int n) {
     const int64_t N = (int64_t)m + n;
-    const int64_t v = N * ka_ldk(m, n) + N /*piv (as ints)*/ + (int64_t)m /*rb*/ + 6 * (int64_t)n;
+    // K once per LP; piv, rb and six n-vectors once per CTA of the cluster (each CTA keeps its own redundant copy)
+    const int64_t v = N * ka_ldk(m, n) + (int64_t)KA_CL_MAX * (N + (int64_t)m + 6 * (int64_t)n);
     return (v + 15) / 16 * 16;
 }
 inline size_t ka_smem_bytes(int m, int n) {
@@ -61,6 +71,21 @@ inline size_t ka_smem_bytes(int m, int n) {
 }
 
 #ifdef __CUDACC__
+__device__ __forceinline__ unsigned ka_cluster_rank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned ka_cluster_size() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+// barrier over all threads of all CTAs of the cluster; release/acquire at cluster scope orders their global writes
+__device__ __forceinline__ void ka_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // argmax |v| with the lowest index on ties (LAPACK idamax): result valid in ALL threads.
 __device__ __forceinline__ void ka_block_argmax(double v, int idx, double* shv, int* shi, double& vout, int& iout) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -96,8 +121,11 @@ __device__ __forceinline__ double ka_block_all(double v, double* sh, double* bc)
 
 // In-place LU with partial pivoting of K (N x N, row-major, leading dimension ld), blocked by KA_PW columns.
 // piv[k] = row swapped with row k at step k (LAPACK ipiv, 0-based).
-__device__ void ka_lu_factor(double* K, int N, int64_t ld, int* piv, double* Psm, double* shv, int* shi) {
+// crank / csize: this CTA's rank in the cluster and the cluster's size (see the header comment).
+__device__ void ka_lu_factor(double* K, int N, int64_t ld, int* piv, double* Psm, double* shv, int* shi, int crank,
+                             int csize) {
     const int tid = threadIdx.x;
+    auto mine = [&](int cc) { return ((cc >> 5) % csize) == crank; };      // 32-column chunks, round-robin
     for (int k0 = 0; k0 < N; k0 += KA_PW) {
         const int pw = (N - k0 < KA_PW) ? (N - k0) : KA_PW;
         const int rows = N - k0;
@@ -134,17 +162,19 @@ __device__ void ka_lu_factor(double* K, int N, int64_t ld, int* piv, double* Psm
             }
             __syncthreads();
         }
-        // (3) panel back to K
-        for (int idx = tid; idx < rows * KA_PW; idx += KA_NT) {
-            const int r = idx / KA_PW, cc = idx - r * KA_PW;
-            if (cc < pw) K[(size_t)(k0 + r) * ld + k0 + cc] = Psm[idx];
+        // (3) panel back to K (every CTA holds the same panel: CTA 0 writes it)
+        if (crank == 0) {
+            for (int idx = tid; idx < rows * KA_PW; idx += KA_NT) {
+                const int r = idx / KA_PW, cc = idx - r * KA_PW;
+                if (cc < pw) K[(size_t)(k0 + r) * ld + k0 + cc] = Psm[idx];
+            }
         }
         // (4) the panel's row interchanges on the columns outside the panel, in order
         for (int j = 0; j < pw; ++j) {
             const int r1 = k0 + j, r2 = piv[k0 + j];        // written by thread 0 before a barrier above
             if (r1 != r2) {
                 for (int cc = tid; cc < N; cc += KA_NT) {
-                    if (cc >= k0 && cc < k0 + pw) continue;
+                    if ((cc >= k0 && cc < k0 + pw) || !mine(cc)) continue;
                     const double t0 = K[(size_t)r1 * ld + cc];
                     K[(size_t)r1 * ld + cc] = K[(size_t)r2 * ld + cc];
                     K[(size_t)r2 * ld + cc] = t0;
@@ -155,6 +185,7 @@ __device__ void ka_lu_factor(double* K, int N, int64_t ld, int* piv, double* Psm
         // (5) U12 = L11^-1 K12 and the trailing update K22 -= L21 U12: one thread owns a column of both
         const int c0 = k0 + pw;
         for (int cc = c0 + tid; cc < N; cc += KA_NT) {
+            if (!mine(cc)) continue;
             double u[KA_PW];
 #pragma unroll
             for (int r = 0; r < KA_PW; ++r) {
@@ -190,7 +221,9 @@ __device__ void ka_lu_factor(double* K, int N, int64_t ld, int* piv, double* Psm
                     if (i + q < N) K[(size_t)(i + q) * ld + cc] = kv[q];
             }
         }
-        __syncthreads();
+        // the next panel's columns were updated by whichever CTA owns their chunk
+        if (csize > 1) ka_cluster_sync();
+        else __syncthreads();
     }
 }
 
@@ -270,7 +303,9 @@ static __global__ void __launch_bounds__(KA_NT, 1) ka_solve(const KktArgs a) {
     __shared__ double shv[32];
     __shared__ int shi[32];
     __shared__ double bc;
-    const int lp = a.list ? a.list[blockIdx.x] : blockIdx.x;
+    const int crank = (int)ka_cluster_rank(), csize = (int)ka_cluster_size();
+    const int slot = blockIdx.x / csize;                    // one LP (and one K) per cluster
+    const int lp = a.list ? a.list[slot] : slot;
     const int m = a.m, n = a.n, N = m + n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t ld = ka_ldk(m, n);
     const double* A = a.A + (size_t)lp * m * n;
@@ -280,8 +315,9 @@ static __global__ void __launch_bounds__(KA_NT, 1) ka_solve(const KktArgs a) {
     double* s = a.s + (size_t)lp * n;
     double* y = a.y + (size_t)lp * m;
     double* scal = a.scal + (size_t)lp * S_COUNT;
-    double* W = a.work + (size_t)blockIdx.x * ka_work_doubles(m, n);
+    double* W = a.work + (size_t)slot * ka_work_doubles(m, n);
     double* K = W;                          W += (size_t)N * ld;
+    W += (size_t)crank * (N + m + 6 * (size_t)n);            // this CTA's own copy of the small arrays
     int* piv = reinterpret_cast<int*>(W);   W += N;
     double* rb = W;                         W += m;
     double* rc = W;                         W += n;
@@ -324,24 +360,27 @@ static __global__ void __launch_bounds__(KA_NT, 1) ka_solve(const KktArgs a) {
         obj = ka_block_all<RED_SUM>(obj, sh, &bc);
         const double nrb = sqrt(nrb2), nrc = sqrt(nrc2);
         const bool cont = (a.tol * (1.0 + nb) < nrb) || (a.tol * (1.0 + nc) < nrc) || (a.tol < xs);
-        if (tid == 0) {
+        if (tid == 0 && crank == 0) {
             scal[S_NRB2] = nrb2; scal[S_NRB] = nrb; scal[S_NRC2] = nrc2; scal[S_NRC] = nrc;
             scal[S_XS] = xs; scal[S_OBJ] = obj; scal[S_CONT] = cont ? 1.0 : 0.0;
         }
         if (!cont || it >= a.max_iter) break;
 
-        // ---- K = [[-D^-1, A^T], [A, 0]]
-        for (int64_t idx = tid; idx < (int64_t)N * ld; idx += KA_NT) K[idx] = 0.0;
-        __syncthreads();
-        for (int j = tid; j < n; j += KA_NT) K[(size_t)j * ld + j] = -(s[j] / x[j]);
-        for (int64_t idx = tid; idx < (int64_t)m * n; idx += KA_NT) {
+        // ---- K = [[-D^-1, A^T], [A, 0]]: the CTAs of the cluster share the work (interleaved slices)
+        const int64_t gstride = (int64_t)KA_NT * csize, g0 = (int64_t)crank * KA_NT + tid;
+        for (int64_t idx = g0; idx < (int64_t)N * ld; idx += gstride) K[idx] = 0.0;
+        if (csize > 1) ka_cluster_sync();
+        else __syncthreads();
+        for (int64_t j = g0; j < n; j += gstride) K[(size_t)j * ld + j] = -(s[j] / x[j]);
+        for (int64_t idx = g0; idx < (int64_t)m * n; idx += gstride) {
             const int i = (int)(idx / n), j = (int)(idx - (int64_t)i * n);
             const double v = A[idx];
             K[(size_t)(n + i) * ld + j] = v;
             K[(size_t)j * ld + n + i] = v;
         }
-        __syncthreads();
-        ka_lu_factor(K, N, ld, piv, Psm, shv, shi);
+        if (csize > 1) ka_cluster_sync();
+        else __syncthreads();
+        ka_lu_factor(K, N, ld, piv, Psm, shv, shi, crank, csize);
 
         // ---- predictor (main.py:66-76, 101-109): rcomp = x s
         for (int j = tid; j < n; j += KA_NT) {
@@ -391,29 +430,52 @@ static __global__ void __launch_bounds__(KA_NT, 1) ka_solve(const KktArgs a) {
         double ad = ka_block_all<RED_MIN>(mind, sh, &bc);
         ap = fmin(1.0, a.eta * ap);                                            // main.py:616-623
         ad = fmin(1.0, a.eta * ad);
-        for (int j = tid; j < n; j += KA_NT) {
-            x[j] = x[j] + ap * dx[j];
-            s[j] = s[j] + ad * ds[j];
+        // every CTA has read the old iterate for the last time (ratio tests above) before CTA 0 overwrites it
+        if (csize > 1) ka_cluster_sync();
+        if (crank == 0) {
+            for (int j = tid; j < n; j += KA_NT) {
+                x[j] = x[j] + ap * dx[j];
+                s[j] = s[j] + ad * ds[j];
+            }
+            for (int i = tid; i < m; i += KA_NT) y[i] = y[i] + ad * vec[n + i];
+            if (tid == 0) {
+                scal[S_AP_AFF] = apa; scal[S_AD_AFF] = ada; scal[S_MU_AFF] = mu_aff; scal[S_MU] = mu;
+                scal[S_SIGMA] = sigma; scal[S_SIGMA_MU] = sigma_mu; scal[S_AP] = ap; scal[S_AD] = ad;
+            }
         }
-        for (int i = tid; i < m; i += KA_NT) y[i] = y[i] + ad * vec[n + i];
         ++it;
-        if (tid == 0) {
-            scal[S_AP_AFF] = apa; scal[S_AD_AFF] = ada; scal[S_MU_AFF] = mu_aff; scal[S_MU] = mu;
-            scal[S_SIGMA] = sigma; scal[S_SIGMA_MU] = sigma_mu; scal[S_AP] = ap; scal[S_AD] = ad;
-        }
-        __syncthreads();
+        if (csize > 1) ka_cluster_sync();           // the new iterate is visible to the whole cluster
+        else __syncthreads();
     }
-    if (tid == 0) a.iters[lp] = it;
+    if (tid == 0 && crank == 0) a.iters[lp] = it;
 }
 
 // count LPs (list[0..count), or LPs 0..count-1 when list is null), work_d: count * ka_work_doubles(m, n) doubles
+inline std::atomic<int>& ka_cluster_ctas() {        // CTAs per LP: 1, 2, 4 (default) or 8 (ipm_set_kkt_cluster)
+    static std::atomic<int> v{4};
+    return v;
+}
 inline int ka_launch(const KktArgs& a, int count, cudaStream_t st) {
     if (a.m + a.n > KA_MAX_N) {
         g_last_error = "augmented-system kernel: n + m exceeds " + std::to_string(KA_MAX_N);
         return IPM_ERR_SHAPE;
     }
     IPM_TRY(ensure_dyn_smem(ka_solve, (size_t)(KA_MAX_N * KA_PW + 32 * 33 + 64) * sizeof(double)));
-    ka_solve<<<count, KA_NT, ka_smem_bytes(a.m, a.n), st>>>(a);
+    const int cl = ka_cluster_ctas().load();
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(count * cl), 1, 1);
+    cfg.blockDim = dim3(KA_NT, 1, 1);
+    cfg.dynamicSmemBytes = ka_smem_bytes(a.m, a.n);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    IPM_CUDA_OK(cudaLaunchKernelEx(&cfg, ka_solve, a));
     count_launch();
     return launch_check();
 }

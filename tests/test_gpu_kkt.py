@@ -69,3 +69,23 @@ def test_kkt_iteration_cap_and_nan(ipm):
     b2 = b.copy(); b2[0] = np.nan
     r = ipm.interior_kkt(A, b2, c, tol=1e-8)
     assert r.status == "nan" and r.iterations <= 1
+
+
+@pytest.mark.parametrize("shape,seed", [((64, 128), 0), ((256, 512), 3), ((33, 47), 5)])
+def test_kkt_cluster_sizes_give_bitwise_equal_results(ipm, shape, seed):
+    """The CTAs of a cluster split only the column-parallel work of the factorisation; everything else is redundant
+    and deterministic, so 1, 2, 4 and 8 CTAs per LP must agree bit for bit."""
+    from interiorpointmethod_b200 import _lib
+    lib = _lib.load()
+    m, n = shape
+    A, b, c = ipm.synthetic_dense_lp(m, n, seed)
+    res = {}
+    try:
+        for cl in (1, 2, 4, 8):
+            assert lib.ipm_set_kkt_cluster(cl) == 0
+            res[cl] = ipm.interior_kkt(A, b, c, tol=1e-8)
+    finally:
+        lib.ipm_set_kkt_cluster(4)
+    for cl in (2, 4, 8):
+        assert res[cl].status == "converged" and res[cl].iterations == res[1].iterations
+        assert res[cl].objective == res[1].objective and np.array_equal(res[cl].x, res[1].x)
