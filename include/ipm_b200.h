@@ -261,6 +261,11 @@ int ipm_solve_dense_kkt(int device_ordinal, int m, int n, const double *A, const
 /* CTAs (= SMs) per LP of that kernel: a thread-block cluster of 1, 2, 4 (default) or 8 CTAs shares the row swaps and the
  * trailing update of every panel; results are bitwise the same for every cluster size.  Process-wide. */
 int ipm_set_kkt_cluster(int ctas);
+/* Cycle counts of the last ipm_solve_dense_kkt call, by phase (CTA 0): [0] residuals + check, [1] building K, [2] panel
+ * loads, [3] panel column steps (pivot search, swap, scale, rank-1 update in shared memory), [4] panel write-back,
+ * [5] row interchanges outside the panel, [6] U12 + trailing update + cluster barrier, [7] the two solves,
+ * [8] elementwise work, ratio tests, update, [9] iterations.  Diagnostic. */
+int ipm_kkt_last_profile(int64_t out[16]);
 
 /* Phase timing of the batched solver (bench.py roofline): CUDA events on the solve stream around the four
  * phases of every lockstep iteration.  ms/calls index: 0 residual pass, 1 SYRK (dmma_nt_kernel, one launch

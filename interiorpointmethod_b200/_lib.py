@@ -67,6 +67,7 @@ SYMBOLS = {
     "ipm_batched_set_option": (c_int, [c_int, c_int]),
     "ipm_batched_last_handoffs": (c_int, []),
     "ipm_set_kkt_cluster": (c_int, [c_int]),
+    "ipm_kkt_last_profile": (c_int, [c_void_p]),
     "ipm_solve_dense_kkt": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_double, c_int, c_void_p, c_void_p,
                                     c_void_p, _dp, _ip, _ip]),
     "ipm_profile_enable": (c_int, [c_int]),

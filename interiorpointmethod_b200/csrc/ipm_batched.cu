@@ -875,6 +875,13 @@ int ipm_batched_set_option(int option, int value) {
 
 int ipm_batched_last_handoffs(void) { return g_last_handoffs.load(); }
 
+static long long g_kkt_prof[16];
+int ipm_kkt_last_profile(int64_t out[16]) {
+    if (!out) return IPM_ERR_ARG;
+    for (int i = 0; i < 16; ++i) out[i] = g_kkt_prof[i];
+    return IPM_OK;
+}
+
 int ipm_set_kkt_cluster(int ctas) {
     if (ctas != 1 && ctas != 2 && ctas != 4 && ctas != 8) return IPM_ERR_ARG;
     ka_cluster_ctas().store(ctas);
@@ -900,7 +907,8 @@ int ipm_solve_dense_kkt(int device_ordinal, int m, int n, const double* A, const
     IPM_CUDA_OK(cudaMalloc(&d.vec, nv * sizeof(double)));
     IPM_CUDA_OK(cudaMalloc(&d.work, (size_t)ka_work_doubles(m, n) * sizeof(double)));
     IPM_CUDA_OK(cudaMalloc(&d.scal, S_COUNT * sizeof(double)));
-    IPM_CUDA_OK(cudaMalloc(&d.ints, 4 * sizeof(int)));
+    IPM_CUDA_OK(cudaMalloc(&d.ints, 4 * sizeof(int) + 16 * sizeof(long long)));
+    IPM_CUDA_OK(cudaMemset(d.ints, 0, 4 * sizeof(int) + 16 * sizeof(long long)));
     double *db = d.vec, *dy = db + m, *dc = dy + m, *dx = dc + n, *ds = dx + n;
     IPM_CUDA_OK(cudaMemcpy(d.A, A, (size_t)m * n * sizeof(double), cudaMemcpyHostToDevice));
     IPM_CUDA_OK(cudaMemcpy(db, b, (size_t)m * sizeof(double), cudaMemcpyHostToDevice));
@@ -914,11 +922,13 @@ int ipm_solve_dense_kkt(int device_ordinal, int m, int n, const double* A, const
     KktArgs k;
     k.A = d.A; k.b = db; k.c = dc; k.x = dx; k.s = ds; k.y = dy; k.scal = d.scal; k.iters = d.ints + 1; k.list = nullptr;
     k.work = d.work; k.m = m; k.n = n; k.tol = tol; k.eta = 0.91; k.max_iter = max_iter;
+    k.prof = reinterpret_cast<long long*>(d.ints + 4);
     IPM_TRY(ka_launch(k, 1, 0));
     double hs[S_COUNT];
     int hi[4];
     IPM_CUDA_OK(cudaMemcpy(hs, d.scal, sizeof(hs), cudaMemcpyDeviceToHost));
     IPM_CUDA_OK(cudaMemcpy(hi, d.ints, sizeof(hi), cudaMemcpyDeviceToHost));
+    IPM_CUDA_OK(cudaMemcpy(g_kkt_prof, d.ints + 4, sizeof(g_kkt_prof), cudaMemcpyDeviceToHost));
     if (x) IPM_CUDA_OK(cudaMemcpy(x, dx, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
     if (y) IPM_CUDA_OK(cudaMemcpy(y, dy, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost));
     if (s) IPM_CUDA_OK(cudaMemcpy(s, ds, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));

@@ -31,12 +31,18 @@
 
 namespace ipm {
 
-constexpr int KA_NT = 1024;
+// Measured (tools/kkt_profile.py, 256 x 512, round 2): the first version - 1024 threads, panel rows 16 doubles apart,
+// 8-row batches - spent 3.7 ms per iteration in the panel's column steps (every access to one panel column by
+// consecutive rows was a 32-way bank conflict) and 6.1 ms in the trailing update (under the 64-register cap of a
+// 1024-thread CTA the compiler sank the batched loads next to their uses: one exposed L2 round trip per row).  Hence:
+// an odd row stride for the panel, 512 threads (128 registers) and 16-row batches.
+constexpr int KA_NT = 512;
 constexpr int KA_NW = KA_NT / 32;
 constexpr int KA_PW = 16;                      // panel width
-constexpr int KA_RB = 8;                       // rows per batch of the trailing update
+constexpr int KA_LDP = KA_PW + 1;              // panel row stride in shared memory (odd: conflict-free columns)
+constexpr int KA_RB = 16;                      // rows per batch of the trailing update
 constexpr int KA_CL_MAX = 8;                   // largest cluster (portable limit)
-constexpr int KA_MAX_N = 1600;                 // order n + m the panel buffer admits (200 KB)
+constexpr int KA_MAX_N = 1600;                 // order n + m the panel buffer admits (218 KB)
 
 struct KktArgs {
     const double* A;        // [B][m][n]
@@ -51,6 +57,7 @@ struct KktArgs {
     int m, n;
     double tol, eta;
     int max_iter;
+    long long* prof = nullptr;   // optional [16]: cycles per phase of cluster 0's CTA 0 (ipm_kkt_last_profile)
 };
 
 #ifdef __CUDACC__
@@ -67,7 +74,7 @@ KA_HD inline int64_t ka_work_doubles(int m, int n) {
 }
 inline size_t ka_smem_bytes(int m, int n) {
     const size_t N = (size_t)m + n;
-    return (N * KA_PW + 32 * 33 + 64) * sizeof(double);
+    return (N * KA_LDP + 32 * 33 + 64) * sizeof(double);
 }
 
 #ifdef __CUDACC__
@@ -98,7 +105,8 @@ __device__ __forceinline__ void ka_block_argmax(double v, int idx, double* shv, 
     __syncthreads();
     if (lane == 0) { shv[w] = v; shi[w] = idx; }
     __syncthreads();
-    v = shv[lane]; idx = shi[lane];                 // KA_NW == 32 warps
+    v = (lane < KA_NW) ? shv[lane] : -1.0;
+    idx = (lane < KA_NW) ? shi[lane] : 0x7fffffff;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const double ov = __shfl_xor_sync(0xffffffffu, v, o);
@@ -122,9 +130,11 @@ __device__ __forceinline__ double ka_block_all(double v, double* sh, double* bc)
 // In-place LU with partial pivoting of K (N x N, row-major, leading dimension ld), blocked by KA_PW columns.
 // piv[k] = row swapped with row k at step k (LAPACK ipiv, 0-based).
 // crank / csize: this CTA's rank in the cluster and the cluster's size (see the header comment).
+#define KA_T(slot) do { if (prof && threadIdx.x == 0) { const long long _t = clock64(); prof[slot] += _t - t_last; t_last = _t; } } while (0)
 __device__ void ka_lu_factor(double* K, int N, int64_t ld, int* piv, double* Psm, double* shv, int* shi, int crank,
-                             int csize) {
+                             int csize, long long* prof) {
     const int tid = threadIdx.x;
+    long long t_last = clock64();
     auto mine = [&](int cc) { return ((cc >> 5) % csize) == crank; };      // 32-column chunks, round-robin
     for (int k0 = 0; k0 < N; k0 += KA_PW) {
         const int pw = (N - k0 < KA_PW) ? (N - k0) : KA_PW;
@@ -132,15 +142,16 @@ __device__ void ka_lu_factor(double* K, int N, int64_t ld, int* piv, double* Psm
         // (1) panel -> shared memory
         for (int idx = tid; idx < rows * KA_PW; idx += KA_NT) {
             const int r = idx / KA_PW, cc = idx - r * KA_PW;
-            Psm[idx] = (cc < pw) ? K[(size_t)(k0 + r) * ld + k0 + cc] : 0.0;
+            Psm[r * KA_LDP + cc] = (cc < pw) ? K[(size_t)(k0 + r) * ld + k0 + cc] : 0.0;
         }
         __syncthreads();
+        KA_T(2);
         // (2) unblocked LU of the panel
         for (int j = 0; j < pw; ++j) {
             double best = -1.0;
             int bi = 0x7fffffff;
             for (int r = j + tid; r < rows; r += KA_NT) {
-                const double av = fabs(Psm[r * KA_PW + j]);
+                const double av = fabs(Psm[r * KA_LDP + j]);
                 if (av > best) { best = av; bi = r; }       // first maximum, like idamax; NaN never compares greater
             }
             double bv; int br;
@@ -148,20 +159,21 @@ __device__ void ka_lu_factor(double* K, int N, int64_t ld, int* piv, double* Psm
             if (br == 0x7fffffff) br = j;                   // all NaN / empty
             if (tid == 0) piv[k0 + j] = k0 + br;
             if (br != j && tid < KA_PW) {
-                const double t0 = Psm[j * KA_PW + tid];
-                Psm[j * KA_PW + tid] = Psm[br * KA_PW + tid];
-                Psm[br * KA_PW + tid] = t0;
+                const double t0 = Psm[j * KA_LDP + tid];
+                Psm[j * KA_LDP + tid] = Psm[br * KA_LDP + tid];
+                Psm[br * KA_LDP + tid] = t0;
             }
             __syncthreads();
-            const double p = Psm[j * KA_PW + j];
+            const double p = Psm[j * KA_LDP + j];
             for (int r = j + 1 + tid; r < rows; r += KA_NT) {
-                double* pr = Psm + r * KA_PW;
+                double* pr = Psm + r * KA_LDP;
                 const double l = pr[j] / p;
                 pr[j] = l;
-                for (int cc = j + 1; cc < pw; ++cc) pr[cc] = fma(-l, Psm[j * KA_PW + cc], pr[cc]);
+                for (int cc = j + 1; cc < pw; ++cc) pr[cc] = fma(-l, Psm[j * KA_LDP + cc], pr[cc]);
             }
             __syncthreads();
         }
+        KA_T(3);
         // (3) panel back to K (every CTA holds the same panel: CTA 0 writes it)
         if (crank == 0) {
             for (int idx = tid; idx < rows * KA_PW; idx += KA_NT) {
@@ -169,6 +181,7 @@ __device__ void ka_lu_factor(double* K, int N, int64_t ld, int* piv, double* Psm
                 if (cc < pw) K[(size_t)(k0 + r) * ld + k0 + cc] = Psm[idx];
             }
         }
+        KA_T(4);
         // (4) the panel's row interchanges on the columns outside the panel, in order
         for (int j = 0; j < pw; ++j) {
             const int r1 = k0 + j, r2 = piv[k0 + j];        // written by thread 0 before a barrier above
@@ -182,6 +195,7 @@ __device__ void ka_lu_factor(double* K, int N, int64_t ld, int* piv, double* Psm
             }
             __syncthreads();
         }
+        KA_T(5);
         // (5) U12 = L11^-1 K12 and the trailing update K22 -= L21 U12: one thread owns a column of both
         const int c0 = k0 + pw;
         for (int cc = c0 + tid; cc < N; cc += KA_NT) {
@@ -192,7 +206,7 @@ __device__ void ka_lu_factor(double* K, int N, int64_t ld, int* piv, double* Psm
                 double v = 0.0;
                 if (r < pw) {
                     v = K[(size_t)(k0 + r) * ld + cc];
-                    for (int q = 0; q < r; ++q) v = fma(-Psm[r * KA_PW + q], u[q], v);
+                    for (int q = 0; q < r; ++q) v = fma(-Psm[r * KA_LDP + q], u[q], v);
                     K[(size_t)(k0 + r) * ld + cc] = v;
                 }
                 u[r] = v;
@@ -206,14 +220,10 @@ __device__ void ka_lu_factor(double* K, int N, int64_t ld, int* piv, double* Psm
                 for (int q = 0; q < KA_RB; ++q) kv[q] = (i + q < N) ? K[(size_t)(i + q) * ld + cc] : 0.0;
 #pragma unroll
                 for (int q = 0; q < KA_RB; ++q) {
-                    const double2* lr = reinterpret_cast<const double2*>(Psm + (size_t)(i + q - k0) * KA_PW);
+                    const double* lr = Psm + (size_t)(i + q - k0) * KA_LDP;      // same address in every lane: broadcast
                     if (i + q < N) {
 #pragma unroll
-                        for (int r = 0; r < KA_PW / 2; ++r) {
-                            const double2 l2 = lr[r];
-                            kv[q] = fma(-l2.x, u[2 * r], kv[q]);
-                            kv[q] = fma(-l2.y, u[2 * r + 1], kv[q]);
-                        }
+                        for (int r = 0; r < KA_PW; ++r) kv[q] = fma(-lr[r], u[r], kv[q]);
                     }
                 }
 #pragma unroll
@@ -224,6 +234,7 @@ __device__ void ka_lu_factor(double* K, int N, int64_t ld, int* piv, double* Psm
         // the next panel's columns were updated by whichever CTA owns their chunk
         if (csize > 1) ka_cluster_sync();
         else __syncthreads();
+        KA_T(6);
     }
 }
 
@@ -238,19 +249,21 @@ __device__ void ka_lu_solve(const double* K, int N, int64_t ld, const int* piv, 
     }
     __syncthreads();
     const int nblk = (N + 31) >> 5;
-    // forward, unit lower
+    // forward, unit lower: the warps share the 32 rows of a block
     for (int I = 0; I < nblk; ++I) {
         const int i0 = I << 5;
-        const int i = i0 + warp;                                  // 32 warps <-> 32 rows
-        if (i < N) {
-            const double* row = K + (size_t)i * ld;
-            double acc = 0.0;
-            for (int k = lane; k < i0; k += 32) acc = fma(row[k], vec[k], acc);
-            acc = warp_sum(acc);
-            blk[warp * 33 + lane] = (i0 + lane < i) ? row[i0 + lane] : 0.0;      // strictly lower part of the block
-            if (lane == 0) vec[i] -= acc;
-        } else {
-            blk[warp * 33 + lane] = 0.0;
+        for (int w = warp; w < 32; w += KA_NW) {
+            const int i = i0 + w;
+            if (i < N) {
+                const double* row = K + (size_t)i * ld;
+                double acc = 0.0;
+                for (int k = lane; k < i0; k += 32) acc = fma(row[k], vec[k], acc);
+                acc = warp_sum(acc);
+                blk[w * 33 + lane] = (i0 + lane < i) ? row[i0 + lane] : 0.0;      // strictly lower part of the block
+                if (lane == 0) vec[i] -= acc;
+            } else {
+                blk[w * 33 + lane] = 0.0;
+            }
         }
         __syncthreads();
         if (warp == 0) {
@@ -267,17 +280,19 @@ __device__ void ka_lu_solve(const double* K, int N, int64_t ld, const int* piv, 
     // backward, upper with diagonal
     for (int I = nblk - 1; I >= 0; --I) {
         const int i0 = I << 5;
-        const int i = i0 + warp;
         const int k1 = (i0 + 32 < N) ? i0 + 32 : N;
-        if (i < N) {
-            const double* row = K + (size_t)i * ld;
-            double acc = 0.0;
-            for (int k = k1 + lane; k < N; k += 32) acc = fma(row[k], vec[k], acc);
-            acc = warp_sum(acc);
-            blk[warp * 33 + lane] = (i0 + lane >= i && i0 + lane < N) ? row[i0 + lane] : 0.0;   // upper part incl. diagonal
-            if (lane == 0) vec[i] -= acc;
-        } else {
-            blk[warp * 33 + lane] = (lane == warp) ? 1.0 : 0.0;
+        for (int w = warp; w < 32; w += KA_NW) {
+            const int i = i0 + w;
+            if (i < N) {
+                const double* row = K + (size_t)i * ld;
+                double acc = 0.0;
+                for (int k = k1 + lane; k < N; k += 32) acc = fma(row[k], vec[k], acc);
+                acc = warp_sum(acc);
+                blk[w * 33 + lane] = (i0 + lane >= i && i0 + lane < N) ? row[i0 + lane] : 0.0;   // upper part incl. diagonal
+                if (lane == 0) vec[i] -= acc;
+            } else {
+                blk[w * 33 + lane] = (lane == w) ? 1.0 : 0.0;
+            }
         }
         __syncthreads();
         if (warp == 0) {
@@ -297,8 +312,8 @@ __device__ void ka_lu_solve(const double* K, int N, int64_t ld, const int* piv, 
 
 static __global__ void __launch_bounds__(KA_NT, 1) ka_solve(const KktArgs a) {
     extern __shared__ __align__(16) double smem_ka[];
-    double* Psm = smem_ka;                                  // [N][KA_PW] panel; the solves keep their vector here
-    double* blk = smem_ka + (size_t)(a.m + a.n) * KA_PW;    // [32][33]
+    double* Psm = smem_ka;                                  // [N][KA_LDP] panel; the solves keep their vector here
+    double* blk = smem_ka + (size_t)(a.m + a.n) * KA_LDP;   // [32][33]
     __shared__ double sh[32];
     __shared__ double shv[32];
     __shared__ int shi[32];
@@ -329,6 +344,8 @@ static __global__ void __launch_bounds__(KA_NT, 1) ka_solve(const KktArgs a) {
     double* vec = Psm;
     const double nb = scal[S_NB], nc = scal[S_NC];
     int it = a.iters[lp];
+    long long* prof = (a.prof && blockIdx.x == 0) ? a.prof : nullptr;
+    long long t_last = clock64();
 
     for (;;) {
         // ---- residuals of the current iterate, from scratch (main.py:67-70), check_optimality (main.py:169-173)
@@ -364,6 +381,7 @@ static __global__ void __launch_bounds__(KA_NT, 1) ka_solve(const KktArgs a) {
             scal[S_NRB2] = nrb2; scal[S_NRB] = nrb; scal[S_NRC2] = nrc2; scal[S_NRC] = nrc;
             scal[S_XS] = xs; scal[S_OBJ] = obj; scal[S_CONT] = cont ? 1.0 : 0.0;
         }
+        KA_T(0);
         if (!cont || it >= a.max_iter) break;
 
         // ---- K = [[-D^-1, A^T], [A, 0]]: the CTAs of the cluster share the work (interleaved slices)
@@ -380,7 +398,9 @@ static __global__ void __launch_bounds__(KA_NT, 1) ka_solve(const KktArgs a) {
         }
         if (csize > 1) ka_cluster_sync();
         else __syncthreads();
-        ka_lu_factor(K, N, ld, piv, Psm, shv, shi, crank, csize);
+        KA_T(1);
+        ka_lu_factor(K, N, ld, piv, Psm, shv, shi, crank, csize, prof);
+        t_last = clock64();
 
         // ---- predictor (main.py:66-76, 101-109): rcomp = x s
         for (int j = tid; j < n; j += KA_NT) {
@@ -390,7 +410,9 @@ static __global__ void __launch_bounds__(KA_NT, 1) ka_solve(const KktArgs a) {
         }
         for (int i = tid; i < m; i += KA_NT) vec[n + i] = -rb[i];
         __syncthreads();
+        KA_T(8);
         ka_lu_solve(K, N, ld, piv, vec, blk);
+        KA_T(7);
         double minp = 1.0, mind = 1.0;
         for (int j = tid; j < n; j += KA_NT) {
             const double dxi = vec[j];
@@ -417,7 +439,9 @@ static __global__ void __launch_bounds__(KA_NT, 1) ka_solve(const KktArgs a) {
         }
         for (int i = tid; i < m; i += KA_NT) vec[n + i] = -rb[i];
         __syncthreads();
+        KA_T(8);
         ka_lu_solve(K, N, ld, piv, vec, blk);
+        KA_T(7);
         minp = 1.0; mind = 1.0;
         for (int j = tid; j < n; j += KA_NT) {
             const double dxi = vec[j];
@@ -446,6 +470,8 @@ static __global__ void __launch_bounds__(KA_NT, 1) ka_solve(const KktArgs a) {
         ++it;
         if (csize > 1) ka_cluster_sync();           // the new iterate is visible to the whole cluster
         else __syncthreads();
+        KA_T(8);
+        if (prof && tid == 0) prof[9] += 1;
     }
     if (tid == 0 && crank == 0) a.iters[lp] = it;
 }
@@ -460,7 +486,7 @@ inline int ka_launch(const KktArgs& a, int count, cudaStream_t st) {
         g_last_error = "augmented-system kernel: n + m exceeds " + std::to_string(KA_MAX_N);
         return IPM_ERR_SHAPE;
     }
-    IPM_TRY(ensure_dyn_smem(ka_solve, (size_t)(KA_MAX_N * KA_PW + 32 * 33 + 64) * sizeof(double)));
+    IPM_TRY(ensure_dyn_smem(ka_solve, (size_t)(KA_MAX_N * KA_LDP + 32 * 33 + 64) * sizeof(double)));
     const int cl = ka_cluster_ctas().load();
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
