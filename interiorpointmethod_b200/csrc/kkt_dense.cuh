@@ -178,7 +178,7 @@ __device__ void ka_lu_factor(double* K, int N, int64_t ld, int* piv, double* Psm
         if (crank == 0) {
             for (int idx = tid; idx < rows * KA_PW; idx += KA_NT) {
                 const int r = idx / KA_PW, cc = idx - r * KA_PW;
-                if (cc < pw) K[(size_t)(k0 + r) * ld + k0 + cc] = Psm[idx];
+                if (cc < pw) K[(size_t)(k0 + r) * ld + k0 + cc] = Psm[r * KA_LDP + cc];
             }
         }
         KA_T(4);
