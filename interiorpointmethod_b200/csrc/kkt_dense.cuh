@@ -196,39 +196,79 @@ __device__ void ka_lu_factor(double* K, int N, int64_t ld, int* piv, double* Psm
             __syncthreads();
         }
         KA_T(5);
-        // (5) U12 = L11^-1 K12 and the trailing update K22 -= L21 U12: one thread owns a column of both
+        // (5) U12 = L11^-1 K12 and the trailing update K22 -= L21 U12.  A work item is (column, row slab): the column's 16
+        // entries of U12 live in registers, the rows of the slab are walked in batches of KA_RB whose loads are issued
+        // together.  This CTA owns the 32-column chunks cq with cq % csize == crank; when it has fewer columns than
+        // threads (late panels, or a cluster), the rows of a column are cut into slabs so that the idle threads take a
+        // share of every column's dependent chain of L2 round trips.
         const int c0 = k0 + pw;
-        for (int cc = c0 + tid; cc < N; cc += KA_NT) {
-            if (!mine(cc)) continue;
-            double u[KA_PW];
+        const int cq0 = c0 >> 5;                                         // first chunk that still has columns >= c0
+        const int cqf = cq0 + ((crank - cq0 % csize) + csize) % csize;   // first such chunk owned by this CTA
+        const int cqn = (N + 31) >> 5;
+        const int nchunk = (cqf < cqn) ? (cqn - cqf + csize - 1) / csize : 0;
+        const int ncol = 32 * nchunk;
+        int nslab = (ncol > 0 && ncol < KA_NT) ? KA_NT / ncol : 1;
+        if (nslab > 8) nslab = 8;
+        const int nrow = N - c0;
+        const int slab_rows = ((nrow + nslab - 1) / nslab + KA_RB - 1) / KA_RB * KA_RB;
+        auto load_u = [&](int cc, double (&u)[KA_PW]) {                  // u = L11^-1 K[k0 .. k0+pw)[cc], K untouched
 #pragma unroll
-            for (int r = 0; r < KA_PW; ++r) {
-                double v = 0.0;
+            for (int r = 0; r < KA_PW; ++r) u[r] = (r < pw) ? K[(size_t)(k0 + r) * ld + cc] : 0.0;
+#pragma unroll
+            for (int r = 1; r < KA_PW; ++r) {
                 if (r < pw) {
-                    v = K[(size_t)(k0 + r) * ld + cc];
+                    double v = u[r];
+#pragma unroll
                     for (int q = 0; q < r; ++q) v = fma(-Psm[r * KA_LDP + q], u[q], v);
-                    K[(size_t)(k0 + r) * ld + cc] = v;
+                    u[r] = v;
                 }
-                u[r] = v;
             }
-            // rows in batches of KA_RB: the loads of a batch are independent and issued together (one L2 round trip
-            // per batch instead of one per row - the first version of this loop ran at 10 ms per factorisation,
-            // latency-bound on K[i][cc]), then 16 FMAs per row against the broadcast row of L21
-            for (int i = c0; i < N; i += KA_RB) {
+        };
+        auto store_u = [&](int cc, const double (&u)[KA_PW]) {
+#pragma unroll
+            for (int r = 0; r < KA_PW; ++r)
+                if (r < pw) K[(size_t)(k0 + r) * ld + cc] = u[r];
+        };
+        auto update_rows = [&](int cc, const double (&u)[KA_PW], int i_begin, int i_end) {
+            for (int i = i_begin; i < i_end; i += KA_RB) {
                 double kv[KA_RB];
 #pragma unroll
-                for (int q = 0; q < KA_RB; ++q) kv[q] = (i + q < N) ? K[(size_t)(i + q) * ld + cc] : 0.0;
+                for (int q = 0; q < KA_RB; ++q) kv[q] = (i + q < i_end) ? K[(size_t)(i + q) * ld + cc] : 0.0;
 #pragma unroll
                 for (int q = 0; q < KA_RB; ++q) {
                     const double* lr = Psm + (size_t)(i + q - k0) * KA_LDP;      // same address in every lane: broadcast
-                    if (i + q < N) {
+                    if (i + q < i_end) {
 #pragma unroll
                         for (int r = 0; r < KA_PW; ++r) kv[q] = fma(-lr[r], u[r], kv[q]);
                     }
                 }
 #pragma unroll
                 for (int q = 0; q < KA_RB; ++q)
-                    if (i + q < N) K[(size_t)(i + q) * ld + cc] = kv[q];
+                    if (i + q < i_end) K[(size_t)(i + q) * ld + cc] = kv[q];
+            }
+        };
+        if (nslab == 1) {
+            for (int w = tid; w < ncol; w += KA_NT) {
+                const int cc = (cqf + (w >> 5) * csize) * 32 + (w & 31);
+                if (cc < c0 || cc >= N) continue;
+                double u[KA_PW];
+                load_u(cc, u);
+                store_u(cc, u);
+                update_rows(cc, u, c0, N);
+            }
+        } else {
+            // at most one work item per thread; U12 is written back only after every slab has read the raw column
+            const int ci = (ncol > 0) ? tid % ncol : 0, slab = (ncol > 0) ? tid / ncol : nslab;
+            const int cc = (cqf + (ci >> 5) * csize) * 32 + (ci & 31);
+            const bool have = ncol > 0 && slab < nslab && cc >= c0 && cc < N;
+            double u[KA_PW];
+            if (have) load_u(cc, u);
+            __syncthreads();
+            if (have) {
+                if (slab == 0) store_u(cc, u);
+                const int ib = c0 + slab * slab_rows;
+                const int ie = (ib + slab_rows < N) ? ib + slab_rows : N;
+                update_rows(cc, u, ib, ie);
             }
         }
         // the next panel's columns were updated by whichever CTA owns their chunk
