@@ -5,7 +5,7 @@
 // Left-looking with look-ahead inside the CTA.  Warp 0 is the FACTOR warp, warps 1-7 are UPDATE warps.
 // While warp 0 factors the 32x32 diagonal block of panel J (lane i keeps row i in registers, the pivot travels by
 // warp shuffle, safeguard p <= tau*maxdiag or NaN -> 1e128), the update warps already build
-// panel J+1:  acc = -M[:, J+1] + sum_{K<J} L[:, K] L[J+1, K]^T  on the tensor pipe (DMMA.8x8x4; A fragments
+// panel J+1:  acc = M[:, J+1] - sum_{K<J} L[:, K] L[J+1, K]^T  on the tensor pipe (DMMA.8x8x4; A fragments
 // straight from global memory = L written by this CTA a moment ago, B fragments from a staged shared chunk).
 // After the rows below the block are solved (one thread per row) and panel J is stored, the missing K = J term
 // is added from SHARED memory (the freshly solved panel is both operands) and the accumulators become the raw
@@ -75,7 +75,12 @@ __device__ __forceinline__ void kbc_update_chunk(double (&acc)[4][4][2], const d
                                              : make_double2(0.0, 0.0);
         double2 bf[4];
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) bf[ni] = *reinterpret_cast<const double2*>(bs + ni * 8 * KBC_LDB + kk);
+        for (int ni = 0; ni < 4; ++ni) {
+            // acc holds +M - sum L L^T: the sign lives in the B fragments (shared memory, short latency), so that the
+            // accumulators can be initialised by plain loads that nothing touches until the first MMA
+            const double2 b2 = *reinterpret_cast<const double2*>(bs + ni * 8 * KBC_LDB + kk);
+            bf[ni] = make_double2(-b2.x, -b2.y);
+        }
 #pragma unroll
         for (int ti = 0; ti < NTI; ++ti)
 #pragma unroll
@@ -105,7 +110,7 @@ __device__ __forceinline__ void kbc_update_late(double (&acc)[4][4][2], const do
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) {
             const int r = ni * 8 + g;
-            bf[ni] = (r < nrows) ? Ps[(size_t)r * KBC_LD + kk + t] : 0.0;
+            bf[ni] = (r < nrows) ? -Ps[(size_t)r * KBC_LD + kk + t] : 0.0;
         }
 #pragma unroll
         for (int ti = 0; ti < NTI; ++ti)
@@ -274,7 +279,7 @@ static __global__ void __launch_bounds__(KBC_NT, KBC_NT == 256 ? 2 : 1) kb_chol(
     } else {
         // =================================================================== UPDATE warps
         double acc[4][4][2];
-        // acc <- -M[tile rows][j1 .. j1+31], the start of the early update of the panel at column j1.  Issued one
+        // acc <- +M[tile rows][j1 .. j1+31], the start of the early update of the panel at column j1.  Issued one
         // panel step ahead (before the loop, then right after the accumulators of the previous panel have gone to
         // shared memory), so that the loads are in flight across the barrier and the staging of the first chunk
         // instead of stalling the first MMA (ncu source view, round 2: 13.6 % of the kernel's stall samples).
@@ -291,9 +296,9 @@ static __global__ void __launch_bounds__(KBC_NT, KBC_NT == 256 ? 2 : 1) kb_chol(
                 for (int ni = 0; ni < 4; ++ni) {
                     const int c = j1 + ni * 8 + 2 * t;
                     double v0 = 0.0, v1 = 0.0;
-                    if (ok) {
-                        if (c < m) v0 = -Mb[(size_t)r * ldm + c];
-                        if (c + 1 < m) v1 = -Mb[(size_t)r * ldm + c + 1];
+                    if (ok) {                        // raw loads: no arithmetic on them before the first MMA
+                        if (c < m) v0 = Mb[(size_t)r * ldm + c];
+                        if (c + 1 < m) v1 = Mb[(size_t)r * ldm + c + 1];
                     }
                     acc[ti][ni][0] = v0;
                     acc[ti][ni][1] = v1;
@@ -363,7 +368,7 @@ static __global__ void __launch_bounds__(KBC_NT, KBC_NT == 256 ? 2 : 1) kb_chol(
             __syncthreads();                                       // (S4) everyone is done reading D / Ps
             KBC_T(6);
             if (nrows1 > 0) {
-                // accumulators (sign restored) become the raw panel J+1
+                // accumulators become the raw panel J+1
 #pragma unroll
                 for (int ti = 0; ti < 4; ++ti) {
                     const int tile = uw + ti * KBC_UW;
@@ -372,8 +377,8 @@ static __global__ void __launch_bounds__(KBC_NT, KBC_NT == 256 ? 2 : 1) kb_chol(
                     double* dst = (pr < 32) ? (D + pr * KBC_LD) : (Ps + (size_t)(pr - 32) * KBC_LD);
 #pragma unroll
                     for (int ni = 0; ni < 4; ++ni) {
-                        dst[ni * 8 + 2 * t] = -acc[ti][ni][0];
-                        dst[ni * 8 + 2 * t + 1] = -acc[ti][ni][1];
+                        dst[ni * 8 + 2 * t] = acc[ti][ni][0];
+                        dst[ni * 8 + 2 * t + 1] = acc[ti][ni][1];
                     }
                 }
                 init_acc(j0 + 64);                                 // for the next panel step, ahead of its barrier
