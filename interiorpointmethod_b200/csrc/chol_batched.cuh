@@ -9,7 +9,7 @@
 // straight from global memory = L written by this CTA a moment ago, B fragments from a staged shared chunk).
 // After the rows below the block are solved (one thread per row) and panel J is stored, the missing K = J term
 // is added from SHARED memory (the freshly solved panel is both operands) and the accumulators become the raw
-// panel J+1.  Per panel: diag || early update, trsm, store + late update - five block barriers.
+// panel J+1.  Per panel: diag || early update, trsm, store + late update - four block barriers.
 #pragma once
 #include "common.cuh"
 
@@ -169,13 +169,6 @@ static __global__ void __launch_bounds__(KBC_NT, KBC_NT == 256 ? 2 : 1) kb_chol(
 #endif
 
     // ---- phases executed by every thread (called from both role loops below)
-    auto phase_transpose = [&](int nb) {
-        // transposed copy of L_JJ so that the substitution reads 8 consecutive entries per step
-        for (int idx = tid; idx < 32 * 32; idx += KBC_NT) {
-            const int jj = idx >> 5, kk = idx & 31;
-            DT[kk * KBC_LDT + jj] = (jj < nb && kk <= jj) ? D[jj * KBC_LD + kk] : 0.0;
-        }
-    };
     auto phase_trsm = [&](int nrows1) {
         // rows below the block: x L_JJ^T = a, one thread per row, 8 columns at a time
         for (int r = tid; r < nrows1; r += KBC_NT) {
@@ -256,6 +249,10 @@ static __global__ void __launch_bounds__(KBC_NT, KBC_NT == 256 ? 2 : 1) kb_chol(
 #pragma unroll
                 for (int c = 0; c < 32; ++c)
                     if (c <= lane) D[lane * KBC_LD + c] = arow[c];
+                // the transposed copy the substitution reads (DT[k][j] = L_JJ[j][k]) straight from the registers: one
+                // block barrier and a pass over the block by all threads less per panel
+#pragma unroll
+                for (int c = 0; c < 32; ++c) DT[c * KBC_LDT + lane] = (lane < nb && c <= lane) ? arow[c] : 0.0;
                 dg[lane] = my_inv;
                 if (a.dep != nullptr && a.dep_mode == 2 && lane < nb) a.dep[j0 + lane] = my_bad ? 1 : 0;
 #pragma unroll
@@ -264,9 +261,6 @@ static __global__ void __launch_bounds__(KBC_NT, KBC_NT == 256 ? 2 : 1) kb_chol(
             }
             KBC_T(0);
             __syncthreads();                                       // (S1)
-            KBC_T(1);
-            phase_transpose(nb);
-            __syncthreads();                                       // (S2)
             KBC_T(2);
             phase_trsm(nrows1);
             __syncthreads();                                       // (S3)
@@ -344,10 +338,7 @@ static __global__ void __launch_bounds__(KBC_NT, KBC_NT == 256 ? 2 : 1) kb_chol(
                 }
             }
             KBC_T(0);
-            __syncthreads();                                       // (S1) block factored, early update done
-            KBC_T(1);
-            phase_transpose(nb);
-            __syncthreads();                                       // (S2)
+            __syncthreads();                                       // (S1) block factored (D, DT, dg), early update done
             KBC_T(2);
             phase_trsm(nrows1);
             __syncthreads();                                       // (S3) panel J final in shared memory

@@ -1,7 +1,7 @@
 #!/bin/bash
 set -u
 export PYTHONPATH=$PWD
-O=gpurun_out/r2c13; mkdir -p $O
+O=gpurun_out/r2c14; mkdir -p $O
 timeout 600 python -m pytest tests/test_gpu_batched.py tests/test_gpu_parity.py -q -k "potrf or batched or chol or dense" > $O/pytest_part.log 2>&1; echo "pytest(part) rc=$?" | tee -a $O/summary.txt
 grep -E "^(FAILED|ERROR)|passed|failed" $O/pytest_part.log | cut -c1-200
 timeout 500 python tools/batched_variants.py 0 2 > $O/variants.log 2>&1; echo "variants rc=$?" | tee -a $O/summary.txt
