@@ -1,5 +1,5 @@
 """Interleaved A/B timing of the batched solver's options on the benchmark batch (8192 generator LPs 256 x 512, seeds
-FIRST..): python tools/batched_variants.py [first_seed] [reps]   -  CUDA-event time per solve, phase breakdown."""
+FIRST..): python tools/batched_variants.py [first_seed] [reps] [B]   -  CUDA-event time per solve, phase breakdown."""
 import ctypes
 import sys
 
@@ -13,7 +13,8 @@ from interiorpointmethod_b200.batch import DeviceBatch
 first = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 lib = _lib.load()
-B, m, n = 8192, 256, 512
+B = int(sys.argv[3]) if len(sys.argv) > 3 else 8192
+m, n = 256, 512
 dev = torch.device("cuda:0")
 A_h = torch.empty((B, m, n), dtype=torch.float64, pin_memory=True)
 b_h = torch.empty((B, m), dtype=torch.float64)
