@@ -519,6 +519,16 @@ def main():
     st_h = torch.empty(count, dtype=torch.int32, pin_memory=True)
 
     db = DeviceBatch(A_h.to(dev), b_h.to(dev), c_h.to(dev))
+    # The strong-scaling arm's shard is generated HERE, long before it is timed: the generator's worker threads (numpy /
+    # BLAS) keep spinning for a while after they finish, and a 1024-LP lockstep iteration (2.8 ms) leaves the solver's host
+    # thread no slack for sharing a core with them (tools/strong_shards.py: solves of 55 ms took 80-150 ms when they
+    # followed the generation directly; round 2 call 5 reported 75 ms at N = 8 for that reason).
+    dbs = None
+    if world > 1 and args.scaling == "weak":
+        sfirst, scount = shard_range(args.batch, rank, world)
+        As, bs, cs = ipm.synthetic_dense_batch(sfirst, scount, M_LP, N_LP, threads=max(1, min(16, host_cores() // world)))
+        dbs = DeviceBatch(torch.from_numpy(As).to(dev), torch.from_numpy(bs).to(dev), torch.from_numpy(cs).to(dev))
+        del As, bs, cs
 
     def barrier():
         if world > 1:
@@ -606,10 +616,7 @@ def main():
 
     # ---- strong scaling beside weak (N > 1): BASELINE.json's literal "8192 LPs sharded across N"
     strong = None
-    if world > 1 and args.scaling == "weak":
-        sfirst, scount = shard_range(args.batch, rank, world)
-        As, bs, cs = ipm.synthetic_dense_batch(sfirst, scount, M_LP, N_LP, threads=max(1, min(16, host_cores() // world)))
-        dbs = DeviceBatch(torch.from_numpy(As).to(dev), torch.from_numpy(bs).to(dev), torch.from_numpy(cs).to(dev))
+    if dbs is not None:
         for _ in range(args.warmup):
             step_device(dbs)
         t_s, _, outs = timed(lambda: step_device(dbs), args.steps)

@@ -244,8 +244,11 @@ int ipm_batched_set_variant(int three_pass, int refresh_every);
  *   own dgesv route, main.py:178).  About one generator LP in a thousand; without it such an LP can iterate for
  *   thousands of iterations at |rb| just above the threshold (LPs 16893, 31186, 54456), the reference needs 17-18.
  * Value 2 of IPM_BOPT_REFINE / IPM_BOPT_HANDOFF is a test hook: every corrector takes the refinement step / every LP
- * is handed off after it (tests/test_zz_gpu_refinement.py exercises both paths on whole blocks with them). */
-enum { IPM_BOPT_REFINE = 1, IPM_BOPT_STRIP_TMA = 2, IPM_BOPT_HANDOFF = 3 };
+ * is handed off after it (tests/test_zz_gpu_refinement.py exercises both paths on whole blocks with them).
+ * IPM_BOPT_SYRK_RHS (default 1, four-pass iteration only): the product A w of the predictor right-hand side
+ *   (main.py:225, rhs = -rb - A d (rc - rcomp/x)) is formed by the diagonal tiles of the SYRK kernel from the operand
+ *   slabs it has in shared memory anyway, instead of by a pass of its own over A; 0 = separate pass (A/B). */
+enum { IPM_BOPT_REFINE = 1, IPM_BOPT_STRIP_TMA = 2, IPM_BOPT_HANDOFF = 3, IPM_BOPT_SYRK_RHS = 4 };
 int ipm_batched_set_option(int option, int value);
 /* LPs the most recent batched solve on this process handed to the augmented-system kernel. */
 int ipm_batched_last_handoffs(void);

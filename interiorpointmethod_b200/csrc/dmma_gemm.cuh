@@ -26,6 +26,11 @@ struct DmmaArgs {
     int col0_only = 0;     // warp-specialised kernel only: compute just the first tile column (tiles (bi, 0)) - the
                            // part of a Cholesky trailing update the next panel needs (look-ahead, chol.cuh)
     int max_ctas = 0;      // warp-specialised kernel only: cap of the persistent grid (0 = one CTA per SM)
+    // warp-specialised kernel, batched IPM only (needs dvec): the diagonal tiles also form the predictor right-hand side
+    //   rhs[z][r] = -rbvec[z][r] - sum_k P[r][k] * dvec[z][k] * vvec[z][k]          (main.py:225 with w = d * v)
+    // from the operand slabs that are in shared memory anyway - one pass over A less per iteration.
+    const double* vvec = nullptr;   int64_t strideV = 0;     // [batch][K]
+    const double* rbvec = nullptr;  double* rhs = nullptr;  int64_t strideR = 0;   // [batch][rowsP]
 };
 
 constexpr int DMMA_BK = 16;

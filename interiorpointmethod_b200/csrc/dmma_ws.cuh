@@ -23,11 +23,18 @@ constexpr int WS_BM = 128, WS_BN = 128;
 template <int BK> struct WsGeom {
     static constexpr int LD = BK + 4;
     static constexpr int STAGES = (BK == 16) ? 5 : 3;
-    static constexpr size_t smem = (size_t)STAGES * ((WS_BM + WS_BN) * LD + BK) * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
+    static constexpr size_t smem = (size_t)STAGES * ((WS_BM + WS_BN) * LD + 2 * BK) * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
 };
 constexpr int WS_CONSUMER_WARPS = 8;
 constexpr int WS_PRODUCER_WARPS = 2;    // warp 8 streams P (and d), warp 9 streams Q
-constexpr int WS_THREADS = (WS_CONSUMER_WARPS + WS_PRODUCER_WARPS) * 32;
+// Three warpgroups: two of consumers, one that holds the two producer warps (its other two warps leave at once).
+// ptxas sizes the launch for 384 threads (168 registers each, the same it assumed for 320: it rounds the CTA up to whole
+// warpgroups); the producer group then hands registers back (setmaxnreg.dec) and the consumers take them
+// (setmaxnreg.inc): 8 x 32 x 224 + 4 x 32 x 56 = 64512 = 384 x 168.  With 168 registers the 128 accumulator registers left
+// no room to hold the fragments of the next k-step: 56 B of spills in the inner loop (ncu: 29.6 M local loads per 2048
+// LPs) and every k-step began with an exposed shared-memory load -> scale -> first MMA chain.
+constexpr int WS_THREADS = 384;
+constexpr int WS_REGS_CONSUMER = 224, WS_REGS_PRODUCER = 56;
 
 
 #ifdef __CUDACC__
@@ -47,6 +54,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "r"(addr), "r"(parity)
             : "memory");
     } while (!ok);
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {      // one non-blocking probe
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
@@ -71,15 +95,28 @@ __device__ __forceinline__ void tri_decode(int t, int& bi, int& bj) {
 // Diagonal tile (bi == bj): only the lower triangle is needed.  The 128 rows are cut into 16 strips of 8 rows;
 // strip s needs the 8x8 sub-tiles 0..s.  Consumer warp W takes strips W and 15-W = (W+1) + (16-W) = 17 sub-tiles
 // for every warp, against 32 in a full tile, so a diagonal tile costs 53 % of an off-diagonal one.
-template <int W, int EPI, bool SCALE, int WS_BK>
+// ONE code path for all warps (W is a run-time value): strip 15-W always needs sub-tiles 0..7 and strip W sub-tile 0
+// (nine static accumulators); the other eight accumulators are "slots": slot i <= W is sub-tile i of strip W, slot
+// i > W is sub-tile 7+i-W of strip 15-W (i = 1..8).  A slot picks its A fragment with a select and its B fragment with a run-time row offset, the
+// register indices stay static.  (Round 1 had eight instantiations behind a switch on the warp index; with the
+// fragment prefetch below ptxas then rotated the loop-carried fragments through local memory.)
+template <int EPI, bool SCALE, int WS_BK, bool RHS>
 __device__ __forceinline__ void ws_diag_tile(const DmmaArgs& a, const double* Ps, const double* Qs, const double* Ds,
-                                             uint64_t* full, uint64_t* empty, uint32_t& it, int nk, int z, int row0,
-                                             int lane) {
+                                             const double* Vs, uint64_t* full, uint64_t* empty, uint32_t& it, int nk, int z,
+                                             int row0, int lane, int W) {
+    static_assert(!RHS || (SCALE && EPI == 0), "the right-hand side rides on the scaled product");
     constexpr int LD = WsGeom<WS_BK>::LD, S = WsGeom<WS_BK>::STAGES;
-    constexpr int N0 = W + 1, N1 = 16 - W;
-    constexpr int R0 = 8 * W, R1 = 8 * (15 - W);
+    constexpr int NS = 8, NV = 8;
+    const int R0 = 8 * W, R1 = 8 * (15 - W);
     const int g = lane >> 2, t = lane & 3;
-    double acc0[N0][2], acc1[N1][2];
+    double accS[NS][2], accV[NV][2], acc00[2];      // acc00: sub-tile 0 of strip W
+    int subv[NV];                  // column sub-tile of slot i + 1
+    bool lo[NV];                   // slot belongs to strip W
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        lo[i] = (i + 1 <= W);
+        subv[i] = lo[i] ? i + 1 : 8 + i - W;
+    }
     double* C = a.C + (size_t)z * a.strideC;
     // EPI == 1 (C -= P Q^T): the accumulators start from C, loaded here so that the latency hides behind the
     // first pipeline stages, and the A fragments are negated; the epilogue is then a plain store.
@@ -92,33 +129,76 @@ __device__ __forceinline__ void ws_diag_tile(const DmmaArgs& a, const double* Ps
         }
     };
 #pragma unroll
-    for (int j = 0; j < N0; ++j) init(row0 + R0 + g, row0 + 8 * j + 2 * t, acc0[j][0], acc0[j][1]);
+    for (int j = 0; j < NS; ++j) init(row0 + R1 + g, row0 + 8 * j + 2 * t, accS[j][0], accS[j][1]);
 #pragma unroll
-    for (int j = 0; j < N1; ++j) init(row0 + R1 + g, row0 + 8 * j + 2 * t, acc1[j][0], acc1[j][1]);
+    for (int i = 0; i < NV; ++i) init(row0 + (lo[i] ? R0 : R1) + g, row0 + 8 * subv[i] + 2 * t, accV[i][0], accV[i][1]);
+    init(row0 + R0 + g, row0 + 2 * t, acc00[0], acc00[1]);
+    // Fragments of the NEXT k-step (and, at a stage boundary, of the next stage) are loaded and scaled while the MMAs of
+    // the current one issue.
+    double a0 = 0.0, a1 = 0.0, bs[NS], bv[NV], a0n, a1n, bsn[NS], bvn[NV];
+    // RHS: lane (g,t) sums its columns k = t (mod 4) of rows R0+g, R1+g.  ND partial sums per row: 1 measured faster than
+    // one per k-step of a stage (SYRK phase 170.7 vs 178.9 ms per solve; the FMA of the previous k-step has long left
+    // the FP64 pipe when the next one issues, and the extra registers cost more than the shorter chain returns)
+    constexpr int ND = 1;
+    double vk = 0.0, vkn = 0.0, dot0[ND], dot1[ND];
+#pragma unroll
+    for (int i = 0; i < ND; ++i) dot0[i] = dot1[i] = 0.0;
+    const int pa0 = (R0 + g) * LD + t, pa1 = (R1 + g) * LD + t, pb = g * LD + t;
+    auto load_frag = [&](int s, int kk, double& x0, double& x1, double (&bS)[NS], double (&bV)[NV], double& vv) {
+        const double* ps = Ps + s * WS_BM * LD + kk;
+        const double* qs = Qs + s * WS_BN * LD + pb + kk;
+        x0 = ps[pa0];
+        x1 = ps[pa1];
+        if (SCALE) {
+            const double dv = Ds[s * WS_BK + t + kk];
+            const double dk = (EPI == 1) ? -dv : dv;
+            x0 *= dk;
+            x1 *= dk;
+        } else if (EPI == 1) {
+            x0 = -x0;
+            x1 = -x1;
+        }
+        if (RHS) vv = Vs[s * WS_BK + t + kk];
+#pragma unroll
+        for (int j = 0; j < NS; ++j) bS[j] = qs[j * 8 * LD];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) bV[i] = qs[subv[i] * 8 * LD];
+    };
+    auto mma = [&](const double x0, const double x1, const double (&bS)[NS], const double (&bV)[NV], const double vv,
+                   double& d0, double& d1) {
+        if (RHS) {
+            d0 = fma(x0, vv, d0);
+            d1 = fma(x1, vv, d1);
+        }
+#pragma unroll
+        for (int j = 0; j < NS; ++j) dmma884(accS[j][0], accS[j][1], x1, bS[j]);
+        dmma884(acc00[0], acc00[1], x0, bS[0]);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) dmma884(accV[i][0], accV[i][1], lo[i] ? x0 : x1, bV[i]);
+    };
+    if (nk > 0) {
+        mbar_wait(full + it % S, (it / S) & 1);
+        load_frag(it % S, 0, a0, a1, bs, bv, vk);
+    }
     for (int kt = 0; kt < nk; ++kt, ++it) {
         const int s = it % S;
-        mbar_wait(full + s, (it / S) & 1);
-        const double* ps0 = Ps + s * WS_BM * LD + (R0 + g) * LD + t;
-        const double* ps1 = Ps + s * WS_BM * LD + (R1 + g) * LD + t;
-        const double* qs = Qs + s * WS_BN * LD + g * LD + t;
-        const double* ds = Ds + s * WS_BK + t;
+        // The NEXT stage is awaited here, at the top (the producer runs S - 1 stages ahead: it is complete), so that the
+        // body is straight-line code: two fragment sets in ping-pong (no register copies), one feeds the MMAs while
+        // the other is loaded and scaled; the last load of the body already reads the next stage.  After the last
+        // stage of a tile that load re-reads the current one (harmless, nothing uses it).
+        int sn = s;
+        if (kt + 1 < nk) {
+            const uint32_t it1 = it + 1;
+            sn = it1 % S;
+            mbar_wait(full + sn, (it1 / S) & 1);
+        }
 #pragma unroll
-        for (int kk = 0; kk < WS_BK; kk += 4) {
-            double a0 = ps0[kk], a1 = ps1[kk];
-            if (SCALE) {
-                const double dk = (EPI == 1) ? -ds[kk] : ds[kk];
-                a0 *= dk;
-                a1 *= dk;
-            } else if (EPI == 1) {
-                a0 = -a0;
-                a1 = -a1;
-            }
-#pragma unroll
-            for (int j = 0; j < N1; ++j) {
-                const double b = qs[j * 8 * LD + kk];
-                dmma884(acc1[j][0], acc1[j][1], a1, b);
-                if (j < N0) dmma884(acc0[j][0], acc0[j][1], a0, b);
-            }
+        for (int kk = 0; kk < WS_BK; kk += 8) {
+            load_frag(s, kk + 4, a0n, a1n, bsn, bvn, vkn);
+            mma(a0, a1, bs, bv, vk, dot0[(kk / 4) % ND], dot1[(kk / 4) % ND]);
+            if (kk + 8 < WS_BK) load_frag(s, kk + 8, a0, a1, bs, bv, vk);
+            else load_frag(sn, 0, a0, a1, bs, bv, vk);
+            mma(a0n, a1n, bsn, bvn, vkn, dot0[(kk / 4 + 1) % ND], dot1[(kk / 4 + 1) % ND]);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + s);
@@ -130,12 +210,30 @@ __device__ __forceinline__ void ws_diag_tile(const DmmaArgs& a, const double* Ps
         else cp[0] = v0;
     };
 #pragma unroll
-    for (int j = 0; j < N0; ++j) store(row0 + R0 + g, row0 + 8 * j + 2 * t, acc0[j][0], acc0[j][1]);
+    for (int j = 0; j < NS; ++j) store(row0 + R1 + g, row0 + 8 * j + 2 * t, accS[j][0], accS[j][1]);
 #pragma unroll
-    for (int j = 0; j < N1; ++j) store(row0 + R1 + g, row0 + 8 * j + 2 * t, acc1[j][0], acc1[j][1]);
+    for (int i = 0; i < NV; ++i) store(row0 + (lo[i] ? R0 : R1) + g, row0 + 8 * subv[i] + 2 * t, accV[i][0], accV[i][1]);
+    store(row0 + R0 + g, row0 + 2 * t, acc00[0], acc00[1]);
+    if (RHS) {
+        // the four lanes of a row group hold the columns k = t (mod 4): fixed shuffle tree, then one lane writes
+        double s0 = dot0[0], s1 = dot1[0];
+#pragma unroll
+        for (int i = 1; i < ND; ++i) { s0 += dot0[i]; s1 += dot1[i]; }
+        s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+        s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+        if (t == 0) {
+            const double* rb = a.rbvec + (size_t)z * a.strideR;
+            double* out = a.rhs + (size_t)z * a.strideR;
+            const int r0 = row0 + R0 + g, r1 = row0 + R1 + g;
+            if (r0 < a.rowsP) out[r0] = -rb[r0] - s0;
+            if (r1 < a.rowsP) out[r1] = -rb[r1] - s1;
+        }
+    }
 }
 
-template <int EPI, bool SCALE, int WS_BK>
+template <int EPI, bool SCALE, int WS_BK, bool RHS = false>
 __global__ void __launch_bounds__(WS_THREADS, 1) dmma_ws_kernel(const DmmaArgs a, int ntri, int total_tiles) {
     constexpr int LD = WsGeom<WS_BK>::LD, S = WsGeom<WS_BK>::STAGES;
     constexpr int HK = WS_BK / 2;                 // lanes that cover one row of a slab (16 bytes each)
@@ -143,8 +241,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dmma_ws_kernel(const DmmaArgs a
     extern __shared__ __align__(128) unsigned char ws_raw[];
     double* Ps = reinterpret_cast<double*>(ws_raw);            // [S][128][LD]
     double* Qs = Ps + S * WS_BM * LD;                          // [S][128][LD]
-    double* Ds = Qs + S * WS_BN * LD;                          // [S][16]
-    uint64_t* full = reinterpret_cast<uint64_t*>(Ds + S * WS_BK);
+    double* Ds = Qs + S * WS_BN * LD;                          // [S][BK]
+    double* Vs = Ds + S * WS_BK;                               // [S][BK]  (RHS only)
+    uint64_t* full = reinterpret_cast<uint64_t*>(Vs + S * WS_BK);
     uint64_t* empty = full + S;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -162,6 +261,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dmma_ws_kernel(const DmmaArgs a
     uint32_t it = 0;                                    // ring position, continues across tiles
 
     if (warp >= WS_CONSUMER_WARPS) {
+        setmaxnreg_dec<WS_REGS_PRODUCER>();
+        if (warp >= WS_CONSUMER_WARPS + WS_PRODUCER_WARPS) return;      // the warpgroup's spare warps
         // ------------------------------------------------------------------ producers
         const bool isQ = (warp != WS_CONSUMER_WARPS);
         const int rsub = lane / HK;                 // row inside a group of RPP
@@ -177,6 +278,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dmma_ws_kernel(const DmmaArgs a
             const int nrows = isQ ? a.rowsQ : a.rowsP;
             const int r0 = (isQ ? bj : bi) * WS_BM;
             const double* dv = (SCALE && !isQ) ? a.dvec + (size_t)z * a.strideD : nullptr;
+            const double* vv = (RHS && !isQ) ? a.vvec + (size_t)z * a.strideV : nullptr;
             const bool rows_full = r0 + WS_BM <= nrows;
             const double* src0 = base + (size_t)(r0 + rsub) * ld + kq;
             const size_t rstep = (size_t)RPP * ld;
@@ -187,9 +289,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dmma_ws_kernel(const DmmaArgs a
                 const int k0 = kt * WS_BK;
                 if (rows_full && k0 + WS_BK <= K) {
                     const double* src = src0 + k0;
-#pragma unroll
+#pragma unroll 8                 // (the producers run on 56 registers: no 32 precomputed addresses)
                     for (int j = 0; j < WS_BM / RPP; ++j) cp_async16_zfill(dst + j * RPP * LD, src + j * rstep, 16u);
                     if (dv != nullptr && lane < HK) cp_async16_zfill(Ds + s * WS_BK + kq, dv + k0 + kq, 16u);
+                    if (RHS && vv != nullptr && lane >= HK && lane < 2 * HK) cp_async16_zfill(Vs + s * WS_BK + kq, vv + k0 + kq, 16u);
                 } else {
                     const int k = k0 + kq;
                     const uint32_t kbytes = (k + 1 < K) ? 16u : ((k < K) ? 8u : 0u);
@@ -201,12 +304,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dmma_ws_kernel(const DmmaArgs a
                         cp_async16_zfill(dst + j * RPP * LD, src, nb);
                     }
                     if (dv != nullptr && lane < HK) cp_async16_zfill(Ds + s * WS_BK + kq, kbytes ? dv + k : dv, kbytes);
+                    if (RHS && vv != nullptr && lane >= HK && lane < 2 * HK)
+                        cp_async16_zfill(Vs + s * WS_BK + kq, kbytes ? vv + k : vv, kbytes);
                 }
                 cp_async_mbar_arrive_noinc(full + s);
             }
         }
     } else {
         // ------------------------------------------------------------------ consumers: 4 x 2 warps, 32 x 64 each
+        setmaxnreg_inc<WS_REGS_CONSUMER>();
         constexpr int MI = 4, NI = 8;
         const int g = lane >> 2, t = lane & 3;
         const int wm0 = (warp >> 1) * 32, wn0 = (warp & 1) * 64;
@@ -218,16 +324,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dmma_ws_kernel(const DmmaArgs a
             else tri_decode(tile - z * ntri, bi, bj);
             if (bi == bj) {
                 const int r0d = bi * WS_BM;
-                switch (warp) {
-                    case 0: ws_diag_tile<0, EPI, SCALE, WS_BK>(a, Ps, Qs, Ds, full, empty, it, nk, z, r0d, lane); break;
-                    case 1: ws_diag_tile<1, EPI, SCALE, WS_BK>(a, Ps, Qs, Ds, full, empty, it, nk, z, r0d, lane); break;
-                    case 2: ws_diag_tile<2, EPI, SCALE, WS_BK>(a, Ps, Qs, Ds, full, empty, it, nk, z, r0d, lane); break;
-                    case 3: ws_diag_tile<3, EPI, SCALE, WS_BK>(a, Ps, Qs, Ds, full, empty, it, nk, z, r0d, lane); break;
-                    case 4: ws_diag_tile<4, EPI, SCALE, WS_BK>(a, Ps, Qs, Ds, full, empty, it, nk, z, r0d, lane); break;
-                    case 5: ws_diag_tile<5, EPI, SCALE, WS_BK>(a, Ps, Qs, Ds, full, empty, it, nk, z, r0d, lane); break;
-                    case 6: ws_diag_tile<6, EPI, SCALE, WS_BK>(a, Ps, Qs, Ds, full, empty, it, nk, z, r0d, lane); break;
-                    default: ws_diag_tile<7, EPI, SCALE, WS_BK>(a, Ps, Qs, Ds, full, empty, it, nk, z, r0d, lane); break;
-                }
+                ws_diag_tile<EPI, SCALE, WS_BK, RHS>(a, Ps, Qs, Ds, Vs, full, empty, it, nk, z, r0d, lane, warp);
                 continue;
             }
             double acc[MI][NI][2];
@@ -249,31 +346,49 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dmma_ws_kernel(const DmmaArgs a
                     acc[i][j][1] = v1;
                 }
             }
+            double af[MI], bf[NI], afn[MI], bfn[NI];
+            auto load_frag = [&](int s, int kk, double (&xa)[MI], double (&xb)[NI]) {
+                const double* ps = Ps + s * WS_BM * LD + (wm0 + g) * LD + t + kk;
+                const double* qs = Qs + s * WS_BN * LD + (wn0 + g) * LD + t + kk;
+#pragma unroll
+                for (int i = 0; i < MI; ++i) xa[i] = ps[i * 8 * LD];
+#pragma unroll
+                for (int j = 0; j < NI; ++j) xb[j] = qs[j * 8 * LD];
+                if (SCALE) {
+                    const double dv = Ds[s * WS_BK + t + kk];
+                    const double dk = (EPI == 1) ? -dv : dv;
+#pragma unroll
+                    for (int i = 0; i < MI; ++i) xa[i] *= dk;
+                } else if (EPI == 1) {
+#pragma unroll
+                    for (int i = 0; i < MI; ++i) xa[i] = -xa[i];
+                }
+            };
+            if (nk > 0) {
+                mbar_wait(full + it % S, (it / S) & 1);
+                load_frag(it % S, 0, af, bf);
+            }
+            auto mma = [&](const double (&xa)[MI], const double (&xb)[NI]) {
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], xa[i], xb[j]);
+            };
             for (int kt = 0; kt < nk; ++kt, ++it) {
                 const int s = it % S;
-                mbar_wait(full + s, (it / S) & 1);
-                const double* ps = Ps + s * WS_BM * LD + (wm0 + g) * LD + t;
-                const double* qs = Qs + s * WS_BN * LD + (wn0 + g) * LD + t;
-                const double* ds = Ds + s * WS_BK + t;
+                int sn = s;                                      // see ws_diag_tile
+                if (kt + 1 < nk) {
+                    const uint32_t it1 = it + 1;
+                    sn = it1 % S;
+                    mbar_wait(full + sn, (it1 / S) & 1);
+                }
 #pragma unroll
-                for (int kk = 0; kk < WS_BK; kk += 4) {
-                    double af[MI], bf[NI];
-#pragma unroll
-                    for (int i = 0; i < MI; ++i) af[i] = ps[i * 8 * LD + kk];
-#pragma unroll
-                    for (int j = 0; j < NI; ++j) bf[j] = qs[j * 8 * LD + kk];
-                    if (SCALE) {
-                        const double dk = (EPI == 1) ? -ds[kk] : ds[kk];
-#pragma unroll
-                        for (int i = 0; i < MI; ++i) af[i] *= dk;
-                    } else if (EPI == 1) {
-#pragma unroll
-                        for (int i = 0; i < MI; ++i) af[i] = -af[i];
-                    }
-#pragma unroll
-                    for (int i = 0; i < MI; ++i)
-#pragma unroll
-                        for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                for (int kk = 0; kk < WS_BK; kk += 8) {
+                    load_frag(s, kk + 4, afn, bfn);
+                    mma(af, bf);
+                    if (kk + 8 < WS_BK) load_frag(s, kk + 8, af, bf);
+                    else load_frag(sn, 0, af, bf);
+                    mma(afn, bfn);
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(empty + s);
@@ -309,9 +424,9 @@ inline std::atomic<int>& ws_stage_width() {          // 16 (default) or 32: ipm_
     return bk;
 }
 
-template <int EPI, bool SCALE, int BK>
+template <int EPI, bool SCALE, int BK, bool RHS = false>
 inline int dmma_ws_launch_bk(const DmmaArgs& a, int batch, cudaStream_t st) {
-    auto kern = dmma_ws_kernel<EPI, SCALE, BK>;
+    auto kern = dmma_ws_kernel<EPI, SCALE, BK, RHS>;
     constexpr size_t smem = WsGeom<BK>::smem;
     IPM_TRY(ensure_dyn_smem(kern, smem));
     if (a.rowsP <= 0 || batch <= 0 || a.K <= 0) return IPM_OK;
@@ -335,6 +450,16 @@ inline int dmma_ws_launch(const DmmaArgs& a, int batch, cudaStream_t st) {
 // the register-staged one (arbitrary leading dimensions) otherwise.
 template <int EPI>
 inline int dmma_syrk_auto(const DmmaArgs& a, int batch, cudaStream_t st) {
+    if (a.vvec != nullptr) {             // right-hand side fused into the diagonal tiles: the caller checked ws_eligible
+        if constexpr (EPI == 0) {
+            if (!ws_eligible(a) || !a.dvec || !a.rbvec || !a.rhs || (a.strideV & 1) ||
+                (reinterpret_cast<uintptr_t>(a.vvec) & 15))
+                return IPM_ERR_ARG;
+            return dmma_ws_launch_bk<0, true, 16, true>(a, batch, st);
+        } else {
+            return IPM_ERR_ARG;
+        }
+    }
     if (ws_eligible(a)) {
         if (a.dvec) return dmma_ws_launch<EPI, true>(a, batch, st);
         return dmma_ws_launch<EPI, false>(a, batch, st);

@@ -99,6 +99,7 @@ struct BatchedOptions {
     std::atomic<int> fused{1};          // 0 forces the literal six-pass iteration (tests, A/B timing)
     std::atomic<int> fresh_every{3};    // four-pass path: residuals from scratch every 3rd iteration
     std::atomic<int> refine{1};         // conditional refinement of the corrector (kbf_dir / kb_dir)
+    std::atomic<int> syrk_rhs{1};       // four-pass path: predictor right-hand side formed by the SYRK's diagonal tiles
     std::atomic<int> strip_tma{1};      // four-pass path: strips of A through a tensor map (1) or a strip-major copy (0)
     std::atomic<int> handoff{1};        // LPs the refined corrector cannot fix go to the augmented-system kernel
 };
@@ -296,6 +297,22 @@ __global__ void __launch_bounds__(KB_NT) kb_rhs(const BatchArgs a, int kind) {
         }
         const double dot = warp_sum(dot0 + dot1);
         if (lane == 0) a.rhs[om + r] = -a.rb[om + r] - dot;
+    }
+}
+
+// The vectors of the predictor right-hand side without the product (four-pass iteration with IPM_BOPT_SYRK_RHS):
+// rcx = rcomp/x, v = rc - rcx, w = d v (main.py:72, 150-152); A w is formed by the SYRK's diagonal tiles (DmmaArgs::vvec).
+__global__ void __launch_bounds__(256) kb_wvec(const BatchArgs a, double* __restrict__ v) {
+    const int lp = blockIdx.x;
+    if (a.active[lp] == 0) return;
+    const size_t on = (size_t)lp * a.n;
+    for (int k = threadIdx.x; k < a.n; k += 256) {
+        const double xi = a.x[on + k];
+        const double q = (xi * a.s[on + k]) / xi;
+        const double vv = a.rc[on + k] - q;
+        a.rcx[on + k] = q;
+        a.w[on + k] = a.d[on + k] * vv;
+        v[on + k] = vv;
     }
 }
 
@@ -605,6 +622,11 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
     const bool fused = g_opt.fused.load() != 0 && m <= KF_MAX_M && (n % 2 == 0) &&
                        ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0);
     const bool tma = fused && g_opt.strip_tma.load() != 0;
+    // predictor right-hand side inside the SYRK (one pass over A less): v = rc - rcx lives in dxc until the corrector
+    // pass of the same iteration overwrites it
+    const bool syrk_rhs = fused && g_opt.syrk_rhs.load() != 0 && ws_eligible(g) &&
+                          ((reinterpret_cast<uintptr_t>(a.dxc) & 15) == 0);
+    if (syrk_rhs) { g.vvec = a.dxc; g.strideV = n; g.rbvec = a.rb; g.rhs = a.rhs; g.strideR = m; }
     const bool refine = g_opt.refine.load() != 0;
     a.refine = refine ? g_opt.refine.load() : 0;
     a.handoff = (refine && g_opt.handoff.load() != 0 && ka_slots(B, m, n) > 0) ? g_opt.handoff.load() : 0;
@@ -656,10 +678,10 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
     // GPU never idles on the host round trip; the price is one empty iteration (every kernel skips inactive LPs)
     // after the last LP has converged.  Every LP is bounded by max_iter, so the loop is.
     unsigned* nact_base = a.n_active;
-    cudaEvent_t ev[2] = {nullptr, nullptr};
-    IPM_CUDA_OK(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
-    IPM_CUDA_OK(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
-    struct EvGuard { cudaEvent_t* e; ~EvGuard() { cudaEventDestroy(e[0]); cudaEventDestroy(e[1]); } } ev_guard{ev};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};       // [0,1]: checks; [2,3]: "SYRK of iteration it done"
+    for (int i = 0; i < 4; ++i) IPM_CUDA_OK(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    struct EvGuard { cudaEvent_t* e; ~EvGuard() { for (int i = 0; i < 4; ++i) if (e[i]) cudaEventDestroy(e[i]); } } ev_guard{ev};
+    cudaEvent_t last_syrk = nullptr;            // most recent SYRK enqueued on st
     int it = 0, bodies = 0;
     bool all_joined[2] = {true, true};          // per check slot: had every chunk joined when the check was enqueued?
     bool joined_pending = false;                // a chunk joined after the last check was enqueued
@@ -696,6 +718,12 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
         if (upto <= ka_launched) return IPM_OK;
         kk.list = a.handoff_list + ka_launched;
         kk.work = w.ka_work + (size_t)ka_launched * ka_work_doubles(m, n);
+        // The host learns of a parked LP at the moment the GPU passes from the residual check to the SYRK that is
+        // ALREADY enqueued with the full grid.  If the augmented-system CTAs (high priority) win that race - they do
+        // whenever a short kernel precedes the SYRK - one SYRK CTA finds no SM and runs after another has finished:
+        // the launch takes twice as long (measured: 18.6 instead of 9.55 ms).  So they start behind that SYRK; the
+        // next one is launched with the SMs they hold left out (below).
+        if (last_syrk) IPM_CUDA_OK(cudaStreamWaitEvent(st_kas[ka_next_stream], last_syrk, 0));
         IPM_TRY(ka_launch(kk, upto - ka_launched, st_kas[ka_next_stream]));
         ka_pending[ka_next_stream] += upto - ka_launched;
         ka_next_stream = (ka_next_stream + 1) % KA_STREAMS;
@@ -760,7 +788,15 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
             }
             g.max_ctas = (busy > 0 && busy < kNumSMs / 2) ? kNumSMs - busy : 0;
         }
+        if (syrk_rhs) {
+            kb_wvec<<<B, 256, 0, st>>>(a, a.dxc);
+            count_launch();
+        }
         IPM_TRY((dmma_syrk_auto<0>(g, B, st)));
+        if (a.handoff) {
+            last_syrk = ev[2 + slot];
+            IPM_CUDA_OK(cudaEventRecord(last_syrk, st));
+        }
         IPM_TRY(debug_check("syrk", st));
         g_prof.end_phase(PH_SYRK, st);
         if (m <= KBC_MAX_M_BIG)
@@ -775,7 +811,7 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
         t.active = a.active;
         if (fused) t.out = a.dy;           // the right-hand side survives: the corrector's is built on top of it
         for (int kind = 0; kind < 2; ++kind) {
-            if (!fused || kind == 0) {
+            if (!fused || (kind == 0 && !syrk_rhs)) {
                 kb_rhs<NPL><<<B, KB_NT, smem_w, st>>>(a, kind);
                 count_launch();
             }
@@ -868,6 +904,7 @@ int ipm_batched_set_option(int option, int value) {
     switch (option) {
         case IPM_BOPT_REFINE: g_opt.refine.store(value < 0 ? 0 : (value > 2 ? 2 : value)); return IPM_OK;
         case IPM_BOPT_STRIP_TMA: g_opt.strip_tma.store(value != 0); return IPM_OK;
+        case IPM_BOPT_SYRK_RHS: g_opt.syrk_rhs.store(value != 0); return IPM_OK;
         case IPM_BOPT_HANDOFF: g_opt.handoff.store(value < 0 ? 0 : (value > 2 ? 2 : value)); return IPM_OK;
         default: return IPM_ERR_ARG;
     }

@@ -154,6 +154,28 @@ def test_tensor_map_strips_equal_strip_major_copy(ipm, m, n, B):
     assert np.array_equal(k0, k1) and np.array_equal(o0, o1) and np.array_equal(x0, x1)
 
 
+@pytest.mark.parametrize("m,n,B", [(256, 512, 48), (100, 300, 7), (16, 1024, 3), (255, 510, 5), (129, 258, 9)])
+def test_rhs_from_syrk_tiles_matches_separate_pass(ipm, m, n, B):
+    """IPM_BOPT_SYRK_RHS: the predictor right-hand side -rb - A d (rc - rcomp/x) (main.py:225) formed by the diagonal
+    tiles of the SYRK kernel against the separate pass over A (kb_rhs).  Same sums in a different order: iteration
+    counts within +-1, objectives within 1e-8 relative (ragged m and n: zero-filled slabs, rows >= m not written)."""
+    from interiorpointmethod_b200 import _lib
+    from interiorpointmethod_b200.batch import solve_batched_host
+    lib = _lib.load()
+    A, b, c = ipm.synthetic_dense_batch(11, B, m, n)
+    try:
+        lib.ipm_batched_set_option(_lib.BOPT_SYRK_RHS, 0)
+        o0, k0, s0, x0 = solve_batched_host(A, b, c, tol=1e-8, want_x=True)
+    finally:
+        lib.ipm_batched_set_option(_lib.BOPT_SYRK_RHS, 1)
+    o1, k1, s1, x1 = solve_batched_host(A, b, c, tol=1e-8, want_x=True)
+    assert (s0 == 0).all() and (s1 == 0).all()
+    assert np.abs(k1.astype(int) - k0.astype(int)).max() <= 1
+    assert (np.abs(o1 - o0) <= 1e-8 * np.maximum(1.0, np.abs(o0))).all()
+    same = k0 == k1
+    assert np.allclose(x1[same], x0[same], rtol=1e-6, atol=1e-7)
+
+
 def test_whole_benchmark_batch_against_frozen_tables(ipm):
     """All 8192 LPs of BASELINE.json configs[4] (generator seeds 0..8191) in one batched solve against the frozen
     tables: every LP converges; iteration count within +-1 and objective within 1e-8 relative of the oracle's
