@@ -26,8 +26,8 @@ template <int BK> struct WsGeom {
     static constexpr size_t smem = (size_t)STAGES * ((WS_BM + WS_BN) * LD + 2 * BK) * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
 };
 constexpr int WS_CONSUMER_WARPS = 8;
-constexpr int WS_PRODUCER_WARPS = 2;    // warp 8 streams P (and d), warp 9 streams Q
-// Three warpgroups: two of consumers, one that holds the two producer warps (its other two warps leave at once).
+constexpr int WS_PRODUCER_WARPS = 4;    // warps 8, 10 stream the two 64-row halves of P (warp 8 also d, v), warps 9, 11 those of Q
+// Three warpgroups: two of consumers, one of producers.
 // ptxas sizes the launch for 384 threads (168 registers each, the same it assumed for 320: it rounds the CTA up to whole
 // warpgroups); the producer group then hands registers back (setmaxnreg.dec) and the consumers take them
 // (setmaxnreg.inc): 8 x 32 x 224 + 4 x 32 x 56 = 64512 = 384 x 168.  With 168 registers the 128 accumulator registers left
@@ -264,8 +264,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dmma_ws_kernel(const DmmaArgs a
         setmaxnreg_dec<WS_REGS_PRODUCER>();
         if (warp >= WS_CONSUMER_WARPS + WS_PRODUCER_WARPS) return;      // the warpgroup's spare warps
         // ------------------------------------------------------------------ producers
-        const bool isQ = (warp != WS_CONSUMER_WARPS);
-        const int rsub = lane / HK;                 // row inside a group of RPP
+        const int pw = warp - WS_CONSUMER_WARPS;
+        const bool isQ = (pw & 1) != 0;
+        constexpr int HROWS = WS_BM / (WS_PRODUCER_WARPS / 2);      // rows of a slab per producer warp
+        const int rhalf = (pw >> 1) * HROWS;
+        const bool aux = pw == 0;                   // this warp also brings d and v
+        const int rsub = rhalf + lane / HK;         // row inside the slab: rsub + RPP * j
         const int kq = (lane % HK) * 2;             // this lane's column pair inside the slab
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int z = tile / ntri;
@@ -277,8 +281,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dmma_ws_kernel(const DmmaArgs a
             const int64_t ld = isQ ? a.ldq : a.ldp;
             const int nrows = isQ ? a.rowsQ : a.rowsP;
             const int r0 = (isQ ? bj : bi) * WS_BM;
-            const double* dv = (SCALE && !isQ) ? a.dvec + (size_t)z * a.strideD : nullptr;
-            const double* vv = (RHS && !isQ) ? a.vvec + (size_t)z * a.strideV : nullptr;
+            const double* dv = (SCALE && aux) ? a.dvec + (size_t)z * a.strideD : nullptr;
+            const double* vv = (RHS && aux) ? a.vvec + (size_t)z * a.strideV : nullptr;
             const bool rows_full = r0 + WS_BM <= nrows;
             const double* src0 = base + (size_t)(r0 + rsub) * ld + kq;
             const size_t rstep = (size_t)RPP * ld;
@@ -290,14 +294,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dmma_ws_kernel(const DmmaArgs a
                 if (rows_full && k0 + WS_BK <= K) {
                     const double* src = src0 + k0;
 #pragma unroll 8                 // (the producers run on 56 registers: no 32 precomputed addresses)
-                    for (int j = 0; j < WS_BM / RPP; ++j) cp_async16_zfill(dst + j * RPP * LD, src + j * rstep, 16u);
+                    for (int j = 0; j < HROWS / RPP; ++j) cp_async16_zfill(dst + j * RPP * LD, src + j * rstep, 16u);
                     if (dv != nullptr && lane < HK) cp_async16_zfill(Ds + s * WS_BK + kq, dv + k0 + kq, 16u);
                     if (RHS && vv != nullptr && lane >= HK && lane < 2 * HK) cp_async16_zfill(Vs + s * WS_BK + kq, vv + k0 + kq, 16u);
                 } else {
                     const int k = k0 + kq;
                     const uint32_t kbytes = (k + 1 < K) ? 16u : ((k < K) ? 8u : 0u);
 #pragma unroll 4
-                    for (int j = 0; j < WS_BM / RPP; ++j) {
+                    for (int j = 0; j < HROWS / RPP; ++j) {
                         const int gr = r0 + rsub + RPP * j;
                         const uint32_t nb = (gr < nrows) ? kbytes : 0u;
                         const double* src = nb ? base + (size_t)gr * ld + k : base;
