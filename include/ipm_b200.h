@@ -290,6 +290,10 @@ int ipm_syrk_d(int device_ordinal, int m, int n, const double *A_d, int64_t lda,
 /* Stage width of the SYRK / trailing-update kernel's operand ring: 16 columns x 5 stages (default) or 32 x 3 (half as
  * many stage boundaries per tile).  Process-wide, for A/B measurements; results are bitwise the same. */
 int ipm_set_syrk_stage_width(int columns);
+/* Panel kernel of the blocked Cholesky of ONE large matrix (m > 512; solve_linear, main.py:176-182): 1 (default) = the
+ * diagonal blocks are factored by the fused kernel of the batched solver (32-wide sub-panels, rank-32 updates on the
+ * tensor pipe, look-ahead inside the CTA), 0 = by the round-1 shared-memory kernel.  Process-wide, for A/B. */
+int ipm_set_chol_fused_diag(int on);
 /* In-place safeguarded Cholesky of a dense row-major device matrix (lower). */
 int ipm_potrf_d(int device_ordinal, int m, double *M_d, int64_t ldm, double pivot_rel_thresh, int *n_fixed);
 

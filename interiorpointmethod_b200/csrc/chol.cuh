@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "dmma_gemm.cuh"
 #include "dmma_ws.cuh"
+#include "chol_batched.cuh"
 
 namespace ipm {
 
@@ -223,38 +224,43 @@ static __global__ void __launch_bounds__(TRSM_NT, 1) k_chol_trsm(const CholArgs 
     const int r = j1 + blockIdx.x * ROWS + tid;
     if (tid >= ROWS || r >= a.m) return;
     double* row = Mb + (size_t)r * a.ldm + j0;
+    // Register blocks of CB columns.  Every x[j] sees the same operations in the same order whatever CB is (columns
+    // k = 0..j-1 in increasing order, then the division), so the block width is a pure scheduling choice: 32 gives the
+    // rank-1 updates 32 independent FMAs per column instead of 8 (the kernel is latency-bound: one or two warps per
+    // SM; measured 50 -> see profiles/ microseconds per 128-wide panel).
+    constexpr int CB = (NB % 32 == 0) ? 32 : 8;
 #pragma unroll 1
-    for (int jb = 0; jb < NB; jb += 8) {
-        double acc[8];
+    for (int jb = 0; jb < NB; jb += CB) {
+        double acc[CB];
         {
             const double2* rp = reinterpret_cast<const double2*>(row + jb);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { double2 v = rp[q]; acc[2 * q] = v.x; acc[2 * q + 1] = v.y; }
+            for (int q = 0; q < CB / 2; ++q) { double2 v = rp[q]; acc[2 * q] = v.x; acc[2 * q + 1] = v.y; }
         }
-#pragma unroll 4
+#pragma unroll 2
         for (int k = 0; k < jb; ++k) {
             const double xk = Xs[k * ROWS + tid];
             const double2* lp = reinterpret_cast<const double2*>(LsT + k * LDT + jb);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < CB / 2; ++q) {
                 const double2 l = lp[q];
                 acc[2 * q] -= xk * l.x;
                 acc[2 * q + 1] -= xk * l.y;
             }
         }
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
+        for (int jj = 0; jj < CB; ++jj) {
             const double* lrow = LsT + (jb + jj) * LDT + jb;
             const double x = acc[jj] / lrow[jj];
             acc[jj] = x;
             Xs[(jb + jj) * ROWS + tid] = x;
 #pragma unroll
-            for (int j2 = jj + 1; j2 < 8; ++j2) acc[j2] -= x * lrow[j2];
+            for (int j2 = jj + 1; j2 < CB; ++j2) acc[j2] -= x * lrow[j2];
         }
         {
             double2* wp = reinterpret_cast<double2*>(row + jb);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) wp[q] = make_double2(acc[2 * q], acc[2 * q + 1]);
+            for (int q = 0; q < CB / 2; ++q) wp[q] = make_double2(acc[2 * q], acc[2 * q + 1]);
         }
     }
 }
@@ -277,6 +283,12 @@ struct CholSide {
 };
 static thread_local CholSide g_chol_side[16];
 static bool g_chol_lookahead = true;
+// one matrix: the diagonal blocks go through the fused kernel of the batched solver (32-wide sub-panels with the
+// rank-32 updates on the tensor pipe and look-ahead inside the CTA) instead of k_chol_diag
+inline std::atomic<int>& chol_fused_diag() {
+    static std::atomic<int> on{1};
+    return on;
+}
 
 // ------------------------------------------------------------------------------------------------
 // Host driver: in-place factorisation of `batch` matrices of order m.
@@ -314,8 +326,16 @@ inline int potrf_blocked(double* M, int64_t ldm, int64_t strideM, int m, int bat
     for (int j0 = 0; j0 < m; j0 += NB) {
         a.j0 = j0;
         a.nb = (m - j0 < NB) ? (m - j0) : NB;
-        kd<<<dim3(1, 1, batch), NT_DIAG, chol_diag_smem<NB>(), st>>>(a);
-        count_launch();
+        // (not with a dependent-row mask: on rank-deficient LPs the opt-in path is sensitive to the last bits of the
+        // factor - QAP12 converges in 112 iterations with k_chol_diag's sqrt/divide pivots and stalls 1e-5 short of the
+        // optimum with the fused kernel's rsqrt/multiply ones - so that path keeps the kernel it was validated with)
+        if (batch == 1 && NB <= KBC_MAX_M && scal != nullptr && chol_fused_diag().load() != 0 && (ldm % 2 == 0) &&
+            ((reinterpret_cast<uintptr_t>(M) & 15) == 0) && a.dep == nullptr) {
+            IPM_TRY(potrf_diag_block_fused(M, ldm, j0, a.nb, scal, tau, st, a.dep, a.dep_mode));
+        } else {
+            kd<<<dim3(1, 1, batch), NT_DIAG, chol_diag_smem<NB>(), st>>>(a);
+            count_launch();
+        }
         const int below = m - (j0 + NB);
         if (below > 0) {
             kt<<<dim3(ceil_div(below, ROWS), 1, batch), TRSM_NT, chol_trsm_smem<NB, ROWS>(), st>>>(a);

@@ -35,6 +35,9 @@ struct CholBatchedArgs {
     const int* active;
     unsigned char* dep = nullptr;         // single matrix only: dependent-row mask (see CholArgs in chol.cuh)
     int dep_mode = 0;
+    // Diagonal block of a LARGER matrix (potrf_blocked, chol.cuh): the safeguard threshold comes from the whole
+    // matrix (scal[S_MAXDIAG], set by k_maxdiag), the count of replaced pivots is accumulated, S_MAXDIAG is left alone.
+    int as_block = 0;
 };
 
 inline size_t kbc_smem_bytes(int m) {
@@ -163,7 +166,7 @@ static __global__ void __launch_bounds__(KBC_NT, KBC_NT == 256 ? 2 : 1) kb_chol(
         if (tid == 0) { s_maxdiag = v; s_nfix = 0; }
         __syncthreads();
     }
-    const double thresh = a.tau * s_maxdiag;
+    const double thresh = a.tau * (a.as_block ? a.scal[(size_t)lp * a.strideScal + S_MAXDIAG] : s_maxdiag);
 #ifdef KBC_PROFILE
     long long t_last = clock64();
 #endif
@@ -380,9 +383,28 @@ static __global__ void __launch_bounds__(KBC_NT, KBC_NT == 256 ? 2 : 1) kb_chol(
     }
     __syncthreads();
     if (tid == 0 && a.scal) {
-        a.scal[(size_t)lp * a.strideScal + S_MAXDIAG] = s_maxdiag;
-        a.scal[(size_t)lp * a.strideScal + S_NFIXED] = (double)s_nfix;
+        if (a.as_block) {
+            if (s_nfix) a.scal[(size_t)lp * a.strideScal + S_NFIXED] += (double)s_nfix;
+        } else {
+            a.scal[(size_t)lp * a.strideScal + S_MAXDIAG] = s_maxdiag;
+            a.scal[(size_t)lp * a.strideScal + S_NFIXED] = (double)s_nfix;
+        }
     }
+}
+
+// The diagonal block M[j0 : j0+nb, j0 : j0+nb] (nb <= 256) of one matrix of order m, factored by the fused kernel: the
+// panel kernel of the blocked factorisation (chol.cuh) for one large matrix.
+inline int potrf_diag_block_fused(double* M, int64_t ldm, int j0, int nb, double* scal, double tau, cudaStream_t st,
+                                  unsigned char* dep, int dep_mode) {
+    IPM_TRY(ensure_dyn_smem(kb_chol<KBC_NT>, kbc_smem_bytes(kbc_max_m(KBC_NT))));
+    CholBatchedArgs a;
+    a.M = M + (size_t)j0 * ldm + j0; a.ldm = ldm; a.strideM = 0; a.scal = scal; a.strideScal = 0; a.tau = tau; a.m = nb;
+    a.active = nullptr;
+    a.dep = dep ? dep + j0 : nullptr; a.dep_mode = dep ? dep_mode : 0;
+    a.as_block = 1;
+    kb_chol<KBC_NT><<<1, KBC_NT, kbc_smem_bytes(nb), st>>>(a);
+    count_launch();
+    return launch_check();
 }
 
 template <int NT>

@@ -821,6 +821,11 @@ int ipm_set_syrk_stage_width(int columns) {
     return IPM_OK;
 }
 
+int ipm_set_chol_fused_diag(int on) {
+    chol_fused_diag().store(on != 0);
+    return IPM_OK;
+}
+
 int ipm_potrf_d(int device_ordinal, int m, double* M_d, int64_t ldm, double pivot_rel_thresh, int* n_fixed) {
     if (!M_d) return IPM_ERR_ARG;
     if (m <= 0 || ldm < m || (ldm & 1) || (reinterpret_cast<uintptr_t>(M_d) & 15)) return IPM_ERR_SHAPE;

@@ -47,7 +47,9 @@ def test_table_covers_the_whole_directory():
 
 
 # rank-deficient A: these need the opt-in dependent-row elimination (+ refinement) on top of the Mehrotra start
-RANK_DEFICIENT = {"QAP8", "QAP12", "QAP15"}
+# (DFL001: 13 dependent rows of 6071.  Without the elimination it crawls for 250-350 iterations and whether it arrives
+# depends on the rounding of the factorisation: the round-1 panel kernel did after 258, the fused one does not within 500.)
+RANK_DEFICIENT = {"QAP8", "QAP12", "QAP15", "DFL001"}
 
 
 @pytest.mark.parametrize("name", sorted(k for k, e in TABLE.items() if verdict(e) in ("highs", "unpinned")))
