@@ -290,6 +290,9 @@ int ipm_syrk_d(int device_ordinal, int m, int n, const double *A_d, int64_t lda,
 /* Stage width of the SYRK / trailing-update kernel's operand ring: 16 columns x 5 stages (default) or 32 x 3 (half as
  * many stage boundaries per tile).  Process-wide, for A/B measurements; results are bitwise the same. */
 int ipm_set_syrk_stage_width(int columns);
+/* Consumer warps of that kernel: 8 of 32 x 64 accumulator blocks (default) or 16 of 16 x 64 (four MMA-issuing warps per
+ * scheduler instead of two; csrc/dmma_ws16.cuh).  Process-wide, for A/B measurements; results are bitwise the same. */
+int ipm_set_syrk_consumers(int warps);
 /* Panel kernel of the blocked Cholesky of ONE large matrix (m > 512; solve_linear, main.py:176-182): 1 (default) = the
  * diagonal blocks are factored by the fused kernel of the batched solver (32-wide sub-panels, rank-32 updates on the
  * tensor pipe, look-ahead inside the CTA), 0 = by the round-1 shared-memory kernel.  Process-wide, for A/B. */

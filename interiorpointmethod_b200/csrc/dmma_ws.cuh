@@ -85,6 +85,11 @@ __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsr
 
 // tile index inside one matrix -> (bi, bj) with bj <= bi
 __device__ __forceinline__ void tri_decode(int t, int& bi, int& bj) {
+    if (t < 3) {                 // matrices of up to two tile rows (the batched workload): no double-precision sqrt per tile
+        bi = t > 0;
+        bj = t > 1;
+        return;
+    }
     int i = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
     while ((i + 1) * (i + 2) / 2 <= t) ++i;
     while (i * (i + 1) / 2 > t) --i;
@@ -182,22 +187,29 @@ __device__ __forceinline__ void ws_diag_tile(const DmmaArgs& a, const double* Ps
     }
     for (int kt = 0; kt < nk; ++kt, ++it) {
         const int s = it % S;
-        // The NEXT stage is awaited here, at the top (the producer runs S - 1 stages ahead: it is complete), so that the
+        // The NEXT stage is probed here, at the top (the producer runs S - 1 stages ahead: it is complete), so that the
         // body is straight-line code: two fragment sets in ping-pong (no register copies), one feeds the MMAs while
         // the other is loaded and scaled; the last load of the body already reads the next stage.  After the last
         // stage of a tile that load re-reads the current one (harmless, nothing uses it).
         int sn = s;
+        uint32_t pn = 0;
+        bool ready = true;
         if (kt + 1 < nk) {
             const uint32_t it1 = it + 1;
             sn = it1 % S;
-            mbar_wait(full + sn, (it1 / S) & 1);
-        }
+            pn = (it1 / S) & 1;
+            ready = mbar_test(full + sn, pn);      // probed here, looked at only before the first load from that stage:
+        }                                          // the probe's latency hides behind a k-step of MMAs
 #pragma unroll
         for (int kk = 0; kk < WS_BK; kk += 8) {
             load_frag(s, kk + 4, a0n, a1n, bsn, bvn, vkn);
             mma(a0, a1, bs, bv, vk, dot0[(kk / 4) % ND], dot1[(kk / 4) % ND]);
-            if (kk + 8 < WS_BK) load_frag(s, kk + 8, a0, a1, bs, bv, vk);
-            else load_frag(sn, 0, a0, a1, bs, bv, vk);
+            if (kk + 8 < WS_BK) {
+                load_frag(s, kk + 8, a0, a1, bs, bv, vk);
+            } else {
+                if (!ready) mbar_wait(full + sn, pn);
+                load_frag(sn, 0, a0, a1, bs, bv, vk);
+            }
             mma(a0n, a1n, bsn, bvn, vkn, dot0[(kk / 4 + 1) % ND], dot1[(kk / 4 + 1) % ND]);
         }
         __syncwarp();
@@ -233,6 +245,68 @@ __device__ __forceinline__ void ws_diag_tile(const DmmaArgs& a, const double* Ps
     }
 }
 
+// Producer side of the ring (shared by the 8- and the 16-consumer kernel): producer warp pw of NPW streams its rows of
+// the P (even pw) or Q (odd pw) slabs of every tile this CTA owns, warp 0 also the matching entries of d and v.
+template <bool SCALE, int WS_BK, bool RHS, int NPW>
+__device__ __forceinline__ void ws_produce(const DmmaArgs& a, double* Ps, double* Qs, double* Ds, double* Vs,
+                                           uint64_t* full, uint64_t* empty, int ntri, int total_tiles, int pw, int lane) {
+    constexpr int LD = WsGeom<WS_BK>::LD, S = WsGeom<WS_BK>::STAGES;
+    constexpr int HK = WS_BK / 2;                 // lanes that cover one row of a slab (16 bytes each)
+    constexpr int RPP = 32 / HK;                  // rows per pass of a producer warp
+    const int K = a.K;
+    const int nk = (K + WS_BK - 1) / WS_BK;
+    uint32_t it = 0;
+    const bool isQ = (pw & 1) != 0;
+    constexpr int HROWS = WS_BM / (NPW / 2);      // rows of a slab per producer warp
+    const int rhalf = (pw >> 1) * HROWS;
+    const bool aux = pw == 0;                   // this warp also brings d and v
+    const int rsub = rhalf + lane / HK;         // row inside the slab: rsub + RPP * j
+    const int kq = (lane % HK) * 2;             // this lane's column pair inside the slab
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int z = tile / ntri;
+        if (a.active && a.active[z] == 0) continue;
+        int bi, bj;
+        if (a.col0_only) { bi = tile - z * ntri; bj = 0; }
+        else tri_decode(tile - z * ntri, bi, bj);
+        const double* base = isQ ? a.Q + (size_t)z * a.strideQ : a.P + (size_t)z * a.strideP;
+        const int64_t ld = isQ ? a.ldq : a.ldp;
+        const int nrows = isQ ? a.rowsQ : a.rowsP;
+        const int r0 = (isQ ? bj : bi) * WS_BM;
+        const double* dv = (SCALE && aux) ? a.dvec + (size_t)z * a.strideD : nullptr;
+        const double* vv = (RHS && aux) ? a.vvec + (size_t)z * a.strideV : nullptr;
+        const bool rows_full = r0 + WS_BM <= nrows;
+        const double* src0 = base + (size_t)(r0 + rsub) * ld + kq;
+        const size_t rstep = (size_t)RPP * ld;
+        for (int kt = 0; kt < nk; ++kt, ++it) {
+            const int s = it % S;
+            mbar_wait(empty + s, ((it / S) & 1) ^ 1);
+            double* dst = (isQ ? Qs + s * WS_BN * LD : Ps + s * WS_BM * LD) + rsub * LD + kq;
+            const int k0 = kt * WS_BK;
+            if (rows_full && k0 + WS_BK <= K) {
+                const double* src = src0 + k0;
+#pragma unroll 8                 // (the producers run on 56 registers: no 32 precomputed addresses)
+                for (int j = 0; j < HROWS / RPP; ++j) cp_async16_zfill(dst + j * RPP * LD, src + j * rstep, 16u);
+                if (dv != nullptr && lane < HK) cp_async16_zfill(Ds + s * WS_BK + kq, dv + k0 + kq, 16u);
+                if (RHS && vv != nullptr && lane >= HK && lane < 2 * HK) cp_async16_zfill(Vs + s * WS_BK + kq, vv + k0 + kq, 16u);
+            } else {
+                const int k = k0 + kq;
+                const uint32_t kbytes = (k + 1 < K) ? 16u : ((k < K) ? 8u : 0u);
+#pragma unroll 4
+                for (int j = 0; j < HROWS / RPP; ++j) {
+                    const int gr = r0 + rsub + RPP * j;
+                    const uint32_t nb = (gr < nrows) ? kbytes : 0u;
+                    const double* src = nb ? base + (size_t)gr * ld + k : base;
+                    cp_async16_zfill(dst + j * RPP * LD, src, nb);
+                }
+                if (dv != nullptr && lane < HK) cp_async16_zfill(Ds + s * WS_BK + kq, kbytes ? dv + k : dv, kbytes);
+                if (RHS && vv != nullptr && lane >= HK && lane < 2 * HK)
+                    cp_async16_zfill(Vs + s * WS_BK + kq, kbytes ? vv + k : vv, kbytes);
+            }
+            cp_async_mbar_arrive_noinc(full + s);
+        }
+    }
+}
+
 template <int EPI, bool SCALE, int WS_BK, bool RHS = false>
 __global__ void __launch_bounds__(WS_THREADS, 1) dmma_ws_kernel(const DmmaArgs a, int ntri, int total_tiles) {
     constexpr int LD = WsGeom<WS_BK>::LD, S = WsGeom<WS_BK>::STAGES;
@@ -264,65 +338,24 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dmma_ws_kernel(const DmmaArgs a
         setmaxnreg_dec<WS_REGS_PRODUCER>();
         if (warp >= WS_CONSUMER_WARPS + WS_PRODUCER_WARPS) return;      // the warpgroup's spare warps
         // ------------------------------------------------------------------ producers
-        const int pw = warp - WS_CONSUMER_WARPS;
-        const bool isQ = (pw & 1) != 0;
-        constexpr int HROWS = WS_BM / (WS_PRODUCER_WARPS / 2);      // rows of a slab per producer warp
-        const int rhalf = (pw >> 1) * HROWS;
-        const bool aux = pw == 0;                   // this warp also brings d and v
-        const int rsub = rhalf + lane / HK;         // row inside the slab: rsub + RPP * j
-        const int kq = (lane % HK) * 2;             // this lane's column pair inside the slab
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int z = tile / ntri;
-            if (a.active && a.active[z] == 0) continue;
-            int bi, bj;
-            if (a.col0_only) { bi = tile - z * ntri; bj = 0; }
-            else tri_decode(tile - z * ntri, bi, bj);
-            const double* base = isQ ? a.Q + (size_t)z * a.strideQ : a.P + (size_t)z * a.strideP;
-            const int64_t ld = isQ ? a.ldq : a.ldp;
-            const int nrows = isQ ? a.rowsQ : a.rowsP;
-            const int r0 = (isQ ? bj : bi) * WS_BM;
-            const double* dv = (SCALE && aux) ? a.dvec + (size_t)z * a.strideD : nullptr;
-            const double* vv = (RHS && aux) ? a.vvec + (size_t)z * a.strideV : nullptr;
-            const bool rows_full = r0 + WS_BM <= nrows;
-            const double* src0 = base + (size_t)(r0 + rsub) * ld + kq;
-            const size_t rstep = (size_t)RPP * ld;
-            for (int kt = 0; kt < nk; ++kt, ++it) {
-                const int s = it % S;
-                mbar_wait(empty + s, ((it / S) & 1) ^ 1);
-                double* dst = (isQ ? Qs + s * WS_BN * LD : Ps + s * WS_BM * LD) + rsub * LD + kq;
-                const int k0 = kt * WS_BK;
-                if (rows_full && k0 + WS_BK <= K) {
-                    const double* src = src0 + k0;
-#pragma unroll 8                 // (the producers run on 56 registers: no 32 precomputed addresses)
-                    for (int j = 0; j < HROWS / RPP; ++j) cp_async16_zfill(dst + j * RPP * LD, src + j * rstep, 16u);
-                    if (dv != nullptr && lane < HK) cp_async16_zfill(Ds + s * WS_BK + kq, dv + k0 + kq, 16u);
-                    if (RHS && vv != nullptr && lane >= HK && lane < 2 * HK) cp_async16_zfill(Vs + s * WS_BK + kq, vv + k0 + kq, 16u);
-                } else {
-                    const int k = k0 + kq;
-                    const uint32_t kbytes = (k + 1 < K) ? 16u : ((k < K) ? 8u : 0u);
-#pragma unroll 4
-                    for (int j = 0; j < HROWS / RPP; ++j) {
-                        const int gr = r0 + rsub + RPP * j;
-                        const uint32_t nb = (gr < nrows) ? kbytes : 0u;
-                        const double* src = nb ? base + (size_t)gr * ld + k : base;
-                        cp_async16_zfill(dst + j * RPP * LD, src, nb);
-                    }
-                    if (dv != nullptr && lane < HK) cp_async16_zfill(Ds + s * WS_BK + kq, kbytes ? dv + k : dv, kbytes);
-                    if (RHS && vv != nullptr && lane >= HK && lane < 2 * HK)
-                        cp_async16_zfill(Vs + s * WS_BK + kq, kbytes ? vv + k : vv, kbytes);
-                }
-                cp_async_mbar_arrive_noinc(full + s);
-            }
-        }
+        ws_produce<SCALE, WS_BK, RHS, WS_PRODUCER_WARPS>(a, Ps, Qs, Ds, Vs, full, empty, ntri, total_tiles, warp - WS_CONSUMER_WARPS, lane);
     } else {
         // ------------------------------------------------------------------ consumers: 4 x 2 warps, 32 x 64 each
         setmaxnreg_inc<WS_REGS_CONSUMER>();
         constexpr int MI = 4, NI = 8;
         const int g = lane >> 2, t = lane & 3;
         const int wm0 = (warp >> 1) * 32, wn0 = (warp & 1) * 64;
+        // the active flag of the NEXT tile's matrix is fetched while this tile is computed (a global-memory round trip
+        // at every tile boundary otherwise: all eight consumers stall on it together and the pipe drains)
+        int act_next = (a.active && (int)blockIdx.x < total_tiles) ? a.active[blockIdx.x / ntri] : 1;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int z = tile / ntri;
-            if (a.active && a.active[z] == 0) continue;
+            const int act = act_next;
+            {
+                const int tn = tile + gridDim.x;
+                act_next = (a.active && tn < total_tiles) ? a.active[tn / ntri] : 1;
+            }
+            if (act == 0) continue;
             int bi, bj;
             if (a.col0_only) { bi = tile - z * ntri; bj = 0; }
             else tri_decode(tile - z * ntri, bi, bj);
@@ -381,17 +414,24 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dmma_ws_kernel(const DmmaArgs a
             for (int kt = 0; kt < nk; ++kt, ++it) {
                 const int s = it % S;
                 int sn = s;                                      // see ws_diag_tile
+                uint32_t pn = 0;
+                bool ready = true;
                 if (kt + 1 < nk) {
                     const uint32_t it1 = it + 1;
                     sn = it1 % S;
-                    mbar_wait(full + sn, (it1 / S) & 1);
+                    pn = (it1 / S) & 1;
+                    ready = mbar_test(full + sn, pn);
                 }
 #pragma unroll
                 for (int kk = 0; kk < WS_BK; kk += 8) {
                     load_frag(s, kk + 4, afn, bfn);
                     mma(af, bf);
-                    if (kk + 8 < WS_BK) load_frag(s, kk + 8, af, bf);
-                    else load_frag(sn, 0, af, bf);
+                    if (kk + 8 < WS_BK) {
+                        load_frag(s, kk + 8, af, bf);
+                    } else {
+                        if (!ready) mbar_wait(full + sn, pn);
+                        load_frag(sn, 0, af, bf);
+                    }
                     mma(afn, bfn);
                 }
                 __syncwarp();
@@ -444,8 +484,14 @@ inline int dmma_ws_launch_bk(const DmmaArgs& a, int batch, cudaStream_t st) {
     count_launch();
     return launch_check();
 }
+// 16-consumer variant (dmma_ws16.cuh, included at the end of this file)
+inline std::atomic<int>& ws_consumer_warps();
+template <int EPI, bool SCALE, bool RHS>
+inline int dmma_ws16_launch(const DmmaArgs& a, int batch, cudaStream_t st);
+
 template <int EPI, bool SCALE>
 inline int dmma_ws_launch(const DmmaArgs& a, int batch, cudaStream_t st) {
+    if (ws_consumer_warps().load() == 16) return dmma_ws16_launch<EPI, SCALE, false>(a, batch, st);
     if (ws_stage_width().load() == 32) return dmma_ws_launch_bk<EPI, SCALE, 32>(a, batch, st);
     return dmma_ws_launch_bk<EPI, SCALE, 16>(a, batch, st);
 }
@@ -459,6 +505,7 @@ inline int dmma_syrk_auto(const DmmaArgs& a, int batch, cudaStream_t st) {
             if (!ws_eligible(a) || !a.dvec || !a.rbvec || !a.rhs || (a.strideV & 1) ||
                 (reinterpret_cast<uintptr_t>(a.vvec) & 15))
                 return IPM_ERR_ARG;
+            if (ws_consumer_warps().load() == 16) return dmma_ws16_launch<0, true, true>(a, batch, st);
             return dmma_ws_launch_bk<0, true, 16, true>(a, batch, st);
         } else {
             return IPM_ERR_ARG;
@@ -473,3 +520,5 @@ inline int dmma_syrk_auto(const DmmaArgs& a, int batch, cudaStream_t st) {
 #endif
 
 }  // namespace ipm
+
+#include "dmma_ws16.cuh"

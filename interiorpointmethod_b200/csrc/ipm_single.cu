@@ -821,6 +821,12 @@ int ipm_set_syrk_stage_width(int columns) {
     return IPM_OK;
 }
 
+int ipm_set_syrk_consumers(int warps) {
+    if (warps != 8 && warps != 16) return IPM_ERR_ARG;
+    ws_consumer_warps().store(warps);
+    return IPM_OK;
+}
+
 int ipm_set_chol_fused_diag(int on) {
     chol_fused_diag().store(on != 0);
     return IPM_OK;

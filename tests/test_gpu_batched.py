@@ -176,6 +176,26 @@ def test_rhs_from_syrk_tiles_matches_separate_pass(ipm, m, n, B):
     assert np.allclose(x1[same], x0[same], rtol=1e-6, atol=1e-7)
 
 
+def test_sixteen_consumer_syrk_in_the_batched_solve_bitwise_equal(ipm):
+    """The 16-consumer SYRK (with the predictor right-hand side formed in its diagonal tiles) inside the batched
+    solver: same operations in the same order as the 8-consumer kernel, so whole solves are bitwise equal."""
+    from interiorpointmethod_b200 import _lib
+    from interiorpointmethod_b200.batch import solve_batched_host
+    lib = _lib.load()
+    res = []
+    for (m, n, B) in ((256, 512, 40), (100, 300, 7), (255, 510, 5)):
+        A, b, c = ipm.synthetic_dense_batch(5, B, m, n)
+        try:
+            lib.ipm_set_syrk_consumers(16)
+            r16 = solve_batched_host(A, b, c, tol=1e-8, want_x=True)
+        finally:
+            lib.ipm_set_syrk_consumers(8)
+        r8 = solve_batched_host(A, b, c, tol=1e-8, want_x=True)
+        assert (r8[2] == 0).all()
+        for u, v in zip(r8, r16):
+            assert np.array_equal(u, v)
+
+
 def test_whole_benchmark_batch_against_frozen_tables(ipm):
     """All 8192 LPs of BASELINE.json configs[4] (generator seeds 0..8191) in one batched solve against the frozen
     tables: every LP converges; iteration count within +-1 and objective within 1e-8 relative of the oracle's

@@ -304,6 +304,38 @@ def test_syrk_kernel_against_torch(ipm, m, n):
     assert err <= 1e-12 * ref.abs().max().item() * max(1, n ** 0.5)
 
 
+@pytest.mark.parametrize("m,n", [(256, 512), (129, 258), (300, 77), (1000, 2048), (2500, 300)])
+def test_syrk_sixteen_consumer_warps_bitwise_equal(ipm, m, n):
+    """ipm_set_syrk_consumers(16): sixteen consumer warps of 16 x 64 accumulator blocks (csrc/dmma_ws16.cuh) against the
+    default eight of 32 x 64 - every accumulator sees the same operations in the same order: bitwise equal products,
+    and bitwise equal factors (the trailing updates of the blocked Cholesky go through the same kernel, EPI = 1)."""
+    import ctypes
+    import torch
+    from interiorpointmethod_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(m * 7 + n)
+    A = torch.randn(m, n, dtype=torch.float64, device="cuda", generator=g)
+    d = torch.rand(n, dtype=torch.float64, device="cuda", generator=g) + 0.1
+    ldm = (m + 15) // 16 * 16
+    out = []
+    try:
+        for warps in (8, 16):
+            assert lib.ipm_set_syrk_consumers(warps) == 0
+            M = torch.zeros((m, ldm), dtype=torch.float64, device="cuda")
+            assert lib.ipm_syrk_d(0, m, n, ctypes.c_void_p(A.data_ptr()), n, ctypes.c_void_p(d.data_ptr()),
+                                  ctypes.c_void_p(M.data_ptr()), ldm) == 0
+            M += 10.0 * torch.eye(m, ldm, dtype=torch.float64, device="cuda")      # n < m: make it definite
+            S = torch.tril(M[:, :m]).clone()
+            nf = ctypes.c_int(0)
+            assert lib.ipm_potrf_d(0, m, ctypes.c_void_p(M.data_ptr()), ldm, 1e-30, ctypes.byref(nf)) == 0
+            torch.cuda.synchronize()
+            out.append((S, torch.tril(M[:, :m]).clone()))
+    finally:
+        lib.ipm_set_syrk_consumers(8)
+    assert lib.ipm_set_syrk_consumers(12) != 0
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+
+
 @pytest.mark.parametrize("m", [1, 5, 64, 129, 300, 1000, 2500])
 def test_potrf_kernel_against_torch(ipm, m):
     import ctypes

@@ -22,7 +22,8 @@ c_h = torch.empty((B, n), dtype=torch.float64)
 ipm.synthetic_dense_batch(first, B, m, n, out_A=A_h.numpy(), out_b=b_h.numpy(), out_c=c_h.numpy(), threads=16)
 A_d, b_d, c_d = A_h.to(dev), b_h.to(dev), c_h.to(dev)
 VARIANTS = [("default", []), ("rhs pass of its own", [(_lib.BOPT_SYRK_RHS, 0)]), ("refinement off", [(_lib.BOPT_REFINE, 0)]), ("hand-off off", [(_lib.BOPT_HANDOFF, 0)]),
-            ("strip-major copy", [(_lib.BOPT_STRIP_TMA, 0)]), ("six-pass", "six"), ("syrk stages 32x3", "bk32")]
+            ("strip-major copy", [(_lib.BOPT_STRIP_TMA, 0)]), ("six-pass", "six"), ("syrk stages 32x3", "bk32"),
+            ("syrk 16 consumer warps", "c16")]
 
 
 def setup(v):
@@ -30,7 +31,10 @@ def setup(v):
     for k in (_lib.BOPT_REFINE, _lib.BOPT_HANDOFF, _lib.BOPT_STRIP_TMA, _lib.BOPT_SYRK_RHS):
         lib.ipm_batched_set_option(k, 1)
     lib.ipm_set_syrk_stage_width(16)
-    if v == "six":
+    lib.ipm_set_syrk_consumers(8)
+    if v == "c16":
+        lib.ipm_set_syrk_consumers(16)
+    elif v == "six":
         lib.ipm_batched_set_variant(0, 3)
     elif v == "bk32":
         lib.ipm_set_syrk_stage_width(32)

@@ -1,0 +1,8 @@
+#!/bin/bash
+set -u
+export PYTHONPATH=$PWD
+O=gpurun_out/r2c34; mkdir -p $O
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_batched.py -q -x -k "sixteen or syrk" > $O/pytest_part.log 2>&1; echo "pytest(part) rc=$?" | tee -a $O/summary.txt
+tail -5 $O/pytest_part.log
+timeout 500 python tools/batched_variants.py 0 3 > $O/variants.log 2>&1; echo "variants rc=$?" | tee -a $O/summary.txt
+cat $O/variants.log | cut -c1-200

@@ -1,0 +1,9 @@
+#!/bin/bash
+set -u
+export PYTHONPATH=$PWD
+O=gpurun_out/r2c35; mkdir -p $O
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_batched.py -q -x -k "sixteen or syrk or potrf or batched" > $O/pytest_part.log 2>&1; echo "pytest(part) rc=$?" | tee -a $O/summary.txt
+tail -3 $O/pytest_part.log
+timeout 300 python tools/syrk_shapes.py | tee $O/syrk_shapes.txt
+timeout 500 python tools/batched_variants.py 0 2 > $O/variants.log 2>&1; echo "variants rc=$?" | tee -a $O/summary.txt
+head -3 $O/variants.log | cut -c1-200
