@@ -17,6 +17,7 @@
 //   trsv, kbf_dir<1>            corrector direction, update, residuals of the new point by recurrence
 //   kb_residual<.,true>         from-scratch check_optimality, only for LPs the recurrences declare finished
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -1129,19 +1130,26 @@ int ipm_solve_batched_dense(int device_ordinal, int B, int m, int n, const doubl
     static std::mutex host_ctx_mu[16];
     std::lock_guard<std::mutex> host_ctx_lock(host_ctx_mu[device_ordinal]);
     IPM_CUDA_OK(cudaSetDevice(device_ordinal));
-    // The whole batch gets device buffers; it is copied in chunks on a copy stream (a small first chunk: its copy
-    // is the only one nothing can hide) and ONE lockstep loop runs from the moment the first chunk has landed:
+    // The whole batch gets device buffers; it is copied in chunks of 128 LPs on a copy stream (small chunks: an LP can
+    // join 2.5 ms after its predecessor instead of 20, so the loop has more LPs to work on while the copy is ahead of
+    // it by little - 1024-LP chunks cost 9 ms per 8192-LP solve, tools/e2e_trace.py) and ONE lockstep loop runs from
+    // the moment the first chunk has landed:
     // the LPs of a chunk join the loop at the first iteration after their copy has completed (Arrival).  Solving
     // chunk after chunk instead paid the latency-bound last iterations of a lockstep solve once per chunk.
     std::vector<int> first_of, count_of;
     {
-        int next = std::min(B, 256), at = 0;
+        static const int chunk_lps = [] {
+            const char* e = getenv("IPM_E2E_CHUNK");           // LPs per chunk after the first (A/B measurements)
+            const int v = e ? atoi(e) : 0;
+            return (v >= 32 && v <= 65536) ? v : 128;
+        }();
+        int next = std::min(B, std::min(chunk_lps, 256)), at = 0;
         while (at < B) {
             const int cnt = std::min(next, B - at);
             first_of.push_back(at);
             count_of.push_back(cnt);
             at += cnt;
-            next = 1024;
+            next = chunk_lps;
         }
     }
     const int nchunks = (int)first_of.size();
