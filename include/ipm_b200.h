@@ -297,6 +297,11 @@ int ipm_set_syrk_consumers(int warps);
  * diagonal blocks are factored by the fused kernel of the batched solver (32-wide sub-panels, rank-32 updates on the
  * tensor pipe, look-ahead inside the CTA), 0 = by the round-1 shared-memory kernel.  Process-wide, for A/B. */
 int ipm_set_chol_fused_diag(int on);
+/* Small sparse LPs (n <= 512, m <= 256, no dependent-row mask, no refinement): ipm_solve runs the whole
+ * predictor-corrector loop (main.py:776-815) in ONE launch of one CTA - the kernels of the single-LP path as device
+ * functions, bitwise the same iterates - instead of one CUDA-graph replay and one host round trip per iteration.
+ * 1 (default) / 0: process-wide switch for A/B measurements. */
+int ipm_set_small_lp_fused(int on);
 /* In-place safeguarded Cholesky of a dense row-major device matrix (lower). */
 int ipm_potrf_d(int device_ordinal, int m, double *M_d, int64_t ldm, double pivot_rel_thresh, int *n_fixed);
 

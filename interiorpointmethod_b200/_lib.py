@@ -76,6 +76,7 @@ SYMBOLS = {
     "ipm_measure_dmma_peak": (c_double, [c_int]),
     "ipm_set_syrk_stage_width": (c_int, [c_int]),
     "ipm_set_chol_fused_diag": (c_int, [c_int]),
+    "ipm_set_small_lp_fused": (c_int, [c_int]),
     "ipm_set_syrk_consumers": (c_int, [c_int]),
     "ipm_syrk_d": (c_int, [c_int, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_int64]),
     "ipm_potrf_d": (c_int, [c_int, c_int, c_void_p, c_int64, c_double, _ip]),

@@ -684,7 +684,7 @@ static __global__ void __launch_bounds__(TRSVB_NT, 3) k_trsv_batched(const TrsvB
 constexpr int TRSVI_MAX_BLK = 8;
 inline size_t trsv_batched_inv_smem(int m) { return (size_t)(TRSVI_MAX_BLK * 32 * 33 + m + 32 * TRSVB_NW) * sizeof(double); }
 
-static __global__ void __launch_bounds__(TRSVB_NT, 3) k_trsv_batched_inv(const TrsvBatchedArgs a) {
+static __device__ __forceinline__ void d_trsv_batched_inv(const TrsvBatchedArgs a) {
     extern __shared__ __align__(16) double smem_ti[];
     double* Linv = smem_ti;                              // [8][32][33] block inverses (staging area first)
     double* vec = smem_ti + TRSVI_MAX_BLK * 32 * 33;     // [m]
@@ -805,6 +805,7 @@ static __global__ void __launch_bounds__(TRSVB_NT, 3) k_trsv_batched_inv(const T
         for (int i = tid; i < m; i += TRSVB_NT) dst[i] = vec[i];
     }
 }
+static __global__ void __launch_bounds__(TRSVB_NT, 3) k_trsv_batched_inv(const TrsvBatchedArgs a) { d_trsv_batched_inv(a); }
 
 inline size_t trsv_batched_smem(int m) { return (size_t)(2 * 32 * 33 + m) * sizeof(double); }
 

@@ -123,7 +123,7 @@ __device__ __forceinline__ void kbc_update_late(double (&acc)[4][4][2], const do
 }
 
 template <int KBC_NT>
-static __global__ void __launch_bounds__(KBC_NT, KBC_NT == 256 ? 2 : 1) kb_chol(const CholBatchedArgs a) {
+static __device__ __forceinline__ void d_kb_chol(const CholBatchedArgs& a) {
     constexpr int KBC_UW = KBC_NT / 32 - 1;   // update warps
     extern __shared__ __align__(16) double smem[];
     double* D = smem;                       // [32][33]  diagonal block, becomes L_JJ
@@ -390,6 +390,11 @@ static __global__ void __launch_bounds__(KBC_NT, KBC_NT == 256 ? 2 : 1) kb_chol(
             a.scal[(size_t)lp * a.strideScal + S_NFIXED] = (double)s_nfix;
         }
     }
+}
+
+template <int KBC_NT>
+static __global__ void __launch_bounds__(KBC_NT, KBC_NT == 256 ? 2 : 1) kb_chol(const CholBatchedArgs a) {
+    d_kb_chol<KBC_NT>(a);
 }
 
 // The diagonal block M[j0 : j0+nb, j0 : j0+nb] (nb <= 256) of one matrix of order m, factored by the fused kernel: the

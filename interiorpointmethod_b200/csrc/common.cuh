@@ -172,6 +172,13 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NV], double* partials, u
     if (NV > 1) r[1 % NV] = block_red<OP1>(v[1 % NV], sh);
     if (NV > 2) r[2 % NV] = block_red<OP2>(v[2 % NV], sh);
     if (NV > 3) r[3 % NV] = block_red<OP3>(v[3 % NV], sh);
+    if (gridDim.x == 1) {
+        // one block: the combine below would fold r with identities only (r + 0, min(r, inf)) - the same value without
+        // the fence, the atomic and the round trip through `partials` (small LPs pay them five times per iteration)
+#pragma unroll
+        for (int i = 0; i < NV; ++i) out[i] = r[i];
+        return true;
+    }
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int i = 0; i < NV; ++i) partials[(size_t)blockIdx.x * NV + i] = r[i];

@@ -8,7 +8,9 @@
 #include <vector>
 
 #include "chol.cuh"
+#include <cstdio>
 #include "potrf_auto.cuh"
+#include "small_lp.cuh"
 #include "common.cuh"
 #include "dense.cuh"
 #include "dmma_gemm.cuh"
@@ -341,8 +343,8 @@ int ipm_create(ipm_handle** out, int device_ordinal) {
         IPM_CUDA_OK(cudaMalloc(&h->scal, S_COUNT * sizeof(double)));
         IPM_CUDA_OK(cudaMemset(h->scal, 0, S_COUNT * sizeof(double)));
         IPM_CUDA_OK(cudaMalloc(&h->partials, (size_t)VEC_MAX_BLOCKS * 4 * sizeof(double)));
-        IPM_CUDA_OK(cudaMalloc(&h->counter, sizeof(unsigned)));
-        IPM_CUDA_OK(cudaMemset(h->counter, 0, sizeof(unsigned)));
+        IPM_CUDA_OK(cudaMalloc(&h->counter, 4 * sizeof(unsigned)));      // [1]: iterations of k_small_solve
+        IPM_CUDA_OK(cudaMemset(h->counter, 0, 4 * sizeof(unsigned)));
         IPM_CUDA_OK(cudaMallocHost(&h->h_scal, S_COUNT * sizeof(double)));
         return IPM_OK;
     };
@@ -754,6 +756,51 @@ int ipm_solve(ipm_handle* h, double tol, int max_iter, int y0_is_one, double* x,
     }
     H_TRY(residual_step(h));                     // check_optimality, main.py:780
     H_TRY(fetch_scal(h));
+    // Small sparse LPs: the whole loop in one launch of one CTA (small_lp.cuh) - same device functions, same block
+    // size, bitwise the same iterates as the loop below, without 21 kernel launches and a host round trip per iteration.
+    // (one CTA also forms M: beyond ~10^4 products the many-CTA SpGEMM of the loop below wins - E226, 17.7 k terms:
+    // 228 against 215 us per iteration; BOEING2, 8.3 k: 213 against 234)
+    if (small_lp_fused().load() != 0 && !h->dense && h->n <= SMALL_MAX_N && h->m <= SMALL_MAX_M && h->dep == nullptr &&
+        h->pat && h->pat->nterms <= SMALL_MAX_TERMS &&
+        h->refine_thresh < 0.0 && !h->pipe.Linv && (h->ldm % 2 == 0) && h->h_scal[S_CONT] > 0.5 && max_iter > 0) {
+        H_TRY(ensure_dyn_smem(k_small_solve, small_smem_bytes_max()));
+        SmallArgs sa;
+        sa.m = h->m; sa.n = h->n; sa.nnz = h->nnz; sa.nent = h->nent; sa.ldm = h->ldm;
+        sa.rowptr = h->rowptr; sa.colind = h->colind; sa.t_rowptr = h->t_rowptr; sa.t_colind = h->t_colind;
+        sa.val = h->val; sa.t_val = h->t_val; sa.ad = h->ad;
+        sa.out_idx = h->out_idx; sa.prod_ptr = h->prod_ptr; sa.pa = h->pa; sa.pb = h->pb;
+        sa.b = h->b; sa.c = h->c; sa.x = h->x; sa.y = h->y; sa.s = h->s; sa.rb = h->rb; sa.rc = h->rc; sa.d = h->d;
+        sa.w = h->w; sa.rcx = h->rcx; sa.dxa = h->dxa; sa.dya = h->dya; sa.dsa = h->dsa; sa.dx = h->dx; sa.dy = h->dy;
+        sa.ds = h->ds; sa.tm = h->tm; sa.tn = h->tn; sa.rhs = h->rhs; sa.M = h->M;
+        sa.scal = h->scal; sa.partials = h->partials; sa.counter = h->counter;
+        sa.tol = tol; sa.eta = h->eta; sa.tau = tau; sa.max_iter = max_iter;
+        sa.k_out = reinterpret_cast<int*>(h->counter + 1);
+        sa.vec_off = (int)(small_work_bytes(h->m) / sizeof(double));
+        static const bool want_prof = getenv("IPM_SMALL_PROF") != nullptr;      // tools/small_lp_rate.py: phase cycles
+        long long* prof_d = nullptr;
+        if (want_prof) {
+            H_CUDA(cudaMalloc(&prof_d, 16 * sizeof(long long)));
+            H_CUDA(cudaMemsetAsync(prof_d, 0, 16 * sizeof(long long), h->st));
+        }
+        sa.prof = prof_d;
+        k_small_solve<<<1, VEC_NT, small_smem_bytes(h->m, h->n), h->st>>>(sa);
+        count_launch();
+        H_TRY(launch_check());
+        if (prof_d) {
+            long long hp[16];
+            H_CUDA(cudaMemcpyAsync(hp, prof_d, sizeof(hp), cudaMemcpyDeviceToHost, h->st));
+            H_CUDA(cudaStreamSynchronize(h->st));
+            cudaFree(prof_d);
+            static const char* nm[10] = {"assemble", "cholesky", "make_w", "A w + rhs", "solves", "A^T dy", "direction", "sigma",
+                                         "update", "residual check"};
+            fprintf(stderr, "k_small_solve m=%d n=%d cycles:", h->m, h->n);
+            for (int i = 0; i < 10; ++i) fprintf(stderr, " %s %lld |", nm[i], hp[i]);
+            fprintf(stderr, "\n");
+        }
+        H_CUDA(cudaMemcpyAsync(h->h_scal, h->scal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+        H_CUDA(cudaMemcpyAsync(&k, h->counter + 1, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+        H_CUDA(cudaStreamSynchronize(h->st));
+    }
     while (h->h_scal[S_CONT] > 0.5 && k < max_iter) {
         if (h->use_graph && k >= 1) {
             // iteration 0 ran eagerly (it also sets the kernels' shared-memory attributes); from here on the
@@ -824,6 +871,11 @@ int ipm_set_syrk_stage_width(int columns) {
 int ipm_set_syrk_consumers(int warps) {
     if (warps != 8 && warps != 16) return IPM_ERR_ARG;
     ws_consumer_warps().store(warps);
+    return IPM_OK;
+}
+
+int ipm_set_small_lp_fused(int on) {
+    small_lp_fused().store(on != 0);
     return IPM_OK;
 }
 

@@ -78,8 +78,8 @@ inline void spgemm_symbolic(int m, int n, const int32_t* rowptr, const int32_t* 
 
 #ifdef __CUDACC__
 // y = A v for CSR A, 8 lanes per row (Netlib rows are short), fixed shuffle tree.
-static __global__ void k_spmv_csr(int rows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
-                           const double* __restrict__ val, const double* __restrict__ v, double* __restrict__ y) {
+static __device__ __forceinline__ void d_spmv_csr(int rows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+                           const double* __restrict__ val, const double* v, double* y) {
     const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, sub = lane & 7;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -96,19 +96,23 @@ static __global__ void k_spmv_csr(int rows, const int32_t* __restrict__ rowptr, 
         if (sub == 0 && r < rows) y[r] = acc;
     }
 }
+static __global__ void k_spmv_csr(int rows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+                           const double* __restrict__ val, const double* __restrict__ v, double* __restrict__ y) { d_spmv_csr(rows, rowptr, colind, val, v, y); }
 
 // ad[p] = val[p] * d[colind[p]]   (the A @ D_square factor of main.py:224)
-static __global__ void k_scale_vals(int64_t nnz, const int32_t* __restrict__ colind, const double* __restrict__ val,
-                             const double* __restrict__ d, double* __restrict__ ad) {
+static __device__ __forceinline__ void d_scale_vals(int64_t nnz, const int32_t* __restrict__ colind, const double* __restrict__ val,
+                             const double* d, double* ad) {
     for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nnz; p += (int64_t)gridDim.x * blockDim.x)
         ad[p] = val[p] * d[colind[p]];
 }
+static __global__ void k_scale_vals(int64_t nnz, const int32_t* __restrict__ colind, const double* __restrict__ val,
+                             const double* __restrict__ d, double* __restrict__ ad) { d_scale_vals(nnz, colind, val, d, ad); }
 
 // numeric SpGEMM: one thread per lower-triangle entry of M, terms summed in pattern order (deterministic).
-static __global__ void k_spgemm_numeric(int64_t nent, const int64_t* __restrict__ out_idx,
+static __device__ __forceinline__ void d_spgemm_numeric(int64_t nent, const int64_t* __restrict__ out_idx,
                                  const int64_t* __restrict__ prod_ptr, const int32_t* __restrict__ pa,
-                                 const int32_t* __restrict__ pb, const double* __restrict__ ad,
-                                 const double* __restrict__ val, double* __restrict__ M) {
+                                 const int32_t* __restrict__ pb, const double* ad,
+                                 const double* __restrict__ val, double* M) {
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < nent; e += (int64_t)gridDim.x * blockDim.x) {
         double acc = 0.0;
         const int64_t t1 = prod_ptr[e + 1];
@@ -116,6 +120,10 @@ static __global__ void k_spgemm_numeric(int64_t nent, const int64_t* __restrict_
         M[out_idx[e]] = acc;
     }
 }
+static __global__ void k_spgemm_numeric(int64_t nent, const int64_t* __restrict__ out_idx,
+                                 const int64_t* __restrict__ prod_ptr, const int32_t* __restrict__ pa,
+                                 const int32_t* __restrict__ pb, const double* __restrict__ ad,
+                                 const double* __restrict__ val, double* __restrict__ M) { d_spgemm_numeric(nent, out_idx, prod_ptr, pa, pb, ad, val, M); }
 #endif
 
 }  // namespace ipm

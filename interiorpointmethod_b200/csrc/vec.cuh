@@ -34,7 +34,7 @@ static __global__ void k_norm2(const double* v, int len, double* out, double* pa
 }
 
 // rb = Ax - b and |rb|^2   (main.py:67, 169).  Ax comes from the mat-vec kernel.
-static __global__ void k_resid_primal(const double* Ax, const double* b, double* rb, int m, double* scal, double* partials,
+static __device__ __forceinline__ void d_resid_primal(const double* Ax, const double* b, double* rb, int m, double* scal, double* partials,
                                unsigned* counter) {
     __shared__ double sh[32];
     double acc[1] = {0.0};
@@ -49,10 +49,12 @@ static __global__ void k_resid_primal(const double* Ax, const double* b, double*
         scal[S_NRB] = sqrt(tot[0]);
     }
 }
+static __global__ void k_resid_primal(const double* Ax, const double* b, double* rb, int m, double* scal, double* partials,
+                               unsigned* counter) { d_resid_primal(Ax, b, rb, m, scal, partials, counter); }
 
 // rc = A^T y + s - c, |rc|^2, x^T s, c^T x, d = x/s   (main.py:70, 170-172, 223, 815) and the continue flag
 // of check_optimality (main.py:169-173): strict '<', NaN => stop.  Runs after k_resid_primal on the same stream.
-static __global__ void k_resid_dual(const double* ATy, const double* s, const double* c, const double* x, double* rc,
+static __device__ __forceinline__ void d_resid_dual(const double* ATy, const double* s, const double* c, const double* x, double* rc,
                              double* d, int n, double tol, double* scal, double* partials, unsigned* counter) {
     __shared__ double sh[32];
     double acc[3] = {0.0, 0.0, 0.0};
@@ -94,12 +96,14 @@ static __global__ void k_resid_dual(const double* ATy, const double* s, const do
         scal[S_CONT] = (primal || dual || gap) ? 1.0 : 0.0;
     }
 }
+static __global__ void k_resid_dual(const double* ATy, const double* s, const double* c, const double* x, double* rc,
+                             double* d, int n, double tol, double* scal, double* partials, unsigned* counter) { d_resid_dual(ATy, s, c, x, rc, d, n, tol, scal, partials, counter); }
 
 // Complementarity right-hand side and the eliminated vector of the normal equations:
 //   kind 0: rcomp = x*s                                  (main.py:72)
 //   kind 1: rcomp = x*s + dxa*dsa - sigma*mu             (main.py:150-152)
 //   rcx = rcomp / x ;  w = d * (rc - rcx)                (main.py:225: D^2 (r1 - r3/x))
-static __global__ void k_make_w(int kind, const double* x, const double* s, const double* rc, const double* d,
+static __device__ __forceinline__ void d_make_w(int kind, const double* x, const double* s, const double* rc, const double* d,
                          const double* dxa, const double* dsa, const double* scal, double* rcx, double* w, int n) {
     const double sigma_mu = kind ? scal[S_SIGMA_MU] : 0.0;
     const int64_t T = (int64_t)gridDim.x * blockDim.x;
@@ -130,17 +134,20 @@ static __global__ void k_make_w(int kind, const double* x, const double* s, cons
         w[i] = d[i] * (rc[i] - q);
     }
 }
+static __global__ void k_make_w(int kind, const double* x, const double* s, const double* rc, const double* d,
+                         const double* dxa, const double* dsa, const double* scal, double* rcx, double* w, int n) { d_make_w(kind, x, s, rc, d, dxa, dsa, scal, rcx, w, n); }
 
 // rhs = -rb - A w   (main.py:225)
-static __global__ void k_make_rhs(const double* rb, const double* Aw, double* rhs, int m) {
+static __device__ __forceinline__ void d_make_rhs(const double* rb, const double* Aw, double* rhs, int m) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x)
         rhs[i] = -rb[i] - Aw[i];
 }
+static __global__ void k_make_rhs(const double* rb, const double* Aw, double* rhs, int m) { d_make_rhs(rb, Aw, rhs, m); }
 
 // dx = d*(A^T dy) + w ; ds = -s*dx/x - rcx   (main.py:227-228) fused with the ratio test
 //   alpha = min({-v_i/dv_i : dv_i < 0} U {1})            (main.py:308-319)
 //   kind 1 additionally alpha = min(1, eta*alpha)        (main.py:616-623)
-static __global__ void k_direction(int kind, const double* ATdy, const double* d, const double* w, const double* rcx,
+static __device__ __forceinline__ void d_direction(int kind, const double* ATdy, const double* d, const double* w, const double* rcx,
                             const double* x, const double* s, double* dx, double* ds, int n, double eta, double* scal,
                             double* partials, unsigned* counter) {
     __shared__ double sh[32];
@@ -187,9 +194,12 @@ static __global__ void k_direction(int kind, const double* ATdy, const double* d
         }
     }
 }
+static __global__ void k_direction(int kind, const double* ATdy, const double* d, const double* w, const double* rcx,
+                            const double* x, const double* s, double* dx, double* ds, int n, double eta, double* scal,
+                            double* partials, unsigned* counter) { d_direction(kind, ATdy, d, w, rcx, x, s, dx, ds, n, eta, scal, partials, counter); }
 
 // mu_aff = (x + ap dxa)^T (s + ad dsa)/n ; mu = x^T s/n ; sigma = (mu_aff/mu)^3   (main.py:582-584, 598-600)
-static __global__ void k_sigma(const double* x, const double* s, const double* dxa, const double* dsa, int n, double* scal,
+static __device__ __forceinline__ void d_sigma(const double* x, const double* s, const double* dxa, const double* dsa, int n, double* scal,
                         double* partials, unsigned* counter) {
     __shared__ double sh[32];
     const double ap = scal[S_AP_AFF], ad = scal[S_AD_AFF];
@@ -208,9 +218,11 @@ static __global__ void k_sigma(const double* x, const double* s, const double* d
         scal[S_SIGMA_MU] = sigma * mu;
     }
 }
+static __global__ void k_sigma(const double* x, const double* s, const double* dxa, const double* dsa, int n, double* scal,
+                        double* partials, unsigned* counter) { d_sigma(x, s, dxa, dsa, n, scal, partials, counter); }
 
 // x += ap dx ; s += ad ds ; y += ad dy   (main.py:694-696).  alpha read from scal unless overridden (>= 0).
-static __global__ void k_update(double* x, double* y, double* s, const double* dx, const double* dy, const double* ds, int m,
+static __device__ __forceinline__ void d_update(double* x, double* y, double* s, const double* dx, const double* dy, const double* ds, int m,
                          int n, const double* scal, double ap_override, double ad_override) {
     const double ap = ap_override >= 0.0 ? ap_override : scal[S_AP];
     const double ad = ad_override >= 0.0 ? ad_override : scal[S_AD];
@@ -223,6 +235,8 @@ static __global__ void k_update(double* x, double* y, double* s, const double* d
         if (i < m) y[i] = y[i] + ad * dy[i];
     }
 }
+static __global__ void k_update(double* x, double* y, double* s, const double* dx, const double* dy, const double* ds, int m,
+                         int n, const double* scal, double ap_override, double ad_override) { d_update(x, y, s, dx, dy, ds, m, n, scal, ap_override, ad_override); }
 
 // Conditional refinement of the corrector, single LP (same rule as the batched kbf_dir, ipm_batched_fused.cuh):
 // delta = -rb - A dx; flag = |delta| > thresh |rb| (NaN compares false).  The solve M ddy = delta runs
