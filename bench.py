@@ -671,7 +671,9 @@ def main():
     # rank 0's own share of the step: lp_it counts rank 0's LP-iterations over args.steps solves
     whole_tf = float(lp_it.value) * F_LP_ITER / (per_rank_dev[0] * 1e-3 * args.steps) * 1e-12
     roofline = {
-        "kernel": "dmma_ws_kernel<0,true> (batched SYRK M = A diag(x/s) A^T, warp-specialised persistent, DMMA.8x8x4)",
+        "kernel": "dmma_ws_kernel<0,true,16,true> (batched SYRK M = A diag(x/s) A^T, warp-specialised persistent, DMMA.8x8x4; "
+                  "its diagonal tiles also form the predictor right-hand side; the timed phase includes the elementwise "
+                  "kb_wvec launch that precedes it)",
         "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
         "frac": achieved_tf / peak_tf if peak_tf > 0 else None, "traffic": traffic,
         "peak_source": "FP64 DMMA issue-rate ceiling measured live on this GPU (ipm_measure_dmma_peak); "
@@ -681,6 +683,11 @@ def main():
         "share_of_step": syrk_s / t_dev if t_dev > 0 else None,
         "whole_step_tflops": whole_tf, "whole_step_frac": whole_tf / peak_tf if peak_tf > 0 else None,
         "whole_step_flop_per_lp_iteration": F_LP_ITER,
+        "full_batch_launch": (lambda v: None if not v else {
+            "ms": sorted(v)[len(v) // 2], "tflops": count * M_LP * M_LP * N_LP / (sorted(v)[len(v) // 2] * 1e-3) * 1e-12,
+            "frac": (count * M_LP * M_LP * N_LP / (sorted(v)[len(v) // 2] * 1e-3) * 1e-12 / peak_tf) if peak_tf > 0 else None,
+            "what": "median SYRK phase of the lockstep iterations in which every LP of the batch is still active"})(
+            [trace_ms[i] for i in range(min(ntr, 512)) if trace_ph[i] == 1][:12]),
         "last_step_syrk_ms_per_iteration": [round(trace_ms[i], 3) for i in range(min(ntr, 512)) if trace_ph[i] == 1],
         "last_step_cholesky_ms_per_iteration": [round(trace_ms[i], 3) for i in range(min(ntr, 512)) if trace_ph[i] == 2],
         "phase_ms_per_step": {"residual_pass": ms[0] / args.steps, "syrk": ms[1] / args.steps,

@@ -733,21 +733,44 @@ static __device__ __forceinline__ void d_trsv_batched_inv(const TrsvBatchedArgs 
         for (int i = 0; i < 32; ++i) Ls[i * 33 + lane] = x[i];                        // column `lane` of the inverse
     }
     __syncthreads();
+    // Both sweeps are chains of block steps, each: off-diagonal mat-vec, barrier, inverse applied by warp 0, barrier.
+    // The entries of L a step multiplies do not depend on the solve, only the vector does: they are loaded into
+    // registers one step AHEAD, right after the previous step has consumed its own, so that the L2 / HBM round trip
+    // runs behind the reduction, the barriers and the inverse instead of in front of every step (ncu, round 2: 26 % of
+    // the stall samples on the load of the forward mat-vec, 24 % on the barriers behind it).  Same products summed in
+    // the same order: bitwise the results of the unpipelined sweeps.
     // ---- forward
+    constexpr int FW_J = TRSVI_MAX_BLK - 1;                        // k-chunks of 32 a block row can have
+    double lv[4][FW_J];
+    auto load_rows = [&](int I) {                                  // block row I: rows i0 + warp + 8 q, columns lane + 32 j
+        const int i0 = I << 5;
+        const int nb = (m - i0 < 32) ? (m - i0) : 32;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int rr = warp + q * TRSVB_NW;
+            const double* row = L + (size_t)(i0 + rr) * ldm + lane;
+#pragma unroll
+            for (int j = 0; j < FW_J; ++j) lv[q][j] = (j < I && rr < nb) ? row[32 * j] : 0.0;
+        }
+    };
+    if (nblk > 1) load_rows(1);
     for (int I = 0; I < nblk; ++I) {
         const int i0 = I << 5;
         const int nb = (m - i0 < 32) ? (m - i0) : 32;
         if (i0 > 0) {
             double acc[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 4
-            for (int k = lane; k < i0; k += 32) {
-                const double zk = vec[k];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int rr = warp + q * TRSVB_NW;
-                    if (rr < nb) acc[q] += L[(size_t)(i0 + rr) * ldm + k] * zk;
+            for (int j = 0; j < FW_J; ++j) {
+                if (j < I) {
+                    const double zk = vec[lane + 32 * j];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int rr = warp + q * TRSVB_NW;
+                        if (rr < nb) acc[q] += lv[q][j] * zk;
+                    }
                 }
             }
+            if (I + 1 < nblk) load_rows(I + 1);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const double sum = warp_sum(acc[q]);
@@ -769,7 +792,16 @@ static __device__ __forceinline__ void d_trsv_batched_inv(const TrsvBatchedArgs 
         }
         __syncthreads();
     }
-    // ---- backward
+    // ---- backward (m <= 256: thread k owns column k of the block row being eliminated)
+    double cv[32];
+    auto load_cols = [&](int I) {                                  // block row I, column tid: 32 entries
+        const int i0 = I << 5;
+        const int nb = (m - i0 < 32) ? (m - i0) : 32;
+        const double* col = L + (size_t)i0 * ldm + tid;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) cv[i] = (tid < i0 && i < nb) ? col[(size_t)i * ldm] : 0.0;
+    };
+    if (nblk > 1) load_cols(nblk - 1);
     for (int I = nblk - 1; I >= 0; --I) {
         const int i0 = I << 5;
         const int nb = (m - i0 < 32) ? (m - i0) : 32;
@@ -785,17 +817,19 @@ static __device__ __forceinline__ void d_trsv_batched_inv(const TrsvBatchedArgs 
             if (lane < nb) vec[i0 + lane] = acc0 + acc1;
         }
         __syncthreads();
-        for (int k = tid; k < i0; k += TRSVB_NT) {
-            const double* col = L + (size_t)i0 * ldm + k;
+        if (tid < i0) {
             double acc = 0.0;
             if (nb == 32) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) acc += col[(size_t)i * ldm] * vec[i0 + i];
+                for (int i = 0; i < 32; ++i) acc += cv[i] * vec[i0 + i];
             } else {
-                for (int i = 0; i < nb; ++i) acc += col[(size_t)i * ldm] * vec[i0 + i];
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (i < nb) acc += cv[i] * vec[i0 + i];          // (static indices: cv stays in registers)
             }
-            vec[k] -= acc;
+            vec[tid] -= acc;
         }
+        if (I - 1 >= 1) load_cols(I - 1);
         __syncthreads();
     }
     double* dst = a.out ? a.out + (size_t)bz * a.strideV : v;
@@ -805,7 +839,8 @@ static __device__ __forceinline__ void d_trsv_batched_inv(const TrsvBatchedArgs 
         for (int i = tid; i < m; i += TRSVB_NT) dst[i] = vec[i];
     }
 }
-static __global__ void __launch_bounds__(TRSVB_NT, 3) k_trsv_batched_inv(const TrsvBatchedArgs a) { d_trsv_batched_inv(a); }
+// (two CTAs per SM: the prefetch buffers need the registers; three were no faster, IPM_TRSV_SMEM_KB A/B)
+static __global__ void __launch_bounds__(TRSVB_NT, 2) k_trsv_batched_inv(const TrsvBatchedArgs a) { d_trsv_batched_inv(a); }
 
 inline size_t trsv_batched_smem(int m) { return (size_t)(2 * 32 * 33 + m) * sizeof(double); }
 

@@ -731,8 +731,15 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
         ka_launched = upto;
         return IPM_OK;
     };
+    static const size_t trsv_pad_kb = [] {       // A/B: extra dynamic shared memory caps the CTAs per SM (IPM_TRSV_SMEM_KB)
+        const char* e = getenv("IPM_TRSV_SMEM_KB");
+        const int v = e ? atoi(e) : 0;
+        return (size_t)((v >= 0 && v <= 220) ? v : 0);
+    }();
+    const size_t trsv_smem = std::max(trsv_batched_inv_smem(m), trsv_pad_kb * 1024);
+    if (trsv_pad_kb) IPM_TRY(ensure_dyn_smem(k_trsv_batched_inv, std::max(trsv_batched_inv_smem(32 * TRSVI_MAX_BLK), trsv_pad_kb * 1024)));
     auto launch_trsv = [&](const TrsvBatchedArgs& t) {
-        if (small_m) k_trsv_batched_inv<<<B, TRSVB_NT, trsv_batched_inv_smem(m), st>>>(t);
+        if (small_m) k_trsv_batched_inv<<<B, TRSVB_NT, trsv_smem, st>>>(t);
         else k_trsv_batched<<<B, TRSVB_NT, trsv_batched_smem(m), st>>>(t);
         count_launch();
     };

@@ -3,7 +3,7 @@
 # reference arm under torchrun.   gpurun --gpus 8 --timeout 1200 -- 'bash tools/r2_call5_multi.sh'
 set -u
 export PYTHONPATH=$PWD
-O=gpurun_out/r2c33; mkdir -p $O
+O=gpurun_out/r2c43; mkdir -p $O
 N=${1:-8}
 nvidia-smi topo -m > $O/topo.txt 2>&1
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 \
