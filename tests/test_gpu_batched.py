@@ -104,10 +104,10 @@ def test_three_pass_iteration_matches_six_pass(ipm, m, n, B):
     try:
         lib.ipm_batched_set_variant(0, 3)
         o6, k6, s6 = solve_batched_host(A, b, c, tol=1e-8)
-        lib.ipm_batched_set_variant(1, 3)
+        lib.ipm_batched_set_variant(1, _lib.REFRESH_DEFAULT)
         o3, k3, s3, x3 = solve_batched_host(A, b, c, tol=1e-8, want_x=True)
     finally:
-        lib.ipm_batched_set_variant(1, 3)
+        lib.ipm_batched_set_variant(1, _lib.REFRESH_DEFAULT)
     assert (s6 == 0).all() and (s3 == 0).all()
     assert np.abs(k3.astype(int) - k6.astype(int)).max() <= 1
     assert (np.abs(o3 - o6) <= 1e-8 * np.abs(o6)).all()      # the parity bar of SURVEY 8(c)
@@ -127,7 +127,7 @@ def test_three_pass_refresh_keeps_ill_conditioned_lp_on_track(ipm):
         lib.ipm_batched_set_variant(0, 3)
         o6, k6, s6 = solve_batched_host(A, b, c, tol=1e-8)
     finally:
-        lib.ipm_batched_set_variant(1, 3)
+        lib.ipm_batched_set_variant(1, _lib.REFRESH_DEFAULT)
     o3, k3, s3 = solve_batched_host(A, b, c, tol=1e-8)
     assert (s6 == 0).all() and (s3 == 0).all()
     assert np.abs(k3.astype(int) - k6.astype(int)).max() <= 1

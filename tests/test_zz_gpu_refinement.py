@@ -40,10 +40,10 @@ def test_refinement_keeps_the_trapped_lps_at_the_reference_count(ipm, tables, se
     first = seed - seed % 64
     A, b, c = ipm.synthetic_dense_batch(first, 64, 256, 512)
     try:
-        lib.ipm_batched_set_variant(three_pass, 3)
+        lib.ipm_batched_set_variant(three_pass, _lib.REFRESH_DEFAULT)
         obj, it, st, x = solve_batched_host(A, b, c, tol=1e-8, max_iter=400, want_x=True)
     finally:
-        lib.ipm_batched_set_variant(1, 3)
+        lib.ipm_batched_set_variant(1, _lib.REFRESH_DEFAULT)
     assert (st == 0).all(), (st, it)
     want_k, want_obj = ok[first:first + 64].astype(int), oobj[first:first + 64]
     assert np.abs(it.astype(int) - want_k).max() <= 1, (it, want_k)
@@ -70,7 +70,7 @@ def test_forced_refinement_and_forced_handoff(ipm, three_pass):
     A, b, c = ipm.synthetic_dense_batch(0, 40, 256, 512)
     A2, b2, c2 = ipm.synthetic_dense_batch(50, 24, 48, 100)
     try:
-        lib.ipm_batched_set_variant(three_pass, 3)
+        lib.ipm_batched_set_variant(three_pass, _lib.REFRESH_DEFAULT)
         lib.ipm_batched_set_option(_lib.BOPT_REFINE, 2)
         o_r, k_r, s_r = solve_batched_host(A, b, c, tol=1e-8)
         assert lib.ipm_batched_last_handoffs() == 0 or True
@@ -80,7 +80,7 @@ def test_forced_refinement_and_forced_handoff(ipm, three_pass):
         o_h2, k_h2, s_h2 = solve_batched_host(A2, b2, c2, tol=1e-8)
         n_h2 = lib.ipm_batched_last_handoffs()
     finally:
-        lib.ipm_batched_set_variant(1, 3)
+        lib.ipm_batched_set_variant(1, _lib.REFRESH_DEFAULT)
         lib.ipm_batched_set_option(_lib.BOPT_REFINE, 1)
         lib.ipm_batched_set_option(_lib.BOPT_HANDOFF, 1)
     assert (s_r == 0).all() and (s_h == 0).all() and (s_h2 == 0).all()
@@ -107,12 +107,14 @@ def test_the_trap_is_there_without_refinement(ipm):
         # Which LP falls into the trap depends on the last bits of the right-hand side: LP 16893 is
         # the one under the summation order of the separate right-hand-side pass, so both arms use that pass here.
         lib.ipm_batched_set_option(_lib.BOPT_SYRK_RHS, 0)
+        lib.ipm_batched_set_variant(1, 3)       # ... and the residual refresh period the trap was recorded with
         obj1, it1, st1 = solve_batched_host(A, b, c, tol=1e-8, max_iter=120)
         lib.ipm_batched_set_option(_lib.BOPT_REFINE, 0)
         obj0, it0, st0 = solve_batched_host(A, b, c, tol=1e-8, max_iter=120)
     finally:
         lib.ipm_batched_set_option(_lib.BOPT_REFINE, 1)
         lib.ipm_batched_set_option(_lib.BOPT_SYRK_RHS, 1)
+        lib.ipm_batched_set_variant(1, _lib.REFRESH_DEFAULT)
     assert int(st1[at]) == 0 and int(it1[at]) <= 20
     assert int(it0[at]) == 120 and int(st0[at]) == 1
     same = np.array([i for i in range(64) if i != at and it0[i] == it1[i]])

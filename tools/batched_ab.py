@@ -22,7 +22,7 @@ dev = torch.device("cuda:0")
 db = DeviceBatch(torch.from_numpy(A).to(dev), torch.from_numpy(b).to(dev), torch.from_numpy(c).to(dev))
 res = {}
 for variant in variants:
-    lib.ipm_batched_set_variant(variant, 3)
+    lib.ipm_batched_set_variant(variant, _lib.REFRESH_DEFAULT)
     db.solve(tol=1e-8, max_iter=max_iter)
     lib.ipm_profile_enable(1)
     t0 = time.perf_counter()

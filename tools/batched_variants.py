@@ -27,7 +27,7 @@ VARIANTS = [("default", []), ("rhs pass of its own", [(_lib.BOPT_SYRK_RHS, 0)]),
 
 
 def setup(v):
-    lib.ipm_batched_set_variant(1, 3)
+    lib.ipm_batched_set_variant(1, _lib.REFRESH_DEFAULT)
     for k in (_lib.BOPT_REFINE, _lib.BOPT_HANDOFF, _lib.BOPT_STRIP_TMA, _lib.BOPT_SYRK_RHS):
         lib.ipm_batched_set_option(k, 1)
     lib.ipm_set_syrk_stage_width(16)

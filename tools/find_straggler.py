@@ -15,7 +15,7 @@ t_start = time.time()
 for blk in blocks:
     ipm.synthetic_dense_batch(blk * BLK, BLK, m, n, out_A=A_h.numpy(), out_b=b_h.numpy(), out_c=c_h.numpy(), threads=16)
     db = DeviceBatch(A_h.to(dev), b_h.to(dev), c_h.to(dev))
-    lib.ipm_batched_set_variant(1, 3); lib.ipm_batched_set_straggler_restart(0 if '--no-restart' in sys.argv else 8)
+    lib.ipm_batched_set_variant(1, _lib.REFRESH_DEFAULT); lib.ipm_batched_set_straggler_restart(0 if '--no-restart' in sys.argv else 8)
     t = time.perf_counter(); nit = db.solve(tol=1e-8); dt = time.perf_counter() - t
     it = db.iters.cpu().numpy()
     bad = np.nonzero(it > 30)[0]
@@ -29,5 +29,5 @@ for blk in blocks:
             print("   %-28s lockstep %4d  %.0f ms  outlier its %s status %s obj %s  max|dk| others %d" % (
                 label, nit, dt * 1e3, [int(it2[i]) for i in bad[:8]], [int(st2[i]) for i in bad[:8]],
                 ["%.10g" % ob[i] for i in bad[:4]], int(np.abs(np.delete(it2, bad).astype(int) - np.delete(it, bad).astype(int)).max())), flush=True)
-        lib.ipm_batched_set_variant(1, 3); lib.ipm_batched_set_straggler_restart(8)
+        lib.ipm_batched_set_variant(1, _lib.REFRESH_DEFAULT); lib.ipm_batched_set_straggler_restart(8)
     del db

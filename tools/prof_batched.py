@@ -18,6 +18,6 @@ reps = (B + A.shape[0] - 1) // A.shape[0]
 A = np.tile(A, (reps, 1, 1))[:B]; b = np.tile(b, (reps, 1))[:B]; c = np.tile(c, (reps, 1))[:B]
 dev = torch.device("cuda:0")
 db = DeviceBatch(torch.from_numpy(A).to(dev), torch.from_numpy(b).to(dev), torch.from_numpy(c).to(dev))
-lib.ipm_batched_set_variant(variant, 3)
+lib.ipm_batched_set_variant(variant, _lib.REFRESH_DEFAULT)
 nit = db.solve(tol=1e-8, max_iter=max_iter)
 print("lockstep iterations", nit, "status ok", bool((db.status == 0).all()))

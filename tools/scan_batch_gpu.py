@@ -25,6 +25,9 @@ A_h = torch.empty((BLK, m, n), dtype=torch.float64, pin_memory=True)
 b_h = torch.empty((BLK, m), dtype=torch.float64, pin_memory=True)
 c_h = torch.empty((BLK, n), dtype=torch.float64, pin_memory=True)
 blocks = [int(v) for v in sys.argv[1:] if not v.startswith("--")] or list(range(8))
+for v in sys.argv[1:]:
+    if v.startswith("--refresh="):          # period of the from-scratch residual check of the four-pass iteration (default 3)
+        lib.ipm_batched_set_variant(1, int(v.split("=")[1]))
 t_start = time.time()
 tot_bad = 0
 
@@ -76,7 +79,7 @@ for blk in blocks:
                   % (label, dt2 * 1e3, nit2, int((st2 == 0).sum()), int(np.abs(it2 - base[0]).max()),
                      bool(np.array_equal(ob2, base[1]))), flush=True)
             del db2
-            lib.ipm_batched_set_variant(1, 3)
+            lib.ipm_batched_set_variant(1, _lib.REFRESH_DEFAULT)
             lib.ipm_batched_set_option(_lib.BOPT_STRIP_TMA, 1)
             lib.ipm_batched_set_option(_lib.BOPT_REFINE, 1)
             lib.ipm_batched_set_option(_lib.BOPT_HANDOFF, 1)
