@@ -214,12 +214,14 @@ int64_t ipm_batched_workspace_bytes(int B, int m, int n);
  *   direction, corrector direction): the corrector right-hand side comes from the predictor's by linearity of
  *   main.py:150-152 and the residuals of the new point from the recurrences rb += ap A dx, rc += ad (A^T dy + ds).
  *   check_optimality (main.py:169-173) is re-evaluated from scratch before an LP is declared finished and in
- *   every refresh_every-th iteration (default 6; 0 = only at the end).  Without the periodic refresh the
- *   recurrences drift from the true residuals in the ill-conditioned last iterations (measured: LP 7466 of the
- *   benchmark batch needs 60 iterations instead of 16).  With a refresh every 6 iterations all 65536 generator LPs
- *   of the frozen table converge, 65535 of them in exactly the table's iteration count and one in one more, objectives
- *   within 3.2e-9 (tools/scan_batch_gpu.py --refresh=6, profiles/r2_scan_65536_refresh6.txt); a period of 3 (the
- *   default until late in round 2) costs twice the from-scratch passes over A for the same parity.
+ *   every refresh_every-th iteration (default 12; 0 = only at the end).  The recurrences drift from the true
+ *   residuals in the ill-conditioned last iterations (round 1, before an LP's residuals were REPLACED by the
+ *   from-scratch values whenever it was checked: LP 7466 of the benchmark batch needed 60 iterations instead of 16
+ *   without a periodic refresh).  Measured on all 65536 generator LPs of the frozen table with periods 6, 9, 12 and
+ *   18: every LP converges, 65535 in exactly the table's iteration count and one in one more, objectives within
+ *   4.1e-9 - the same as with the period of 3 that was the default until late in round 2 and cost four from-scratch
+ *   passes over A more per solve (tools/scan_batch_gpu.py --refresh=N, profiles/r2_scan_65536_refresh*.txt).  12 keeps
+ *   one refresh just before the ill-conditioned phase of a 15-19 iteration solve.
  * three_pass = 0: six passes, every residual from scratch in every iteration, exactly as main.py:725-751 orders it.
  * Process-wide; for A/B measurements and parity tests. */
 int ipm_batched_set_variant(int three_pass, int refresh_every);

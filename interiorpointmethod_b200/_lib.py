@@ -13,7 +13,7 @@ IPM_OK = 0
 ERRORS = {-1: "IPM_ERR_CUDA", -2: "IPM_ERR_ARG", -3: "IPM_ERR_SHAPE", -4: "IPM_ERR_STATE", -5: "IPM_ERR_NOMEM"}
 STATUS = {0: "converged", 1: "max_iter", 2: "nan"}
 BOPT_REFINE, BOPT_STRIP_TMA, BOPT_HANDOFF, BOPT_SYRK_RHS = 1, 2, 3, 4      # ipm_batched_set_option
-REFRESH_DEFAULT = 6      # ipm_batched_set_variant: default period of the from-scratch residual check
+REFRESH_DEFAULT = 12     # ipm_batched_set_variant: default period of the from-scratch residual check
 
 # every symbol include/ipm_b200.h declares: name -> (restype, argtypes)
 _dp = POINTER(c_double)

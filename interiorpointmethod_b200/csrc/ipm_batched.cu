@@ -98,7 +98,7 @@ Profiler g_prof;
 // start of every solve, atomics so that setting them from another thread is not a data race.
 struct BatchedOptions {
     std::atomic<int> fused{1};          // 0 forces the literal six-pass iteration (tests, A/B timing)
-    std::atomic<int> fresh_every{6};    // four-pass path: residuals from scratch every 6th iteration (ipm_b200.h)
+    std::atomic<int> fresh_every{12};   // four-pass path: residuals from scratch every 12th iteration (ipm_b200.h)
     std::atomic<int> refine{1};         // conditional refinement of the corrector (kbf_dir / kb_dir)
     std::atomic<int> syrk_rhs{1};       // four-pass path: predictor right-hand side formed by the SYRK's diagonal tiles
     std::atomic<int> strip_tma{1};      // four-pass path: strips of A through a tensor map (1) or a strip-major copy (0)
