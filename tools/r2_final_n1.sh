@@ -2,7 +2,7 @@
 # Round 2 final records on one B200: bench (both arms), launch list of the bench command, ncu --set full of the step's kernels.
 set -u
 export PYTHONPATH=$PWD
-O=gpurun_out/r2c41; mkdir -p $O
+O=gpurun_out/r2c48; mkdir -p $O
 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err; echo "bench rc=$?" | tee -a $O/summary.txt
 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_reference.json 2> $O/bench_reference.err; echo "bench ref rc=$?" | tee -a $O/summary.txt
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $O/bench_launches.csv python bench.py --steps 1 --warmup 3 > $O/ncu_bench_launches.log 2>&1; echo "launch list rc=$?" | tee -a $O/summary.txt
