@@ -169,6 +169,14 @@ int ipm_update(ipm_handle *h, double alpha_p, double alpha_d);
  * ipm_solve_spd: z = M^-1 rhs by the safeguarded Cholesky (solve_linear on main.py:226's matrix, main.py:176-182). */
 int ipm_op_ratio_test(int device_ordinal, int n, const double *x, const double *dx, const double *s,
                       const double *ds, double eta, double alpha[2]);
+/* step_size (main.py:325-547) = predicted_stepsize_lb_ub (main.py:550-559) / full_stepsize_lb_ub (main.py:629-660): the
+ * ratio test with simple bounds lb <= x <= ub kept implicit (either may be NULL: x >= 0 only on that side, the four
+ * cases of the reference).  eta <= 0: predictor step lengths; eta > 0 (0.91 in the reference): corrector,
+ * min(eta * ratio, 1).  The reference's quirks are kept: an empty index set gives 1 BEFORE the eta scaling where the
+ * reference does so, and the corrector without bounds returns alpha_dual = 1 (main.py:449-454 reads an unbound name
+ * and swallows the error).  alpha = { alpha_primal, alpha_dual }. */
+int ipm_op_step_size_bounded(int device_ordinal, int n, const double *x, const double *dx, const double *s,
+                             const double *ds, const double *lb, const double *ub, double eta, double alpha[2]);
 int ipm_op_sigma(int device_ordinal, int n, const double *x, const double *s, const double *dx_aff,
                  const double *ds_aff, double out[3]);
 int ipm_op_update(int device_ordinal, int m, int n, double *x, double *y, double *s, const double *dx,

@@ -50,6 +50,8 @@ SYMBOLS = {
     "ipm_sigma": (c_int, [c_void_p, c_void_p]),
     "ipm_update": (c_int, [c_void_p, c_double, c_double]),
     "ipm_op_ratio_test": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_void_p]),
+    "ipm_op_step_size_bounded": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double,
+                                 c_void_p]),
     "ipm_op_sigma": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ipm_op_update": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double,
                               c_double]),

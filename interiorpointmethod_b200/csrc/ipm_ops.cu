@@ -30,6 +30,44 @@ __global__ void k_ratio_pair(const double* x, const double* dx, const double* s,
     }
 }
 
+// Bounded-variable ratio test (step_size, main.py:325-547): three minima and whether each set is empty
+//   neg : min over dx_i < 0 of (lo_i - x_i)/dx_i   (lo = lb, or 0 when lb is null)
+//   pos : min over dx_i > 0 of (ub_i - x_i)/dx_i   (only with ub)
+//   dual: min over ds_i < 0 of -s_i/ds_i
+// out[0..2] = minima (+inf when empty), out[3..5] = 1.0 where the set is not empty (the reference distinguishes an empty
+// set from one whose ratios are all infinite: `min(...) if any(i) else 1`).
+__global__ void k_ratio_bounded(const double* x, const double* dx, const double* s, const double* ds, const double* lb,
+                                const double* ub, int n, double* out, double* partials, unsigned* counter) {
+    __shared__ double sh[32];
+    const double inf = red_identity<RED_MIN>();
+    double mn[3] = {inf, inf, inf};
+    double any[3] = {0.0, 0.0, 0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double dxi = dx[i], dsi = ds[i], xi = x[i];
+        if (dxi < 0.0) {
+            const double lo = lb ? lb[i] : 0.0;
+            mn[0] = fmin(mn[0], (lo - xi) / dxi);
+            any[0] = 1.0;
+        }
+        if (ub && dxi > 0.0) {
+            mn[1] = fmin(mn[1], (ub[i] - xi) / dxi);
+            any[1] = 1.0;
+        }
+        if (dsi < 0.0) {
+            mn[2] = fmin(mn[2], -s[i] / dsi);
+            any[2] = 1.0;
+        }
+    }
+    double tot[3];
+    if (grid_reduce<3, RED_MIN, RED_MIN, RED_MIN>(mn, partials, counter, sh, tot) && threadIdx.x == 0) {
+        out[0] = tot[0]; out[1] = tot[1]; out[2] = tot[2];
+    }
+    __syncthreads();
+    if (grid_reduce<3, RED_MAX, RED_MAX, RED_MAX>(any, partials + 3 * VEC_MAX_BLOCKS, counter + 1, sh, tot) && threadIdx.x == 0) {
+        out[3] = tot[0]; out[4] = tot[1]; out[5] = tot[2];
+    }
+}
+
 struct Scratch {
     std::vector<void*> ptrs;
     ~Scratch() { for (void* p : ptrs) cudaFree(p); }
@@ -76,6 +114,52 @@ int ipm_op_ratio_test(int device_ordinal, int n, const double* x, const double* 
     // eta <= 0: predicted_stepsize (main.py:305-322); eta > 0: full_stepsize min(1, eta*min(...)) (main.py:616-623)
     alpha[0] = eta > 0.0 ? fmin(1.0, eta * h[0]) : h[0];
     alpha[1] = eta > 0.0 ? fmin(1.0, eta * h[1]) : h[1];
+    return IPM_OK;
+}
+
+int ipm_op_step_size_bounded(int device_ordinal, int n, const double* x, const double* dx, const double* s,
+                             const double* ds, const double* lb, const double* ub, double eta, double alpha[2]) {
+    if (!x || !dx || !s || !ds || !alpha) return IPM_ERR_ARG;
+    if (n <= 0) return IPM_ERR_SHAPE;
+    IPM_CUDA_OK(cudaSetDevice(device_ordinal));
+    Scratch sc;
+    double *dxv, *ddx, *dsv, *dds, *dlb = nullptr, *dub = nullptr, *out, *partials;
+    unsigned* counter;
+    IPM_TRY(sc.up(&dxv, x, n)); IPM_TRY(sc.up(&ddx, dx, n)); IPM_TRY(sc.up(&dsv, s, n)); IPM_TRY(sc.up(&dds, ds, n));
+    if (lb) IPM_TRY(sc.up(&dlb, lb, n));
+    if (ub) IPM_TRY(sc.up(&dub, ub, n));
+    IPM_TRY(sc.dev(&out, 6));
+    IPM_TRY(sc.dev(&partials, (size_t)VEC_MAX_BLOCKS * 6));
+    IPM_TRY(sc.dev(&counter, 2));
+    IPM_CUDA_OK(cudaMemset(counter, 0, 2 * sizeof(unsigned)));
+    k_ratio_bounded<<<vec_grid(n), VEC_NT>>>(dxv, ddx, dsv, dds, dlb, dub, n, out, partials, counter);
+    count_launch();
+    IPM_TRY(launch_check());
+    double h[6];
+    IPM_CUDA_OK(cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost));
+    // The case split of main.py:325-547, quirks included.  `one` = `min(np.append(ratios, 1)) if any else 1`,
+    // `raw` = `min(ratios) if any else 1` (an all-infinite set stays infinite, an empty one gives 1).
+    const bool corr = eta > 0.0;
+    auto one = [&](int k) { return h[3 + k] > 0.5 ? fmin(h[k], 1.0) : 1.0; };
+    auto raw = [&](int k) { return h[3 + k] > 0.5 ? h[k] : 1.0; };
+    double ap, ad;
+    if (!lb && !ub) {                       // main.py:328-341 (predictor), 441-455 (corrector)
+        ap = corr ? fmin(1.0, eta * one(0)) : one(0);
+        // corrector: the reference tests `delta_s_aff < 0` there, a name that is not bound in that branch; the bare
+        // `except:` turns the error into alpha_dual = 1 (main.py:449-454)
+        ad = corr ? 1.0 : one(2);
+    } else if (!lb) {                       // 0 <= x <= ub: main.py:342-383, 456-493
+        ap = corr ? fmin(fmin(eta * raw(0), eta * raw(1)), 1.0) : fmin(fmin(raw(0), raw(1)), 1.0);
+        ad = corr ? fmin(eta * raw(2), 1.0) : fmin(raw(2), 1.0);
+    } else if (!ub) {                       // lb <= x: main.py:384-413, 494-522 (only dx < 0 can hit a bound)
+        ap = corr ? fmin(eta * raw(0), 1.0) : fmin(raw(0), 1.0);
+        ad = corr ? fmin(eta * raw(2), 1.0) : fmin(raw(2), 1.0);
+    } else {                                // lb <= x <= ub: main.py:414-438, 523-547
+        ap = corr ? fmin(fmin(eta * one(1), eta * one(0)), 1.0) : fmin(fmin(one(1), one(0)), 1.0);
+        ad = corr ? fmin(eta * one(2), 1.0) : one(2);
+    }
+    alpha[0] = ap;
+    alpha[1] = ad;
     return IPM_OK;
 }
 

@@ -383,6 +383,43 @@ def full_stepsize(x, y, s, delta_x, delta_y, delta_s, delta_x_aff=None, delta_y_
     return _ratio(x, delta_x, s, delta_s, ETA, device)
 
 
+def step_size(x, y, s, delta_aff=None, delta=None, lb=None, ub=None, device: int = 0):
+    """main.py:325-547: the ratio test with simple bounds kept implicit, `lb <= x <= ub` with either side optional
+    (None: only x >= 0 on the lower side, no upper side).  `delta_aff=(dx, dy, ds)`: predictor step lengths;
+    `delta=(dx, dy, ds)`: corrector step lengths min(0.91 * ratio, 1).  Returns (alpha_primal, alpha_dual), or None when
+    neither direction is given, like the reference.  The reference's behaviour is kept case by case, including
+    alpha_dual = 1 for the corrector without bounds (main.py:449-454)."""
+    if delta_aff is not None:
+        d, eta = delta_aff, 0.0
+    elif delta is not None:
+        d, eta = delta, ETA
+    else:
+        return None
+    lib = _lib.load()
+    xv, dxv, sv, dsv = _f64(x), _f64(d[0]), _f64(s), _f64(d[2])
+    lbv = None if lb is None else _f64(lb)
+    ubv = None if ub is None else _f64(ub)
+    if xv.size != dxv.size or sv.size != dsv.size or xv.size != sv.size or \
+            (lbv is not None and lbv.size != xv.size) or (ubv is not None and ubv.size != xv.size):
+        raise ValueError("step_size: x, s, the direction and the bounds must have the same length")
+    out = np.empty(2)
+    _lib.check(lib.ipm_op_step_size_bounded(int(device), xv.size, _ptr(xv), _ptr(dxv), _ptr(sv), _ptr(dsv),
+                                            None if lbv is None else _ptr(lbv), None if ubv is None else _ptr(ubv),
+                                            float(eta), _ptr(out)), None, "ipm_op_step_size_bounded")
+    return float(out[0]), float(out[1])
+
+
+def predicted_stepsize_lb_ub(delta_x_aff, delta_y_aff, delta_s_aff, x, s, lb, ub, device: int = 0):
+    """main.py:550-559."""
+    return step_size(x=x, y=None, s=s, delta_aff=(delta_x_aff, delta_y_aff, delta_s_aff), lb=lb, ub=ub, device=device)
+
+
+def full_stepsize_lb_ub(x, y, s, delta_x, delta_y, delta_s, delta_x_aff, delta_y_aff, delta_s_aff, lb, ub,
+                        device: int = 0):
+    """main.py:629-660."""
+    return step_size(x, y, s, delta=(delta_x, delta_y, delta_s), lb=lb, ub=ub, device=device)
+
+
 def _ratio(x, dx, s, ds, eta, device):
     lib = _lib.load()
     xv, dxv, sv, dsv = _f64(x), _f64(dx), _f64(s), _f64(ds)

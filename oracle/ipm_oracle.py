@@ -309,6 +309,41 @@ def full_stepsize(x, s, dx, ds, eta=ETA):
     return min(1.0, eta * ratio_test(x, dx)), min(1.0, eta * ratio_test(s, ds))
 
 
+def step_size_bounded(x, s, dx, ds, lb=None, ub=None, corrector=False, eta=ETA):
+    """step_size (main.py:325-547) restated case by case: the ratio test with bounds lb <= x <= ub kept implicit.
+    `one(...)` = `min(np.append(r, 1)) if any else 1`, `raw(...)` = `min(r) if any else 1` - the reference uses one or the
+    other depending on the case, and scales by eta before or after.  Corrector without bounds: alpha_dual = 1 (the
+    reference reads the unbound name delta_s_aff at main.py:449 and its bare `except:` returns 1)."""
+    x, s, dx, ds = (np.asarray(v, dtype=float).ravel() for v in (x, s, dx, ds))
+    lo = None if lb is None else np.asarray(lb, dtype=float).ravel()
+    up = None if ub is None else np.asarray(ub, dtype=float).ravel()
+
+    def ratios(num, den, mask):
+        with np.errstate(all="ignore"):
+            return num[mask] / den[mask]
+
+    neg, pos, dual = dx < 0, dx > 0, ds < 0
+    r_neg = ratios((lo - x) if lo is not None else -x, dx, neg)
+    r_pos = ratios(up - x, dx, pos) if up is not None else np.empty(0)
+    r_dual = ratios(-s, ds, dual)
+    one = lambda r: float(min(np.min(r), 1.0)) if r.size else 1.0       # noqa: E731
+    raw = lambda r: float(np.min(r)) if r.size else 1.0                  # noqa: E731
+    e = eta if corrector else 1.0
+    if lo is None and up is None:
+        ap = min(1.0, eta * one(r_neg)) if corrector else one(r_neg)
+        ad = 1.0 if corrector else one(r_dual)
+    elif lo is None:
+        ap = min(e * raw(r_neg), e * raw(r_pos), 1.0)
+        ad = min(e * raw(r_dual), 1.0)
+    elif up is None:
+        ap = min(e * raw(r_neg), 1.0)
+        ad = min(e * raw(r_dual), 1.0)
+    else:
+        ap = min(e * one(r_pos), e * one(r_neg), 1.0)
+        ad = min(e * one(r_dual), 1.0) if corrector else one(r_dual)
+    return ap, ad
+
+
 def objective(x, c):
     """Python `sum` over rows = sequential left-to-right add (main.py:815)."""
     acc = 0.0
