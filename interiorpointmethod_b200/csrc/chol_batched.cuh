@@ -132,7 +132,7 @@ static __device__ __forceinline__ void d_kb_chol(const CholBatchedArgs& a) {
     double* Ps = Bs + 32 * KBC_LDB;         // [m-32][33] rows below the diagonal block
     __shared__ double sh[32];
     __shared__ double dg[32];               // 1 / diagonal of L_JJ
-    __shared__ double colb[32];             // column j of L_JJ while it is being folded into the rows
+    __shared__ __align__(16) double colb[64];   // column j of L_JJ while it is being folded into the rows (two buffers)
     __shared__ double s_maxdiag;
     __shared__ int s_nfix;
     const int lp = blockIdx.x;
@@ -217,6 +217,27 @@ static __device__ __forceinline__ void d_kb_chol(const CholBatchedArgs& a) {
         }
     };
 
+    // Panel J goes back to global memory from the factor warp alone (128-bit copies, two rows per instruction),
+    // while the update warps apply the K = J term: the store is off the chain of the panel step (it was 15 % of it
+    // with all threads storing before the K = J term).  Needs 16-byte aligned rows (guaranteed by the entry points;
+    // a diagonal block of a larger matrix at an odd offset takes the all-threads path).
+    const bool fw_store = !(ldm & 1) && !(reinterpret_cast<uintptr_t>(Mb) & 15);
+    auto store_by_factor_warp = [&](int j0, int rows, int nb) {
+        const int nrows1 = rows - 32;                                // rows below the block exist only when nb == 32
+        const int half = lane >> 4, c2 = 2 * (lane & 15);
+        double* dstp = Mb + (size_t)(j0 + 32 + half) * ldm + j0 + c2;
+        const double* srcp = Ps + (size_t)half * KBC_LD + c2;
+#pragma unroll 8
+        for (int r = half; r < nrows1; r += 2) {
+            *reinterpret_cast<double2*>(dstp) = *reinterpret_cast<const double2*>(srcp);
+            dstp += 2 * ldm;
+            srcp += 2 * KBC_LD;
+        }
+        const int nd = rows < 32 ? rows : 32;
+        for (int pr = 0; pr < nd; ++pr)
+            if (lane <= pr && lane < nb) Mb[(size_t)(j0 + pr) * ldm + j0 + lane] = D[pr * KBC_LD + lane];
+    };
+
     if (warp == 0) {
         // =================================================================== FACTOR warp
         for (int j0 = 0; j0 < m; j0 += 32) {
@@ -227,6 +248,11 @@ static __device__ __forceinline__ void d_kb_chol(const CholBatchedArgs& a) {
                 double arow[32];
 #pragma unroll
                 for (int c = 0; c < 32; ++c) arow[c] = D[lane * KBC_LD + c];
+                // The lane's own diagonal entry lives in a register of its own: its update needs no value of another
+                // lane (l_ij of this lane, squared), so the next pivot is ready one multiply-add after l_ij - the trip
+                // of column j through shared memory (colb) is off the pivot-to-pivot chain.  Same operations on the
+                // same values as the update through colb: bitwise the same block.
+                double mydiag = D[lane * KBC_LD + lane];
                 int nfix = 0;
                 double my_inv = 1.0;
                 const bool masked = a.dep != nullptr && a.dep_mode == 1;
@@ -235,18 +261,24 @@ static __device__ __forceinline__ void d_kb_chol(const CholBatchedArgs& a) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     if (j < nb) {
-                        double p = __shfl_sync(0xffffffffu, arow[j], j);
+                        double p = __shfl_sync(0xffffffffu, mydiag, j);
                         const bool bad = !(p > thresh) || ((forced_bits >> j) & 1u);
                         if (bad) p = kPivotBig;
                         const double inv = rsqrt(p);
                         const double lij = (lane == j) ? p * inv : arow[j] * inv;
+                        mydiag = fma(-lij, lij, mydiag);                 // matters for lanes > j only
                         if (lane == j) { my_inv = inv; nfix += bad ? 1 : 0; my_bad = bad; }
                         arow[j] = lij;
-                        colb[lane] = lij;
+                        double* cb = colb + (j & 1) * 32;                // two buffers: one warp barrier per column
+                        cb[lane] = lij;
                         __syncwarp();
+                        const double2* cb2 = reinterpret_cast<const double2*>(cb);
 #pragma unroll
-                        for (int k = j + 1; k < 32; ++k) arow[k] = fma(-lij, colb[k], arow[k]);   // k > lane unused
-                        __syncwarp();
+                        for (int k2 = (j + 1) >> 1; k2 < 16; ++k2) {     // k > lane unused
+                            const double2 v = cb2[k2];
+                            if (2 * k2 > j) arow[2 * k2] = fma(-lij, v.x, arow[2 * k2]);
+                            arow[2 * k2 + 1] = fma(-lij, v.y, arow[2 * k2 + 1]);
+                        }
                     }
                 }
 #pragma unroll
@@ -268,7 +300,8 @@ static __device__ __forceinline__ void d_kb_chol(const CholBatchedArgs& a) {
             phase_trsm(nrows1);
             __syncthreads();                                       // (S3)
             KBC_T(3);
-            phase_store(j0, rows, nb);
+            if (fw_store) store_by_factor_warp(j0, rows, nb);
+            else phase_store(j0, rows, nb);
             __syncthreads();                                       // (S4)
             __syncthreads();                                       // (S5)
             KBC_T(4);
@@ -346,7 +379,7 @@ static __device__ __forceinline__ void d_kb_chol(const CholBatchedArgs& a) {
             phase_trsm(nrows1);
             __syncthreads();                                       // (S3) panel J final in shared memory
             KBC_T(3);
-            phase_store(j0, rows, nb);
+            if (!fw_store) phase_store(j0, rows, nb);
             KBC_T(4);
             if (nrows1 > 0) {
                 // K = J term of panel J+1 straight from shared memory
