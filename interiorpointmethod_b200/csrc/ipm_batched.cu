@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(KB_NT, (NPL <= 8) ? 2 : 1) kb_residual(const B
     const int flag = a.active[lp];
     if (flag == 0) return;
     if (CAND && flag == 1) {
-        if (threadIdx.x == 0) atomicAdd(a.n_active, 1u);
+        if (threadIdx.x == 0) a.act_list[atomicAdd(a.n_active, 1u)] = lp;
         return;
     }
     const int m = a.m, n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(KB_NT, (NPL <= 8) ? 2 : 1) kb_residual(const B
         const bool cont = (a.tol * (1.0 + scal[S_NB]) < nrb) || (a.tol * (1.0 + scal[S_NC]) < nrc) || (a.tol < xs);
         scal[S_CONT] = cont ? 1.0 : 0.0;
         const bool go = cont && a.iters[lp] < a.max_iter;
-        if (go) atomicAdd(a.n_active, 1u);
+        if (go) a.act_list[atomicAdd(a.n_active, 1u)] = lp;
         a.active[lp] = go ? 1 : 0;
     }
 }
@@ -540,7 +540,7 @@ int64_t ws_bytes(int B, int m, int n) {
     const int64_t ldm = round_up(m, 16);
     int64_t doubles = (int64_t)B * (10 * (int64_t)n + 4 * (int64_t)m + S_COUNT) + (int64_t)B * m * ldm + at_doubles(B, m, n) +
                       (int64_t)ka_slots(B, m, n) * ka_work_doubles(m, n);
-    int64_t bytes = doubles * 8 + (int64_t)B * 3 * sizeof(int) + 256 + 1024;
+    int64_t bytes = doubles * 8 + (int64_t)B * 4 * sizeof(int) + 256 + 1024;
     return round_up(bytes, 256);
 }
 
@@ -560,9 +560,11 @@ void carve(Workspace& w, void* base, int B, int m, int n) {
     w.a.active = ip; ip += B;
     w.a.iters = ip; ip += B;
     w.a.handoff_list = ip; ip += B;
+    w.a.act_list = ip; ip += B;
     uintptr_t u = (reinterpret_cast<uintptr_t>(ip) + 63) & ~(uintptr_t)63;
     w.a.n_active = reinterpret_cast<unsigned*>(u);          // [0], [16]: the two check slots; [32]: hand-off count
     w.a.n_handoff = w.a.n_active + 32;
+    w.a.kf_ctr = w.a.n_active + 48;                         // [48], [49]: work counter of the direction kernels
     w.a.m = m; w.a.n = n;
 }
 
@@ -580,15 +582,16 @@ struct Arrival {
 template <int SRC>
 void launch_kbf_dir_src(int kind, int pass, const BatchArgs& a, const CUtensorMap& tm, int B, int m, cudaStream_t st) {
     const size_t sm = kf_smem_bytes(m, a.n);
+    const int grid = std::min(B, kNumSMs);        // persistent: one CTA per SM, LPs from the work counter a.kf_ctr
     switch (kf_nrp(m) * 2 + kind) {
-        case 2: kbf_dir<0, 1, SRC><<<B, KF_NTT, sm, st>>>(a, pass, tm); break;
-        case 3: kbf_dir<1, 1, SRC><<<B, KF_NTT, sm, st>>>(a, pass, tm); break;
-        case 4: kbf_dir<0, 2, SRC><<<B, KF_NTT, sm, st>>>(a, pass, tm); break;
-        case 5: kbf_dir<1, 2, SRC><<<B, KF_NTT, sm, st>>>(a, pass, tm); break;
-        case 8: kbf_dir<0, 4, SRC><<<B, KF_NTT, sm, st>>>(a, pass, tm); break;
-        case 9: kbf_dir<1, 4, SRC><<<B, KF_NTT, sm, st>>>(a, pass, tm); break;
-        case 16: kbf_dir<0, 8, SRC><<<B, KF_NTT, sm, st>>>(a, pass, tm); break;
-        default: kbf_dir<1, 8, SRC><<<B, KF_NTT, sm, st>>>(a, pass, tm); break;
+        case 2: kbf_dir<0, 1, SRC><<<grid, KF_NTT, sm, st>>>(a, pass, B, tm); break;
+        case 3: kbf_dir<1, 1, SRC><<<grid, KF_NTT, sm, st>>>(a, pass, B, tm); break;
+        case 4: kbf_dir<0, 2, SRC><<<grid, KF_NTT, sm, st>>>(a, pass, B, tm); break;
+        case 5: kbf_dir<1, 2, SRC><<<grid, KF_NTT, sm, st>>>(a, pass, B, tm); break;
+        case 8: kbf_dir<0, 4, SRC><<<grid, KF_NTT, sm, st>>>(a, pass, B, tm); break;
+        case 9: kbf_dir<1, 4, SRC><<<grid, KF_NTT, sm, st>>>(a, pass, B, tm); break;
+        case 16: kbf_dir<0, 8, SRC><<<grid, KF_NTT, sm, st>>>(a, pass, B, tm); break;
+        default: kbf_dir<1, 8, SRC><<<grid, KF_NTT, sm, st>>>(a, pass, B, tm); break;
     }
 }
 void launch_kbf_dir(int kind, int pass, bool tma, const BatchArgs& a, const CUtensorMap& tm, int B, int m, cudaStream_t st) {
@@ -632,6 +635,7 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
     a.refine = refine ? g_opt.refine.load() : 0;
     a.handoff = (refine && g_opt.handoff.load() != 0 && ka_slots(B, m, n) > 0) ? g_opt.handoff.load() : 0;
     IPM_CUDA_OK(cudaMemsetAsync(a.n_handoff, 0, sizeof(unsigned), st));
+    IPM_CUDA_OK(cudaMemsetAsync(a.kf_ctr, 0, 2 * sizeof(unsigned), st));
     {
         IPM_TRY(ensure_dyn_smem(kb_residual<NPL, false>, 131072 + 8192));
         IPM_TRY(ensure_dyn_smem(kb_residual<NPL, true>, 131072 + 8192));
@@ -647,7 +651,13 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
     memset(&tmapA, 0, sizeof(tmapA));
     if (tma) IPM_TRY(kf_make_strip_tmap(&tmapA, a.A, B, m, n, 32 * kf_nrp(m)));
     IPM_TRY(debug_check("before the first launch (stale error)", st));
+    // Every per-LP kernel of the loop takes LP = block index and skips LPs that are not active.  With host buffers the LPs
+    // join in index order while their copies land, so the grids cover the joined prefix only: during the ramp an
+    // iteration on the first few hundred LPs does not pay for thousands of CTAs that start only to find a zero flag
+    // (eleven launches per iteration, 28-55 waves each).
+    int Bg = 0;
     auto join = [&](int lp0, int cnt) {             // LPs lp0 .. lp0+cnt-1 enter the loop
+        Bg = std::max(Bg, lp0 + cnt);
         kb_init<<<cnt, 256, 0, st>>>(a, fused ? 2 : 1, lp0);
         count_launch();
         if (fused && !tma) {
@@ -739,8 +749,8 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
     const size_t trsv_smem = std::max(trsv_batched_inv_smem(m), trsv_pad_kb * 1024);
     if (trsv_pad_kb) IPM_TRY(ensure_dyn_smem(k_trsv_batched_inv, std::max(trsv_batched_inv_smem(32 * TRSVI_MAX_BLK), trsv_pad_kb * 1024)));
     auto launch_trsv = [&](const TrsvBatchedArgs& t) {
-        if (small_m) k_trsv_batched_inv<<<B, TRSVB_NT, trsv_smem, st>>>(t);
-        else k_trsv_batched<<<B, TRSVB_NT, trsv_batched_smem(m), st>>>(t);
+        if (small_m) k_trsv_batched_inv<<<Bg, TRSVB_NT, trsv_smem, st>>>(t);
+        else k_trsv_batched<<<Bg, TRSVB_NT, trsv_batched_smem(m), st>>>(t);
         count_launch();
     };
     for (;; ++it) {
@@ -756,8 +766,8 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
         a.n_active = nact_base + slot * 16;
         IPM_CUDA_OK(cudaMemsetAsync(a.n_active, 0, sizeof(unsigned), st));
         g_prof.segment(st);
-        if (fused) kb_residual<NPL, true><<<B, KB_NT, smem_res, st>>>(a);
-        else kb_residual<NPL, false><<<B, KB_NT, smem_res, st>>>(a);
+        if (fused) kb_residual<NPL, true><<<Bg, KB_NT, smem_res, st>>>(a);
+        else kb_residual<NPL, false><<<Bg, KB_NT, smem_res, st>>>(a);
         count_launch();
         IPM_TRY(debug_check("kb_init / kb_residual", st));
         g_prof.end_phase(PH_RESID, st);
@@ -797,10 +807,10 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
             g.max_ctas = (busy > 0 && busy < kNumSMs / 2) ? kNumSMs - busy : 0;
         }
         if (syrk_rhs) {
-            kb_wvec<<<B, 256, 0, st>>>(a, a.dxc);
+            kb_wvec<<<Bg, 256, 0, st>>>(a, a.dxc);
             count_launch();
         }
-        IPM_TRY((dmma_syrk_auto<0>(g, B, st)));
+        IPM_TRY((dmma_syrk_auto<0>(g, Bg, st)));
         if (a.handoff) {
             last_syrk = ev[2 + slot];
             IPM_CUDA_OK(cudaEventRecord(last_syrk, st));
@@ -808,9 +818,9 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
         IPM_TRY(debug_check("syrk", st));
         g_prof.end_phase(PH_SYRK, st);
         if (m <= KBC_MAX_M_BIG)
-            IPM_TRY(potrf_batched_fused(w.M, w.ldm, (int64_t)m * w.ldm, m, B, a.scal, S_COUNT, tau, a.active, st));
+            IPM_TRY(potrf_batched_fused(w.M, w.ldm, (int64_t)m * w.ldm, m, Bg, a.scal, S_COUNT, tau, a.active, st));
         else
-            IPM_TRY((potrf_blocked<64, 256, 128>(w.M, w.ldm, (int64_t)m * w.ldm, m, B, a.scal, S_COUNT, tau,
+            IPM_TRY((potrf_blocked<64, 256, 128>(w.M, w.ldm, (int64_t)m * w.ldm, m, Bg, a.scal, S_COUNT, tau,
                                                  a.active, st)));
         IPM_TRY(debug_check("cholesky", st));
         g_prof.end_phase(PH_CHOL, st);
@@ -820,14 +830,14 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
         if (fused) t.out = a.dy;           // the right-hand side survives: the corrector's is built on top of it
         for (int kind = 0; kind < 2; ++kind) {
             if (!fused || (kind == 0 && !syrk_rhs)) {
-                kb_rhs<NPL><<<B, KB_NT, smem_w, st>>>(a, kind);
+                kb_rhs<NPL><<<Bg, KB_NT, smem_w, st>>>(a, kind);
                 count_launch();
             }
             IPM_TRY(debug_check("kb_rhs", st));
             launch_trsv(t);
             IPM_TRY(debug_check("trsv", st));
-            if (!fused) kb_dir<NPL><<<B, KB_NT, smem_col, st>>>(a, kind, 0);
-            else launch_kbf_dir(kind, 0, tma, a, tmapA, B, m, st);
+            if (!fused) kb_dir<NPL><<<Bg, KB_NT, smem_col, st>>>(a, kind, 0);
+            else launch_kbf_dir(kind, 0, tma, a, tmapA, Bg, m, st);
             count_launch();
             IPM_TRY(debug_check(kind ? "direction (corrector)" : "direction (predictor)", st));
         }
@@ -839,8 +849,8 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
             t2.only_flag = FLAG_REFINE; t2.out = nullptr;
             t2.v = fused ? a.rhs : a.dy;
             launch_trsv(t2);
-            if (!fused) kb_dir<NPL><<<B, KB_NT, smem_col, st>>>(a, 1, 1);
-            else launch_kbf_dir(1, 1, tma, a, tmapA, B, m, st);
+            if (!fused) kb_dir<NPL><<<Bg, KB_NT, smem_col, st>>>(a, 1, 1);
+            else launch_kbf_dir(1, 1, tma, a, tmapA, Bg, m, st);
             count_launch();
             IPM_TRY(debug_check("refinement pass", st));
         }

@@ -64,6 +64,9 @@ struct BatchArgs {
     int handoff;       // 1: an LP whose refined corrector still violates A dx = -rb leaves the loop (handoff_list)
     int* handoff_list; // [B] LP indices parked for the augmented-system kernel (kkt_dense.cuh)
     unsigned* n_handoff;
+    int* act_list;     // [B] LPs the last residual check left active, in the order their CTAs got there (n_active entries)
+    unsigned* kf_ctr;  // [2] work counter of the persistent direction kernels: next LP to hand out, CTAs that have left
+                       // (zero between launches: the last CTA to leave resets both)
 };
 // Refinement threshold: |delta| > KF_REFINE_THRESH |rb|.  Measured against the UNMODIFIED reference on 517 generator LPs
 // (CPU restatement): 1.0 -> objectives within 1.2e-8 relative, 0.3 -> 1.7e-9, 0.1 -> 1.6e-10 (iteration counts equal in all
@@ -95,8 +98,13 @@ inline size_t kf_smem_bytes(int m, int n) {
 // (box 16 columns x MR rows x 1 LP, cp.async.bulk.tensor -> UTMALDG; rows >= m and columns >= n are zero-filled by
 // the hardware), SRC = 0: from a strip-major copy of A made once per solve by kbf_repack (one untiled bulk copy per
 // strip, UBLKCP) - kept for A/B measurements, it costs a second copy of A in HBM and 4.4 ms per 8192 LPs.
+// PERSISTENT: one CTA per SM takes LPs from a work counter (a.kf_ctr) over the list of active LPs, so that (1) a lockstep iteration on a few hundred active LPs
+// does not start thousands of CTAs that only find a zero flag, and (2) the first KF_AHEAD strips of the NEXT LP are
+// requested during the last strips of the current one: the bulk copies are in flight across the epilogue (ratio
+// test, update, norms) and the next prologue, where a one-LP-per-CTA launch left HBM idle for 17 % of its time.
+// The ring position (buffer, mbarrier phases) simply continues from one LP to the next.
 template <int KIND, int NRP, int SRC>
-__global__ void __launch_bounds__(KF_NTT, 1) kbf_dir(const BatchArgs a, const int pass,
+__global__ void __launch_bounds__(KF_NTT, 1) kbf_dir(const BatchArgs a, const int pass, const int nlp,
                                                      const __grid_constant__ CUtensorMap tmapA) {
     constexpr int MR = 32 * NRP;                  // padded rows
     constexpr int SB = MR * KF_W;                 // doubles per strip buffer
@@ -104,11 +112,7 @@ __global__ void __launch_bounds__(KF_NTT, 1) kbf_dir(const BatchArgs a, const in
     __shared__ double sh[32];
     __shared__ double s_val[4];
     __shared__ __align__(8) uint64_t full[KF_NBUF], pfull[4], efull[4];
-    const int lp = blockIdx.x;
-    {
-        const int flag = a.active[lp];
-        if (pass == 0 ? (flag == 0) : (flag != FLAG_REFINE)) return;
-    }
+    __shared__ int s_next;
     const int m = a.m, n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int mr = MR;
     double* const dxo = (KIND == 0) ? a.dxa : a.dxc;       // where this pass leaves its direction
@@ -121,22 +125,19 @@ __global__ void __launch_bounds__(KF_NTT, 1) kbf_dir(const BatchArgs a, const in
     double* ev1 = part + 4 * (KF_NT / 32) * KF_W; // [4][16]
     double* ev2 = ev1 + 4 * KF_W;                 // [4][16]
     double* gsm = ev2 + 4 * KF_W;                 // [5][npad] per-column coefficients that do not depend on u
-    const double* A = a.A + (size_t)lp * m * n;
-    const size_t on = (size_t)lp * n, om = (size_t)lp * m;
-    double* scal = a.scal + (size_t)lp * S_COUNT;
     const int c = tid & (KF_W - 1), rg = tid >> 4;
     const int nstrips = (n + KF_W - 1) / KF_W;
 
     // strip s of this LP is one contiguous block of the strip-major copy: a single bulk (TMA) copy per strip,
     // completion signalled on the buffer's mbarrier
-    const double* At = (SRC == 0) ? a.At + (size_t)lp * nstrips * SB : nullptr;
     if (tid == 0) {
         for (int k = 0; k < KF_NBUF; ++k) mbar_init(full + k, 1);
         for (int k = 0; k < 4; ++k) { mbar_init(pfull + k, KF_NT / 32); mbar_init(efull + k, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    auto issue = [&](int sidx, int boff_d, int slot) {     // thread 0 only
+    auto issue = [&](int lp, int sidx, int boff_d, int slot) {     // thread 0 only
+        const double* At = (SRC == 0) ? a.At + (size_t)lp * nstrips * SB : nullptr;
         const uint32_t bar = smem_u32(full + slot);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(SB * 8)) : "memory");
         if (SRC == 0) {
@@ -150,8 +151,62 @@ __global__ void __launch_bounds__(KF_NTT, 1) kbf_dir(const BatchArgs a, const in
                          : "memory");
         }
     };
-    if (tid == 0) {
-        for (int k = 0; k < KF_AHEAD && k < nstrips; ++k) issue(k, k * SB, k);
+    // ---- work distribution (warp E, which has slack at the head of an LP).  pass 0: one entry at a time from the list
+    // of active LPs the residual check of this iteration compiled (a.act_list, *a.n_active entries): no scan, and a
+    // launch on a few LPs spreads them over the SMs.  pass 1 (refinement, about one LP in seventy): the flags are
+    // scanned, eight indices per atomic, the LPs of a group that ask for the pass are kept in a bit mask.
+    int grp_base = 0;
+    unsigned grp_mask = 0u;
+    const unsigned nact = (pass == 0) ? *a.n_active : 0u;
+    auto grab = [&]() -> int {                       // all lanes of warp E; -1: no LP left.  Blocks on two round trips.
+        if (pass == 0) {
+            int v = -1;
+            if (lane == 0) {
+                const unsigned idx = atomicAdd(a.kf_ctr, 1u);
+                if (idx < nact) v = a.act_list[idx];
+                if (v >= nlp) v = -1;
+            }
+            return __shfl_sync(0xffffffffu, v, 0);
+        }
+        for (;;) {
+            if (grp_mask) {
+                const int bit = __ffs(grp_mask) - 1;
+                grp_mask &= grp_mask - 1;
+                return grp_base + bit;
+            }
+            unsigned idx = (lane == 0) ? atomicAdd(a.kf_ctr, 8u) : 0u;
+            idx = __shfl_sync(0xffffffffu, idx, 0);
+            if (idx >= (unsigned)nlp) return -1;
+            bool want = false;
+            if (lane < 8 && (int)idx + lane < nlp) want = a.active[idx + lane] == FLAG_REFINE;
+            grp_mask = __ballot_sync(0xffffffffu, want);
+            grp_base = (int)idx;
+        }
+    };
+    // pass 0, enough strips: the two round trips of the grab are spread over the first strips of warp E's loop (atomic
+    // at strip 0, list entry read at strip 3, published at strip 6), so that nobody ever waits for them
+    const bool lazy_grab = (pass == 0) && nstrips >= 12;
+    // ---- ring state, carried from one LP to the next
+    auto nextb = [](int bo) { return (bo + SB == KF_NBUF * SB) ? 0 : bo + SB; };
+    int b_prev2 = (KF_NBUF - 2) * SB, b_prev = (KF_NBUF - 1) * SB, b_cur = 0;      // buffers of strips s-2, s-1, s
+    int slot = 0;                                 // mbarrier of strip s (= its buffer index)
+    uint32_t parity = 0;
+    uint32_t gs = 0;                              // strips this CTA has been through: position in the part / ev rings
+    bool prefetched = false;                      // the first KF_AHEAD strips of the coming LP are already on their way
+    const bool xlp = nstrips >= 12;               // (s_next must be public three strips before the end)
+    if (warp == KF_NT / 32) {
+        const int v = grab();
+        if (lane == 0) s_next = v;
+    }
+    __syncthreads();
+    int lp = s_next;
+    __syncthreads();                              // everyone has read it: warp 0 writes the next one right away
+
+    auto one_lp = [&](const int lp, int& next_lp) {
+    const size_t on = (size_t)lp * n, om = (size_t)lp * m;
+    double* scal = a.scal + (size_t)lp * S_COUNT;
+    if (tid == 0 && !prefetched) {
+        for (int k = 0; k < KF_AHEAD && k < nstrips; ++k) issue(lp, k, ((slot + k) % KF_NBUF) * SB, (slot + k) % KF_NBUF);
     }
     // pass 1 streams ddy (the in-place refinement solve left it in a.rhs); dy itself is only needed for y
     const double* dy_src = (pass == 0) ? a.dy : a.rhs;
@@ -194,9 +249,23 @@ __global__ void __launch_bounds__(KF_NTT, 1) kbf_dir(const BatchArgs a, const in
 
     if (warp == KF_NT / 32) {
         // ------------------------------------------------------------------ E: u -> dx, ds, e
+        // ... and the LP after this one -> s_next (read by thread 0 behind an efull wait, by everyone behind the
+        // barrier that ends the streaming)
+        unsigned g_idx = 0u;
+        int g_lp = -1;
+        if (!lazy_grab) {
+            const int v = grab();
+            if (lane == 0) s_next = v;
+        }
         for (int sidx = 0; sidx < nstrips; ++sidx) {
-            const int j = sidx & 3;
-            mbar_wait(pfull + j, (uint32_t)(sidx >> 2) & 1u);
+            if (lazy_grab && lane == 0) {
+                if (sidx == 0) g_idx = atomicAdd(a.kf_ctr, 1u);
+                if (sidx == 3 && g_idx < nact) g_lp = a.act_list[g_idx];
+                if (sidx == 6) s_next = (g_lp >= 0 && g_lp < nlp) ? g_lp : -1;
+            }
+            const uint32_t ge = gs + (uint32_t)sidx;
+            const int j = ge & 3;
+            mbar_wait(pfull + j, (ge >> 2) & 1u);
             // u: 16 warp partials per column, two lanes per column (8 each, pairwise), fixed order
             const double* pp = part + j * (KF_NT / 32) * KF_W + (lane >> 4) * 8 * KF_W + (lane & 15);
             const double t0 = pp[0] + pp[KF_W], t1 = pp[2 * KF_W] + pp[3 * KF_W];
@@ -229,8 +298,9 @@ __global__ void __launch_bounds__(KF_NTT, 1) kbf_dir(const BatchArgs a, const in
     } else {
         // ------------------------------------------------------------------ streaming warps
         auto row_sums = [&](int boff_d, int sidx) {
-            const int j = sidx & 3;
-            mbar_wait(efull + j, (uint32_t)(sidx >> 2) & 1u);
+            const uint32_t ge = gs + (uint32_t)sidx;
+            const int j = ge & 3;
+            mbar_wait(efull + j, (ge >> 2) & 1u);
             const double* sb = strip + boff_d + toff;
             const double f1 = ev1[j * KF_W + c], f2 = ev2[j * KF_W + c];
 #pragma unroll
@@ -241,10 +311,6 @@ __global__ void __launch_bounds__(KF_NTT, 1) kbf_dir(const BatchArgs a, const in
             }
         };
         // buffer offsets (doubles) of strips s-2, s-1, s and s+KF_AHEAD rotate through the ring
-        auto nextb = [](int bo) { return (bo + SB == KF_NBUF * SB) ? 0 : bo + SB; };
-        int b_prev2 = (KF_NBUF - 2) * SB, b_prev = (KF_NBUF - 1) * SB, b_cur = 0;
-        int slot = 0;
-        uint32_t parity = 0;
         for (int sidx = 0; sidx < nstrips; ++sidx) {
             mbar_wait(full + slot, parity);                     // strip sidx has landed
             {
@@ -258,13 +324,21 @@ __global__ void __launch_bounds__(KF_NTT, 1) kbf_dir(const BatchArgs a, const in
                 }
                 double p = p0 + p1;
                 p += __shfl_xor_sync(0xffffffffu, p, 16);       // the warp's two row groups
-                if (lane < KF_W) part[(sidx & 3) * (KF_NT / 32) * KF_W + warp * KF_W + lane] = p;
+                const int jp = (gs + (uint32_t)sidx) & 3;
+                if (lane < KF_W) part[jp * (KF_NT / 32) * KF_W + warp * KF_W + lane] = p;
                 __syncwarp();
-                if (lane == 0) mbar_arrive(pfull + (sidx & 3));
+                if (lane == 0) mbar_arrive(pfull + jp);
             }
             if (sidx >= 2) row_sums(b_prev2, sidx - 2);
             stream_bar();                                       // strip sidx-2 is no longer read by anyone
-            if (tid == 0 && sidx + KF_AHEAD < nstrips) issue(sidx + KF_AHEAD, b_prev2, (slot + KF_AHEAD) % KF_NBUF);
+            if (tid == 0) {
+                const int ns = sidx + KF_AHEAD;
+                if (ns < nstrips) issue(lp, ns, b_prev2, (slot + KF_AHEAD) % KF_NBUF);
+                else if (xlp) {
+                    const int nl = *reinterpret_cast<volatile int*>(&s_next);     // public since strip 6 (efull waits)
+                    if (nl >= 0) issue(nl, ns - nstrips, b_prev2, (slot + KF_AHEAD) % KF_NBUF);
+                }
+            }
             b_prev2 = b_prev; b_prev = b_cur; b_cur = nextb(b_cur);
             if (++slot == KF_NBUF) { slot = 0; parity ^= 1u; }
         }
@@ -272,6 +346,7 @@ __global__ void __launch_bounds__(KF_NTT, 1) kbf_dir(const BatchArgs a, const in
         row_sums(b_prev, nstrips - 1);
     }
     __syncthreads();
+    next_lp = s_next;
     // row sums: combine the 16 column lanes of every row group
 #pragma unroll
     for (int i = 0; i < NRP; ++i) {
@@ -399,6 +474,23 @@ __global__ void __launch_bounds__(KF_NTT, 1) kbf_dir(const BatchArgs a, const in
             a.iters[lp] = it;
             // stop candidates (and the iteration cap) are decided by kb_residual on residuals computed from scratch
             a.active[lp] = (!cont || it >= a.max_iter || (a.fresh_every > 0 && it % a.fresh_every == 0)) ? 2 : 1;
+        }
+    }
+    };      // one_lp
+
+    while (lp >= 0) {
+        int next_lp = -1;
+        one_lp(lp, next_lp);
+        gs += (uint32_t)nstrips;
+        prefetched = xlp && next_lp >= 0;
+        lp = next_lp;
+        __syncthreads();                          // shared memory of this LP (and s_next) is free
+    }
+    if (tid == 0) {                               // the last CTA to leave re-arms the counter for the next launch
+        const unsigned left = atomicAdd(a.kf_ctr + 1, 1u);
+        if (left == gridDim.x - 1) {
+            a.kf_ctr[0] = 0u;
+            a.kf_ctr[1] = 0u;
         }
     }
 }
