@@ -797,9 +797,18 @@ static __device__ __forceinline__ void d_trsv_batched_inv(const TrsvBatchedArgs 
     auto load_cols = [&](int I) {                                  // block row I, column tid: 32 entries
         const int i0 = I << 5;
         const int nb = (m - i0 < 32) ? (m - i0) : 32;
-        const double* col = L + (size_t)i0 * ldm + tid;
+        // (only threads tid < i0 use cv, and entries i >= nb are never read: no zero fill, no per-entry predicate on the
+        // full blocks, one pointer increment per load - the ternary per entry was 55 % of the kernel's instructions)
+        if (tid < i0) {
+            const double* col = L + (size_t)i0 * ldm + tid;
+            if (nb == 32) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) cv[i] = (tid < i0 && i < nb) ? col[(size_t)i * ldm] : 0.0;
+                for (int i = 0; i < 32; ++i) { cv[i] = *col; col += ldm; }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { cv[i] = (i < nb) ? *col : 0.0; col += ldm; }
+            }
+        }
     };
     if (nblk > 1) load_cols(nblk - 1);
     for (int I = nblk - 1; I >= 0; --I) {
