@@ -155,12 +155,25 @@ static __device__ __forceinline__ void d_kb_chol(const CholBatchedArgs& a) {
     {
         double v = red_identity<RED_MAX>();
         for (int i = tid; i < m; i += KBC_NT) v = fmax(v, Mb[(size_t)i * ldm + i]);
+        if (!(ldm & 1) && !(reinterpret_cast<uintptr_t>(Mb) & 15)) {        // aligned rows: 16 bytes per copy
 #pragma unroll 8
-        for (int idx = tid; idx < m * 32; idx += KBC_NT) {
-            const int r = idx >> 5, c = idx & 31;
-            const double val = (c < m) ? Mb[(size_t)r * ldm + c] : 0.0;
-            if (r < 32) D[r * KBC_LD + c] = val;
-            else Ps[(size_t)(r - 32) * KBC_LD + c] = val;
+            for (int idx = tid; idx < m * 16; idx += KBC_NT) {
+                const int r = idx >> 4, c = (idx & 15) * 2;
+                const double* src = Mb + (size_t)r * ldm + c;
+                double2 val = make_double2(0.0, 0.0);
+                if (c + 1 < m) val = *reinterpret_cast<const double2*>(src);
+                else if (c < m) val.x = src[0];
+                double* dst = (r < 32) ? D + r * KBC_LD + c : Ps + (size_t)(r - 32) * KBC_LD + c;
+                *reinterpret_cast<double2*>(dst) = val;
+            }
+        } else {
+#pragma unroll 8
+            for (int idx = tid; idx < m * 32; idx += KBC_NT) {
+                const int r = idx >> 5, c = idx & 31;
+                const double val = (c < m) ? Mb[(size_t)r * ldm + c] : 0.0;
+                if (r < 32) D[r * KBC_LD + c] = val;
+                else Ps[(size_t)(r - 32) * KBC_LD + c] = val;
+            }
         }
         v = block_red<RED_MAX>(v, sh);
         if (tid == 0) { s_maxdiag = v; s_nfix = 0; }
@@ -327,8 +340,15 @@ static __device__ __forceinline__ void d_kb_chol(const CholBatchedArgs& a) {
                     const int c = j1 + ni * 8 + 2 * t;
                     double v0 = 0.0, v1 = 0.0;
                     if (ok) {                        // raw loads: no arithmetic on them before the first MMA
-                        if (c < m) v0 = Mb[(size_t)r * ldm + c];
-                        if (c + 1 < m) v1 = Mb[(size_t)r * ldm + c + 1];
+                        const double* src = Mb + (size_t)r * ldm + c;
+                        if (fw_store && c + 1 < m) {
+                            const double2 v = *reinterpret_cast<const double2*>(src);
+                            v0 = v.x;
+                            v1 = v.y;
+                        } else {
+                            if (c < m) v0 = src[0];
+                            if (c + 1 < m) v1 = src[1];
+                        }
                     }
                     acc[ti][ni][0] = v0;
                     acc[ti][ni][1] = v1;
@@ -358,10 +378,21 @@ static __device__ __forceinline__ void d_kb_chol(const CholBatchedArgs& a) {
                     const int kc = (j0 - k0 < KBC_KC) ? (j0 - k0) : KBC_KC;
                     kbc_update_bar<KBC_NT>();                                  // previous chunk fully consumed
                     const int kshift = (kc == KBC_KC) ? 6 : 5;         // kc is 64 or 32 (j0 is a multiple of 32)
+                    if (fw_store) {                                    // aligned rows: 16 bytes per copy
 #pragma unroll 5
-                    for (int idx = tid - 32; idx < 32 * kc; idx += KBC_UW * 32) {
-                        const int r = idx >> kshift, k = idx & (kc - 1);
-                        Bs[r * KBC_LDB + k] = (j1 + r < m) ? Mb[(size_t)(j1 + r) * ldm + k0 + k] : 0.0;
+                        for (int idx = tid - 32; idx < 16 * kc; idx += KBC_UW * 32) {
+                            const int r = idx >> (kshift - 1), k = (idx & ((kc >> 1) - 1)) * 2;
+                            const double2 v = (j1 + r < m)
+                                                  ? *reinterpret_cast<const double2*>(Mb + (size_t)(j1 + r) * ldm + k0 + k)
+                                                  : make_double2(0.0, 0.0);
+                            *reinterpret_cast<double2*>(Bs + r * KBC_LDB + k) = v;
+                        }
+                    } else {
+#pragma unroll 5
+                        for (int idx = tid - 32; idx < 32 * kc; idx += KBC_UW * 32) {
+                            const int r = idx >> kshift, k = idx & (kc - 1);
+                            Bs[r * KBC_LDB + k] = (j1 + r < m) ? Mb[(size_t)(j1 + r) * ldm + k0 + k] : 0.0;
+                        }
                     }
                     kbc_update_bar<KBC_NT>();
                     switch (nti) {
@@ -403,10 +434,8 @@ static __device__ __forceinline__ void d_kb_chol(const CholBatchedArgs& a) {
                     if (tile >= ntile1 || pr >= nrows1) continue;
                     double* dst = (pr < 32) ? (D + pr * KBC_LD) : (Ps + (size_t)(pr - 32) * KBC_LD);
 #pragma unroll
-                    for (int ni = 0; ni < 4; ++ni) {
-                        dst[ni * 8 + 2 * t] = acc[ti][ni][0];
-                        dst[ni * 8 + 2 * t + 1] = acc[ti][ni][1];
-                    }
+                    for (int ni = 0; ni < 4; ++ni)           // (KBC_LD is even and the blocks start on 16-byte boundaries)
+                        *reinterpret_cast<double2*>(dst + ni * 8 + 2 * t) = make_double2(acc[ti][ni][0], acc[ti][ni][1]);
                 }
                 init_acc(j0 + 64);                                 // for the next panel step, ahead of its barrier
             }
