@@ -115,6 +115,29 @@ def test_three_pass_iteration_matches_six_pass(ipm, m, n, B):
     assert (np.linalg.norm(rb, axis=1) <= 1.001e-8 * (1 + np.linalg.norm(b, axis=1))).all()
 
 
+@pytest.mark.parametrize("m,n,B", [(8, 20, 300), (40, 192, 400), (64, 512, 333), (24, 40, 700)])
+def test_persistent_direction_kernels_more_lps_than_sms(ipm, m, n, B):
+    """More LPs than SMs: every CTA of the persistent direction kernels (kbf_dir) walks several LPs, so the strip ring
+    and its mbarrier phases continue across LPs, with 2 strips per LP (fewer than the three in flight), 3, 12 (the
+    first count with cross-LP prefetch and the lazy grab) and 32.  Against the 6-pass iteration, which does not use
+    those kernels; two runs of the 3-pass one must agree bit for bit (the order in which CTAs take LPs is not fixed)."""
+    from interiorpointmethod_b200 import _lib
+    from interiorpointmethod_b200.batch import solve_batched_host
+    lib = _lib.load()
+    A, b, c = ipm.synthetic_dense_batch(11, B, m, n)
+    try:
+        lib.ipm_batched_set_variant(0, 3)
+        o6, k6, s6 = solve_batched_host(A, b, c, tol=1e-8)
+    finally:
+        lib.ipm_batched_set_variant(1, _lib.REFRESH_DEFAULT)
+    o3, k3, s3 = solve_batched_host(A, b, c, tol=1e-8)
+    o3b, k3b, s3b = solve_batched_host(A, b, c, tol=1e-8)
+    assert (s6 == 0).all() and (s3 == 0).all()
+    assert np.abs(k3.astype(int) - k6.astype(int)).max() <= 1
+    assert (np.abs(o3 - o6) <= 1e-8 * np.abs(o6)).all()
+    assert (k3 == k3b).all() and (o3 == o3b).all() and (s3 == s3b).all()
+
+
 def test_three_pass_refresh_keeps_ill_conditioned_lp_on_track(ipm):
     """LP 7466 of the benchmark batch: with residuals carried by recurrence only, the 3-pass iteration needs 60
     iterations (measured on B200) where the six-pass one needs 16; the default refresh period must keep it
