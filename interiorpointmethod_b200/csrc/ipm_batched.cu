@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <chrono>
 #include <vector>
 
 #include "chol.cuh"
@@ -610,6 +611,68 @@ int kbf_configure_nrp() {
     return IPM_OK;
 }
 
+// Host-side resources of one lockstep loop - the pinned page the "still active" counters are read back into, the events
+// of the check slots, the high-priority streams of the augmented-system kernel - come from a per-device pool and go
+// back to it: cudaMallocHost / cudaFreeHost and stream creation per solve cost little most of the time and hundreds of
+// milliseconds now and then (page locking and stream creation serialise on the driver; with eight processes on one box
+// one such stall per few dozen solves made every step wait for the slowest rank: tools/block_times.py).
+constexpr int KA_STREAMS = 6;
+struct LoopRes {
+    int dev = -1;
+    unsigned* h_nact = nullptr;                 // [8] pinned
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t st_kas[KA_STREAMS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    void destroy() {
+        if (h_nact) cudaFreeHost(h_nact);
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
+        for (auto& q : st_kas) if (q) cudaStreamDestroy(q);
+        *this = LoopRes();
+    }
+};
+static std::mutex g_loopres_mu;
+static std::vector<LoopRes*> g_loopres_free[16];
+static int acquire_loopres(LoopRes** out) {
+    int dev = 0;
+    IPM_CUDA_OK(cudaGetDevice(&dev));
+    {
+        std::lock_guard<std::mutex> lk(g_loopres_mu);
+        auto& fr = g_loopres_free[dev & 15];
+        for (size_t i = 0; i < fr.size(); ++i)
+            if (fr[i]->dev == dev) { *out = fr[i]; fr.erase(fr.begin() + (long)i); return IPM_OK; }
+    }
+    LoopRes* r = new LoopRes();
+    r->dev = dev;
+    auto fail = [&](cudaError_t e) { g_last_error = cudaGetErrorString(e); r->destroy(); delete r; return IPM_ERR_CUDA; };
+    cudaError_t e = cudaMallocHost(&r->h_nact, 8 * sizeof(unsigned));
+    if (e != cudaSuccess) return fail(e);
+    for (int i = 0; i < 4; ++i)
+        if ((e = cudaEventCreateWithFlags(&r->ev[i], cudaEventDisableTiming)) != cudaSuccess) return fail(e);
+    int lo = 0, hi = 0;
+    if ((e = cudaDeviceGetStreamPriorityRange(&lo, &hi)) != cudaSuccess) return fail(e);
+    for (int i = 0; i < KA_STREAMS; ++i)
+        if ((e = cudaStreamCreateWithPriority(&r->st_kas[i], cudaStreamNonBlocking, hi)) != cudaSuccess) return fail(e);
+    *out = r;
+    return IPM_OK;
+}
+static void release_loopres(LoopRes* r, bool healthy) {
+    if (!r) return;
+    if (!healthy) { r->destroy(); delete r; return; }          // a failed solve may have left work on the streams
+    std::lock_guard<std::mutex> lk(g_loopres_mu);
+    g_loopres_free[r->dev & 15].push_back(r);
+}
+struct LoopResLease {
+    LoopRes* r = nullptr;
+    bool ok = false;
+    ~LoopResLease() { release_loopres(r, ok); }
+};
+static void drop_loopres_pool() {
+    std::lock_guard<std::mutex> lk(g_loopres_mu);
+    for (auto& fr : g_loopres_free) {
+        for (LoopRes* r : fr) { cudaSetDevice(r->dev); r->destroy(); delete r; }
+        fr.clear();
+    }
+}
+
 template <int NPL>
 int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, int* iterations_run, Arrival* arr) {
     BatchArgs& a = w.a;
@@ -689,9 +752,10 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
     // GPU never idles on the host round trip; the price is one empty iteration (every kernel skips inactive LPs)
     // after the last LP has converged.  Every LP is bounded by max_iter, so the loop is.
     unsigned* nact_base = a.n_active;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};       // [0,1]: checks; [2,3]: "SYRK of iteration it done"
-    for (int i = 0; i < 4; ++i) IPM_CUDA_OK(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
-    struct EvGuard { cudaEvent_t* e; ~EvGuard() { for (int i = 0; i < 4; ++i) if (e[i]) cudaEventDestroy(e[i]); } } ev_guard{ev};
+    LoopResLease lease;
+    IPM_TRY(acquire_loopres(&lease.r));
+    cudaEvent_t* ev = lease.r->ev;                                  // [0,1]: checks; [2,3]: "SYRK of iteration it done"
+    if (!w.h_nact) w.h_nact = lease.r->h_nact;
     cudaEvent_t last_syrk = nullptr;            // most recent SYRK enqueued on st
     int it = 0, bodies = 0;
     bool all_joined[2] = {true, true};          // per check slot: had every chunk joined when the check was enqueued?
@@ -701,12 +765,7 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
     // higher-priority stream WHILE the lockstep loop runs on: a parked LP is off the loop's books (active = 0), its
     // iterate is final, and one CTA per LP for a few milliseconds hides behind the remaining iterations.
     // (several streams: LPs are parked in different iterations, and launches on one stream would run one after the other)
-    constexpr int KA_STREAMS = 6;
-    cudaStream_t st_kas[KA_STREAMS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    struct KaGuard {
-        cudaStream_t* s;
-        ~KaGuard() { for (int i = 0; i < KA_STREAMS; ++i) if (s[i]) cudaStreamDestroy(s[i]); }
-    } ka_guard{st_kas};
+    cudaStream_t* st_kas = lease.r->st_kas;
     int ka_next_stream = 0;
     int ka_pending[KA_STREAMS] = {0, 0, 0, 0, 0, 0};      // CTAs launched on each stream and not known to have finished
     const int slots = ka_slots(B, m, n);
@@ -714,12 +773,6 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
     KktArgs kk;
     kk.A = a.A; kk.b = a.b; kk.c = a.c; kk.x = a.x; kk.s = a.s; kk.y = a.y; kk.scal = a.scal; kk.iters = a.iters;
     kk.m = m; kk.n = n; kk.tol = a.tol; kk.eta = a.eta; kk.max_iter = a.max_iter;
-    if (a.handoff) {
-        int lo = 0, hi = 0;
-        IPM_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        for (int i = 0; i < KA_STREAMS; ++i)
-            IPM_CUDA_OK(cudaStreamCreateWithPriority(&st_kas[i], cudaStreamNonBlocking, hi));
-    }
     auto ka_sync_all = [&]() -> int {
         for (int i = 0; i < KA_STREAMS; ++i) IPM_CUDA_OK(cudaStreamSynchronize(st_kas[i]));
         return IPM_OK;
@@ -753,6 +806,13 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
         else k_trsv_batched<<<Bg, TRSVB_NT, trsv_batched_smem(m), st>>>(t);
         count_launch();
     };
+    static const bool trace_host = getenv("IPM_TRACE_HOST") != nullptr;      // where the host side of one solve spends its time
+    const auto th0 = std::chrono::steady_clock::now();
+    auto since = [&](std::chrono::steady_clock::time_point t) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count();
+    };
+    double th_wait_max = 0.0, th_parked = 0.0;
+    int th_wait_it = -1;
     for (;; ++it) {
         const int slot = it & 1;
         if (arr && it > 0) {
@@ -776,10 +836,14 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
             IPM_CUDA_OK(cudaMemcpyAsync(w.h_nact + 2 + slot, a.n_handoff, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
         IPM_CUDA_OK(cudaEventRecord(ev[slot], st));
         if (it > 0) {
+            const auto tw = std::chrono::steady_clock::now();
             IPM_CUDA_OK(cudaEventSynchronize(ev[slot ^ 1]));
+            if (trace_host) { const double d = since(tw); if (d > th_wait_max) { th_wait_max = d; th_wait_it = it; } }
             const unsigned cnt = w.h_nact[slot ^ 1];
             // everything the stream did before that check has completed: LPs parked by then can start now
+            const auto tp = std::chrono::steady_clock::now();
             if (a.handoff) IPM_TRY(launch_parked((int)w.h_nact[2 + (slot ^ 1)]));
+            if (trace_host) th_parked += since(tp);
             if (cnt == 0) {
                 if (all_joined[slot ^ 1]) break;
                 if (!counted_join) {
@@ -860,9 +924,12 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
     a.n_active = nact_base;
     // ---- LPs parked late (or beyond the workspace's slots): the same kernel, now with the machine to itself
     int handed = 0;
+    const double th_loop = since(th0);
+    double th_drain = 0.0, th_ka = 0.0;
     if (a.handoff) {
         IPM_CUDA_OK(cudaMemcpyAsync(w.h_nact + 4, a.n_handoff, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
         IPM_CUDA_OK(cudaStreamSynchronize(st));
+        th_drain = since(th0) - th_loop;
         handed = (int)w.h_nact[4];
         IPM_TRY(launch_parked(handed));
         IPM_TRY(ka_sync_all());
@@ -874,8 +941,14 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
             IPM_CUDA_OK(cudaStreamSynchronize(st_kas[0]));
         }
     }
+    th_ka = since(th0) - th_loop - th_drain;
     g_last_handoffs.store(handed);
     IPM_CUDA_OK(cudaStreamSynchronize(st));
+    lease.ok = true;                            // nothing of this solve is left on the pooled streams and events
+    if (trace_host)
+        fprintf(stderr, "[ipm host trace] loop enqueued %.1f ms (longest wait for a check %.1f ms at iteration %d, launch_parked %.1f ms), "
+                        "stream drained +%.1f ms, augmented-system tail +%.1f ms, %d handed off, %d launched inside the loop\n",
+                th_loop, th_wait_max, th_wait_it, th_parked, th_drain, th_ka, handed, ka_launched);
     if (iterations_run) *iterations_run = bodies;
     return IPM_OK;
 }
@@ -1080,16 +1153,14 @@ int ipm_solve_batched_dense_d(int device_ordinal, int B, int m, int n, const dou
         IPM_CUDA_OK(cudaMalloc(&own, (size_t)ws_bytes(B, m, n)));
         work_d = own;
     }
-    unsigned* h_nact = nullptr;
     int rc = [&]() -> int {
-        IPM_CUDA_OK(cudaMallocHost(&h_nact, 8 * sizeof(unsigned)));
-        IPM_TRY(solve_on_device(B, m, n, A_d, b_d, c_d, tol, max_iter, obj_d, iters_d, status_d, x_d, work_d, h_nact,
+        // (the pinned read-back page comes from the loop's resource pool: no cudaMallocHost / cudaFreeHost per call)
+        IPM_TRY(solve_on_device(B, m, n, A_d, b_d, c_d, tol, max_iter, obj_d, iters_d, status_d, x_d, work_d, nullptr,
                                 0, iterations_run));
         IPM_CUDA_OK(cudaStreamSynchronize(0));
         return IPM_OK;
     }();
     g_prof.collect();
-    if (h_nact) cudaFreeHost(h_nact);
     if (own) cudaFree(own);
     return rc;
 }
@@ -1132,6 +1203,7 @@ static int ensure_bytes(void** p, int64_t* cap, int64_t need) {
 
 int ipm_release_cached(void) {
     for (auto& c : g_host_ctx) c.release();
+    drop_loopres_pool();
     ipm_pattern_cache_clear();
     return IPM_OK;
 }
