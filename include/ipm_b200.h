@@ -207,7 +207,9 @@ int ipm_solve_batched_dense(int device_ordinal, int B, int m, int n,
                             const double *A, const double *b, const double *c,
                             double tol, int max_iter,
                             double *obj, int *iters, int *status, double *x);
-/* Frees the device/pinned staging buffers ipm_solve_batched_dense keeps between calls. */
+/* Frees what the batched entry points keep between calls: the device/pinned staging buffers of ipm_solve_batched_dense
+ * and the per-device pool of loop resources (a pinned page, events, the streams of the hand-off kernel) both batched
+ * entry points draw from.  Not to be called while a batched solve is running on another thread. */
 int ipm_release_cached(void);
 /* Same with everything resident on `device_ordinal`; stream 0 of that device; synchronises before return.
  * work_d: scratch of ipm_batched_workspace_bytes(B,m,n) bytes or NULL (allocated internally). */
