@@ -580,35 +580,33 @@ struct Arrival {
     int next = 0;                       // first chunk that has not joined yet
 };
 
-template <int SRC>
-void launch_kbf_dir_src(int kind, int pass, const BatchArgs& a, const CUtensorMap& tm, int B, int m, cudaStream_t st) {
-    const size_t sm = kf_smem_bytes(m, a.n);
+template <int KIND, int NRP, int SRC>
+int launch_kbf_one(int pass, const BatchArgs& a, const CUtensorMap& tm, int B, int m, cudaStream_t st) {
+    const int nbuf = kf_nbuf(m, a.n);
+    const size_t sm = kf_smem_bytes(m, a.n, nbuf);
+    IPM_TRY(ensure_dyn_smem(kbf_dir<KIND, NRP, SRC>, sm));
     const int grid = std::min(B, kNumSMs);        // persistent: one CTA per SM, LPs from the work counter a.kf_ctr
+    kbf_dir<KIND, NRP, SRC><<<grid, KF_NTT, sm, st>>>(a, pass, B, nbuf, tm);
+    return IPM_OK;
+}
+template <int SRC>
+int launch_kbf_dir_src(int kind, int pass, const BatchArgs& a, const CUtensorMap& tm, int B, int m, cudaStream_t st) {
     switch (kf_nrp(m) * 2 + kind) {
-        case 2: kbf_dir<0, 1, SRC><<<grid, KF_NTT, sm, st>>>(a, pass, B, tm); break;
-        case 3: kbf_dir<1, 1, SRC><<<grid, KF_NTT, sm, st>>>(a, pass, B, tm); break;
-        case 4: kbf_dir<0, 2, SRC><<<grid, KF_NTT, sm, st>>>(a, pass, B, tm); break;
-        case 5: kbf_dir<1, 2, SRC><<<grid, KF_NTT, sm, st>>>(a, pass, B, tm); break;
-        case 8: kbf_dir<0, 4, SRC><<<grid, KF_NTT, sm, st>>>(a, pass, B, tm); break;
-        case 9: kbf_dir<1, 4, SRC><<<grid, KF_NTT, sm, st>>>(a, pass, B, tm); break;
-        case 16: kbf_dir<0, 8, SRC><<<grid, KF_NTT, sm, st>>>(a, pass, B, tm); break;
-        default: kbf_dir<1, 8, SRC><<<grid, KF_NTT, sm, st>>>(a, pass, B, tm); break;
+        case 2: return launch_kbf_one<0, 1, SRC>(pass, a, tm, B, m, st);
+        case 3: return launch_kbf_one<1, 1, SRC>(pass, a, tm, B, m, st);
+        case 4: return launch_kbf_one<0, 2, SRC>(pass, a, tm, B, m, st);
+        case 5: return launch_kbf_one<1, 2, SRC>(pass, a, tm, B, m, st);
+        case 8: return launch_kbf_one<0, 4, SRC>(pass, a, tm, B, m, st);
+        case 9: return launch_kbf_one<1, 4, SRC>(pass, a, tm, B, m, st);
+        case 16: return launch_kbf_one<0, 8, SRC>(pass, a, tm, B, m, st);
+        default: return launch_kbf_one<1, 8, SRC>(pass, a, tm, B, m, st);
     }
 }
-void launch_kbf_dir(int kind, int pass, bool tma, const BatchArgs& a, const CUtensorMap& tm, int B, int m, cudaStream_t st) {
-    if (tma) launch_kbf_dir_src<1>(kind, pass, a, tm, B, m, st);
-    else launch_kbf_dir_src<0>(kind, pass, a, tm, B, m, st);
-}
-
-template <int KIND, int NRP, int SRC>
-int kbf_configure() {
-    return ensure_dyn_smem(kbf_dir<KIND, NRP, SRC>, kf_smem_bytes(32 * NRP, 2 * KB_NT));
-}
-template <int NRP>
-int kbf_configure_nrp() {
-    IPM_TRY((kbf_configure<0, NRP, 0>())); IPM_TRY((kbf_configure<1, NRP, 0>()));
-    IPM_TRY((kbf_configure<0, NRP, 1>())); IPM_TRY((kbf_configure<1, NRP, 1>()));
-    return IPM_OK;
+// (the launch raises the kernel's dynamic shared-memory limit itself, for the instantiation and size it is about to use:
+// one map lookup, ensure_dyn_smem)
+int launch_kbf_dir(int kind, int pass, bool tma, const BatchArgs& a, const CUtensorMap& tm, int B, int m, cudaStream_t st) {
+    if (tma) return launch_kbf_dir_src<1>(kind, pass, a, tm, B, m, st);
+    return launch_kbf_dir_src<0>(kind, pass, a, tm, B, m, st);
 }
 
 // Host-side resources of one lockstep loop - the pinned page the "still active" counters are read back into, the events
@@ -703,10 +701,6 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
         IPM_TRY(ensure_dyn_smem(kb_residual<NPL, false>, 131072 + 8192));
         IPM_TRY(ensure_dyn_smem(kb_residual<NPL, true>, 131072 + 8192));
         IPM_TRY(ensure_dyn_smem(kb_dir<NPL>, 131072 + 16384));
-        // every NRP instantiation the dispatcher can pick, at the largest n check_shape admits (NRP = 1,
-        // m <= 32, needs more than 48 KB once n >= 466)
-        IPM_TRY(kbf_configure_nrp<1>()); IPM_TRY(kbf_configure_nrp<2>());
-        IPM_TRY(kbf_configure_nrp<4>()); IPM_TRY(kbf_configure_nrp<8>());
         IPM_TRY(ensure_dyn_smem(k_trsv_batched, 65536));
         IPM_TRY(ensure_dyn_smem(k_trsv_batched_inv, trsv_batched_inv_smem(32 * TRSVI_MAX_BLK)));
     }
@@ -901,7 +895,7 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
             launch_trsv(t);
             IPM_TRY(debug_check("trsv", st));
             if (!fused) kb_dir<NPL><<<Bg, KB_NT, smem_col, st>>>(a, kind, 0);
-            else launch_kbf_dir(kind, 0, tma, a, tmapA, Bg, m, st);
+            else IPM_TRY(launch_kbf_dir(kind, 0, tma, a, tmapA, Bg, m, st));
             count_launch();
             IPM_TRY(debug_check(kind ? "direction (corrector)" : "direction (predictor)", st));
         }
@@ -914,7 +908,7 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
             t2.v = fused ? a.rhs : a.dy;
             launch_trsv(t2);
             if (!fused) kb_dir<NPL><<<Bg, KB_NT, smem_col, st>>>(a, 1, 1);
-            else launch_kbf_dir(1, 1, tma, a, tmapA, Bg, m, st);
+            else IPM_TRY(launch_kbf_dir(1, 1, tma, a, tmapA, Bg, m, st));
             count_launch();
             IPM_TRY(debug_check("refinement pass", st));
         }

@@ -75,15 +75,19 @@ constexpr double KF_REFINE_THRESH = 0.1;
 constexpr int FLAG_REFINE = 3;    // active[] value between the corrector pass that asks for a refinement and the one that
                                   // applies it
 
-constexpr int KF_NBUF = 5;                  // strip buffers: row sums of s-2, s-1 (pending), column sums of s, loads ahead
-constexpr int KF_AHEAD = KF_NBUF - 2;       // strips in flight: one CTA per SM keeps 3 x 32 KB on the wire
+// Strip buffers: row sums of s-2, s-1 (pending), column sums of s, and nbuf - 2 loads ahead.  Six buffers (four strips =
+// 128 KB on the wire per SM) when they fit beside the per-column coefficients, five otherwise (m > 128 with n > 640).
+constexpr int KF_NBUF_MAX = 6;
+constexpr size_t KF_SMEM_CAP = 227 * 1024 - 2048;      // opt-in maximum per block minus the kernel's static shared memory
 
 inline int kf_nrp(int m) { return m <= 32 ? 1 : m <= 64 ? 2 : m <= 128 ? 4 : 8; }     // rows per thread
-inline size_t kf_smem_bytes(int m, int n) {
+inline size_t kf_smem_bytes(int m, int n, int nbuf) {
     const int mr = 32 * kf_nrp(m);
     const int npad = (n + KF_W - 1) / KF_W * KF_W;
-    return (size_t)(KF_NBUF * mr * KF_W + 3 * mr + 4 * (KF_NT / 32) * KF_W + 8 * KF_W + 5 * npad) * sizeof(double);
+    // (the row sums q1, q2 of the epilogue live in the buffer of the LP's last strip, which nobody reads by then)
+    return (size_t)(nbuf * mr * KF_W + mr + 4 * (KF_NT / 32) * KF_W + 8 * KF_W + 5 * npad) * sizeof(double);
 }
+inline int kf_nbuf(int m, int n) { return kf_smem_bytes(m, n, KF_NBUF_MAX) <= KF_SMEM_CAP ? KF_NBUF_MAX : KF_NBUF_MAX - 1; }
 
 #ifdef __CUDACC__
 // One CTA per SM, 17 warps.  Thread 0 keeps four strips (4 x 32 KB) in flight with bulk copies (UBLKCP) from the
@@ -104,14 +108,15 @@ inline size_t kf_smem_bytes(int m, int n) {
 // test, update, norms) and the next prologue, where a one-LP-per-CTA launch left HBM idle for 17 % of its time.
 // The ring position (buffer, mbarrier phases) simply continues from one LP to the next.
 template <int KIND, int NRP, int SRC>
-__global__ void __launch_bounds__(KF_NTT, 1) kbf_dir(const BatchArgs a, const int pass, const int nlp,
+__global__ void __launch_bounds__(KF_NTT, 1) kbf_dir(const BatchArgs a, const int pass, const int nlp, const int KF_NBUF,
                                                      const __grid_constant__ CUtensorMap tmapA) {
+    const int KF_AHEAD = KF_NBUF - 2;             // strips in flight
     constexpr int MR = 32 * NRP;                  // padded rows
     constexpr int SB = MR * KF_W;                 // doubles per strip buffer
     extern __shared__ __align__(128) double smem_kf[];        // strip buffers first: TMA destinations, 128-byte aligned
     __shared__ double sh[32];
     __shared__ double s_val[4];
-    __shared__ __align__(8) uint64_t full[KF_NBUF], pfull[4], efull[4];
+    __shared__ __align__(8) uint64_t full[KF_NBUF_MAX], pfull[4], efull[4];
     __shared__ int s_next;
     const int m = a.m, n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int mr = MR;
@@ -119,9 +124,7 @@ __global__ void __launch_bounds__(KF_NTT, 1) kbf_dir(const BatchArgs a, const in
     double* const dso = (KIND == 0) ? a.dsa : a.dsc;
     double* strip = smem_kf;                      // [KF_NBUF][MR][16]
     double* dys = strip + KF_NBUF * SB;           // [MR]   dy
-    double* q1s = dys + MR;                       // [MR]   A e1
-    double* q2s = q1s + MR;                       // [MR]   A e2 (kind 0)
-    double* part = q2s + MR;                      // [4][16 warps][16] column partial sums (ring of 4 strips)
+    double* part = dys + MR;                      // [4][16 warps][16] column partial sums (ring of 4 strips)
     double* ev1 = part + 4 * (KF_NT / 32) * KF_W; // [4][16]
     double* ev2 = ev1 + 4 * KF_W;                 // [4][16]
     double* gsm = ev2 + 4 * KF_W;                 // [5][npad] per-column coefficients that do not depend on u
@@ -187,13 +190,14 @@ __global__ void __launch_bounds__(KF_NTT, 1) kbf_dir(const BatchArgs a, const in
     // at strip 0, list entry read at strip 3, published at strip 6), so that nobody ever waits for them
     const bool lazy_grab = (pass == 0) && nstrips >= 12;
     // ---- ring state, carried from one LP to the next
-    auto nextb = [](int bo) { return (bo + SB == KF_NBUF * SB) ? 0 : bo + SB; };
+    auto nextb = [&](int bo) { return (bo + SB == KF_NBUF * SB) ? 0 : bo + SB; };
+    auto wrap = [&](int k) { return k >= KF_NBUF ? k - KF_NBUF : k; };            // k < 2 KF_NBUF
     int b_prev2 = (KF_NBUF - 2) * SB, b_prev = (KF_NBUF - 1) * SB, b_cur = 0;      // buffers of strips s-2, s-1, s
     int slot = 0;                                 // mbarrier of strip s (= its buffer index)
     uint32_t parity = 0;
     uint32_t gs = 0;                              // strips this CTA has been through: position in the part / ev rings
     bool prefetched = false;                      // the first KF_AHEAD strips of the coming LP are already on their way
-    const bool xlp = nstrips >= 12;               // (s_next must be public three strips before the end)
+    const bool xlp = nstrips >= 12;               // (s_next, out at strip 6, must be public KF_AHEAD strips before the end)
     if (warp == KF_NT / 32) {
         const int v = grab();
         if (lane == 0) s_next = v;
@@ -206,7 +210,7 @@ __global__ void __launch_bounds__(KF_NTT, 1) kbf_dir(const BatchArgs a, const in
     const size_t on = (size_t)lp * n, om = (size_t)lp * m;
     double* scal = a.scal + (size_t)lp * S_COUNT;
     if (tid == 0 && !prefetched) {
-        for (int k = 0; k < KF_AHEAD && k < nstrips; ++k) issue(lp, k, ((slot + k) % KF_NBUF) * SB, (slot + k) % KF_NBUF);
+        for (int k = 0; k < KF_AHEAD && k < nstrips; ++k) issue(lp, k, wrap(slot + k) * SB, wrap(slot + k));
     }
     // pass 1 streams ddy (the in-place refinement solve left it in a.rhs); dy itself is only needed for y
     const double* dy_src = (pass == 0) ? a.dy : a.rhs;
@@ -333,10 +337,10 @@ __global__ void __launch_bounds__(KF_NTT, 1) kbf_dir(const BatchArgs a, const in
             stream_bar();                                       // strip sidx-2 is no longer read by anyone
             if (tid == 0) {
                 const int ns = sidx + KF_AHEAD;
-                if (ns < nstrips) issue(lp, ns, b_prev2, (slot + KF_AHEAD) % KF_NBUF);
+                if (ns < nstrips) issue(lp, ns, b_prev2, wrap(slot + KF_AHEAD));
                 else if (xlp) {
                     const int nl = *reinterpret_cast<volatile int*>(&s_next);     // public since strip 6 (efull waits)
-                    if (nl >= 0) issue(nl, ns - nstrips, b_prev2, (slot + KF_AHEAD) % KF_NBUF);
+                    if (nl >= 0) issue(nl, ns - nstrips, b_prev2, wrap(slot + KF_AHEAD));
                 }
             }
             b_prev2 = b_prev; b_prev = b_cur; b_cur = nextb(b_cur);
@@ -347,6 +351,9 @@ __global__ void __launch_bounds__(KF_NTT, 1) kbf_dir(const BatchArgs a, const in
     }
     __syncthreads();
     next_lp = s_next;
+    // row sums of the whole LP: in the buffer of its last strip (free now; the next LP's first strips land in others)
+    double* const q1s = strip + (size_t)((gs + (uint32_t)nstrips - 1u) % (uint32_t)KF_NBUF) * SB;     // [MR]   A e1
+    double* const q2s = q1s + MR;                                                                  // [MR]   A e2 (kind 0)
     // row sums: combine the 16 column lanes of every row group
 #pragma unroll
     for (int i = 0; i < NRP; ++i) {
