@@ -941,7 +941,7 @@ int run_batched(Workspace& w, int B, int m, int n, double tau, cudaStream_t st, 
     lease.ok = true;                            // nothing of this solve is left on the pooled streams and events
     if (trace_host)
         fprintf(stderr, "[ipm host trace] loop enqueued %.1f ms (longest wait for a check %.1f ms at iteration %d, launch_parked %.1f ms), "
-                        "stream drained +%.1f ms, augmented-system tail +%.1f ms, %d handed off, %d launched inside the loop\n",
+                        "stream drained +%.1f ms, augmented-system tail +%.1f ms, %d handed off, %d of them started by the loop or its tail\n",
                 th_loop, th_wait_max, th_wait_it, th_parked, th_drain, th_ka, handed, ka_launched);
     if (iterations_run) *iterations_run = bodies;
     return IPM_OK;
