@@ -90,8 +90,8 @@ inline size_t kf_smem_bytes(int m, int n, int nbuf) {
 inline int kf_nbuf(int m, int n) { return kf_smem_bytes(m, n, KF_NBUF_MAX) <= KF_SMEM_CAP ? KF_NBUF_MAX : KF_NBUF_MAX - 1; }
 
 #ifdef __CUDACC__
-// One CTA per SM, 17 warps.  Thread 0 keeps four strips (4 x 32 KB) in flight with bulk copies (UBLKCP) from the
-// strip-major copy of A into a ring of six buffers, each with its own mbarrier.  Per strip s the 16 streaming
+// One CTA per SM, 17 warps.  Thread 0 keeps KF_NBUF - 2 strips (four of 32 KB at the benchmark shape) in flight with
+// bulk copies into a ring of KF_NBUF buffers (six when they fit, else five: kf_nbuf), each with its own mbarrier.  Per strip s the 16 streaming
 // warps form the column sums (-> part[s & 3], mbarrier pfull), warp E turns them into dx, ds and the row-sum
 // operand e (-> ev[s & 3], mbarrier efull) and the streaming warps add the row sums of strip s-2, so E's chain
 // of dependent FP64 operations (long latency on this part) is two strips off the critical path.
@@ -102,8 +102,8 @@ inline int kf_nbuf(int m, int n) { return kf_smem_bytes(m, n, KF_NBUF_MAX) <= KF
 // (box 16 columns x MR rows x 1 LP, cp.async.bulk.tensor -> UTMALDG; rows >= m and columns >= n are zero-filled by
 // the hardware), SRC = 0: from a strip-major copy of A made once per solve by kbf_repack (one untiled bulk copy per
 // strip, UBLKCP) - kept for A/B measurements, it costs a second copy of A in HBM and 4.4 ms per 8192 LPs.
-// PERSISTENT: one CTA per SM takes LPs from a work counter (a.kf_ctr) over the list of active LPs, so that (1) a lockstep iteration on a few hundred active LPs
-// does not start thousands of CTAs that only find a zero flag, and (2) the first KF_AHEAD strips of the NEXT LP are
+// PERSISTENT: one CTA per SM takes LPs from a work counter (a.kf_ctr) over the list of active LPs, so that (1) a
+// lockstep iteration on a few hundred active LPs does not start thousands of CTAs that only find a zero flag, and (2) the first KF_AHEAD strips of the NEXT LP are
 // requested during the last strips of the current one: the bulk copies are in flight across the epilogue (ratio
 // test, update, norms) and the next prologue, where a one-LP-per-CTA launch left HBM idle for 17 % of its time.
 // The ring position (buffer, mbarrier phases) simply continues from one LP to the next.
